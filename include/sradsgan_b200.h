@@ -1,0 +1,98 @@
+/*
+ * sradsgan_b200 — C ABI of the B200-native SRADSGAN hot path (libsradsgan_b200.so).
+ *
+ * The reference (Meng-333/SRADSGAN) is pure Python over torch ATen/cuDNN and has no FFI of its own
+ * (SURVEY.md §2); this header therefore DEFINES the boundary a reference maintainer would bind with
+ * ctypes.  Each entry point names the reference call sites whose arithmetic it
+ * replaces (paths relative to SRADSGAN/ in the reference tree).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the library never allocates, never
+ *     synchronises and launches only on the caller's stream (`stream` = cudaStream_t as void*),
+ *     so every call is CUDA-graph capturable;
+ *   - activations are NHWC ("channels_last"), dtype SR_F32 or SR_BF16; parameters/gradients exchanged
+ *     with the host framework stay in the reference's layout: OIHW fp32;
+ *   - return value 0 = ok, <0 = error, text via sr_last_error() (thread local);
+ *   - no CPU fallback: on a device that is not sm_100 every compute call fails with SR_ERR_ARCH.
+ */
+#ifndef SRADSGAN_B200_H
+#define SRADSGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_OK 0
+#define SR_ERR_ARG (-1)
+#define SR_ERR_CUDA (-2)
+#define SR_ERR_ARCH (-3)
+#define SR_ERR_UNSUPPORTED (-4)
+
+enum { SR_F32 = 0, SR_BF16 = 1 };
+enum { SR_ACT_NONE = 0, SR_ACT_LRELU = 1, SR_ACT_RELU = 2, SR_ACT_SIGMOID = 3 };
+enum { SR_IMPL_AUTO = 0, SR_IMPL_SIMT = 1, SR_IMPL_TCGEN05 = 2 };
+
+/* Geometry of one convolution y = act(conv(x, w) + bias) [+ residual] [-> PixelShuffle(r)].
+ * Replaces nn.Conv2d (+ nn.LeakyReLU / nn.ReLU / nn.PixelShuffle / `out += x`) at
+ * model/sradsgan.py:222-223,251-253,274 (RAB), :332-336 (MSB), :375,:381-386 (GAB_UP), :427,:448,
+ * :476-503 (Discriminator), :92-95 (VGG19[:12]). */
+typedef struct sr_conv_desc {
+    int32_t N, H, W, Cin;       /* input  NHWC */
+    int32_t Ho, Wo, Cout;       /* output NHWC, before the optional pixel shuffle */
+    int32_t kh, kw, stride, pad;
+    int32_t in_dtype, out_dtype;/* SR_F32 / SR_BF16 (weights are packed in in_dtype) */
+    int32_t act;                /* SR_ACT_* applied to conv+bias, before residual */
+    float   slope;              /* LeakyReLU negative slope */
+    int32_t shuffle_r;          /* 0/1: none; r>1: y is written as (N, Ho*r, Wo*r, Cout/r^2) */
+    int32_t impl;               /* SR_IMPL_* */
+} sr_conv_desc;
+
+const char* sr_last_error(void);
+int sr_version(void);
+/* 0 when the current device is sm_100 (B200) and the tcgen05/TMA paths are usable. */
+int sr_device_check(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t sr_launch_count(void);
+
+/* 1 when sr_conv2d_fwd (dgrad=0) / sr_conv2d_dgrad (dgrad=1) will run this geometry on the tcgen05 kernel,
+ * 0 when it takes the SIMT kernel (used by bench.py to attribute time per kernel). */
+int sr_conv_uses_tcgen05(const sr_conv_desc* d, int dgrad);
+
+/* OIHW fp32 master weights -> packed [kh*kw][Cout][Cin] (mode 0, forward/B-operand K-major) or
+ * [kh*kw][Cin][Cout] (mode 1, dgrad) in `dtype`.  shuffle_r > 1 (mode 0, convs followed by
+ * nn.PixelShuffle(r), model/sradsgan.py:381-386): rows are stored subpixel-major, row sub*(Cout/r^2)+c
+ * = output channel c*r^2+sub, which is what sr_conv2d_fwd expects when desc.shuffle_r > 1. */
+int sr_pack_weights(const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,
+                    int mode, int dtype, int shuffle_r, void* stream);
+
+/* y = act(conv(x,w)+bias) (+residual) ; w_packed from sr_pack_weights(mode 0); bias/residual may be NULL.
+ * residual has y's layout and dtype. */
+int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                  const void* residual, void* y, void* stream);
+/* dx = conv_transpose(dy, w) for the forward conv described by d (act/shuffle ignored).
+ * w_packed from sr_pack_weights(mode 1).  dy has dtype d->in_dtype, dx has d->out_dtype.
+ * (autograd of every nn.Conv2d above; reference: torch.autograd, model/sradsgan.py:857,886,621) */
+int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
+/* dw (OIHW fp32) (+)= sum_pixels dy (x) x ; dbias (fp32, may be NULL) (+)= sum_pixels dy.
+ * accumulate=0 overwrites (the library zero-fills first), 1 adds (tied upsampler weights, GP double
+ * backward).  x and dy have dtype d->in_dtype. */
+int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float* dw_oihw, float* dbias,
+                    int accumulate, void* stream);
+
+/* out[c] = sum over rows of x[rows][C] (fp32 accumulate); sq (may be NULL) = sum of squares.
+ * BatchNorm2d batch statistics (model/sradsgan.py:478) and bias gradients. */
+int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate,
+              void* stream);
+
+/* Fused Adam (torch.optim.Adam semantics, model/sradsgan.py:724-725,858,887) over a flat fp32 buffer,
+ * optionally followed by the WGAN weight clamp (model/sradsgan.py:891-892) when clamp_hi > clamp_lo. */
+int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                 float clamp_lo, float clamp_hi, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRADSGAN_B200_H */

@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE ONLY — torch-CPU emulation of each C-ABI entry point (include/sradsgan_b200.h).
+
+Two uses, both in tests/:
+  * on the GPU box: per-kernel checker (same packed operands in, compare outputs);
+  * in the CPU container: installed with sradsgan_b200._lib.set_backend() so that the host-side autograd
+    wiring (sradsgan_b200/ops.py, model/, trainer) can be checked against the oracle without a GPU.
+It follows the documented semantics of the ABI (packed weight layouts, subpixel-major PixelShuffle
+packing, epilogue order act -> residual), not the kernels' code.
+"""
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def unpack_weights(packed, mode, g_or_shape, shuffle_r=0):
+    """inverse of sr_pack_weights -> OIHW fp32"""
+    cout, cin, kh, kw = g_or_shape
+    p = packed.float()
+    if mode == 0:
+        w = p.reshape(kh, kw, cout, cin).permute(2, 3, 0, 1)
+        if shuffle_r and shuffle_r > 1:
+            r2 = shuffle_r * shuffle_r
+            cq = cout // r2
+            rows = torch.arange(cout)
+            orig = (rows % cq) * r2 + rows // cq          # packed row n' holds original channel orig[n']
+            w_full = torch.empty_like(w)
+            w_full[orig] = w
+            w = w_full
+    else:
+        w = p.reshape(kh, kw, cin, cout).permute(3, 2, 0, 1)
+    return w.contiguous()
+
+
+class EmuBackend:
+    name = "emu"
+
+    def __init__(self):
+        self.launches = 0
+
+    def launch_count(self):
+        return self.launches
+
+    def device_check(self):
+        return None
+
+    def pack_weights(self, w, mode, dtype, shuffle_r=0):
+        self.launches += 1
+        w = w.detach().float()
+        cout, cin, kh, kw = w.shape
+        if mode == 0:
+            if shuffle_r and shuffle_r > 1:
+                r2 = shuffle_r * shuffle_r
+                cq = cout // r2
+                rows = torch.arange(cout)
+                w = w[(rows % cq) * r2 + rows // cq]
+            out = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+        else:
+            out = w.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+        return out.contiguous().to(dtype)
+
+    def conv_fwd(self, x, w_packed, bias, residual, g, act=ACT_NONE, slope=0.0, shuffle_r=0, out_dtype=None, impl=0):
+        self.launches += 1
+        out_dtype = x.dtype if out_dtype is None else out_dtype
+        w = unpack_weights(w_packed, 0, (g.Cout, g.Cin, g.kh, g.kw), shuffle_r)
+        y = F.conv2d(x.float(), w, None if bias is None else bias.detach().float(), stride=g.stride, padding=g.pad)
+        if act == ACT_LRELU:
+            y = F.leaky_relu(y, slope)
+        elif act == ACT_RELU:
+            y = F.relu(y)
+        elif act == ACT_SIGMOID:
+            y = torch.sigmoid(y)
+        if shuffle_r and shuffle_r > 1:
+            y = F.pixel_shuffle(y, shuffle_r)
+        if residual is not None:
+            y = y + residual.float()
+        return y.to(out_dtype).contiguous(memory_format=torch.channels_last)
+
+    def conv_dgrad(self, dy, w_packed_t, g, out_dtype=None, impl=0):
+        self.launches += 1
+        out_dtype = dy.dtype if out_dtype is None else out_dtype
+        w = unpack_weights(w_packed_t, 1, (g.Cout, g.Cin, g.kh, g.kw))
+        dx = torch.nn.grad.conv2d_input((g.N, g.Cin, g.H, g.W), w, dy.float(), stride=g.stride, padding=g.pad)
+        return dx.to(out_dtype).contiguous(memory_format=torch.channels_last)
+
+    def conv_wgrad(self, x, dy, g, want_bias=True, impl=0):
+        self.launches += 1
+        dw = torch.nn.grad.conv2d_weight(x.float(), (g.Cout, g.Cin, g.kh, g.kw), dy.float(), stride=g.stride, padding=g.pad)
+        db = dy.float().sum(dim=(0, 2, 3)) if want_bias else None
+        return dw.contiguous(), db
+
+    def colsum(self, x2d, want_sq=False):
+        self.launches += 1
+        f = x2d.float()
+        return f.sum(0), (f * f).sum(0) if want_sq else None
+
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, clamp=None):
+        self.launches += 1
+        g = grad * grad_scale
+        exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1 = 1 - beta1 ** step
+        bc2 = 1 - beta2 ** step
+        denom = exp_avg_sq.sqrt() / (bc2 ** 0.5) + eps
+        param.addcdiv_(exp_avg, denom, value=-lr / bc1)
+        if clamp is not None and clamp[1] > clamp[0]:
+            param.clamp_(clamp[0], clamp[1])

@@ -1,0 +1,245 @@
+"""ctypes binding of libsradsgan_b200.so (C ABI declared in include/sradsgan_b200.h).
+
+The library is the ONLY compute path of this package: there is no CPU or eager-PyTorch fallback.  If the
+shared object is missing, or the device is not sm_100, every op raises RuntimeError.
+"""
+import ctypes
+import os
+from collections import namedtuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsradsgan_b200.so")
+
+SR_F32, SR_BF16 = 0, 1
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+
+EXPORTS = [
+    "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
+    "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
+]
+
+
+class ConvDesc(ctypes.Structure):
+    """struct sr_conv_desc"""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "kh", "kw", "stride", "pad", "in_dtype", "out_dtype", "act")]
+    _fields_ += [("slope", ctypes.c_float), ("shuffle_r", ctypes.c_int32), ("impl", ctypes.c_int32)]
+
+
+ConvGeom = namedtuple("ConvGeom", "N H W Cin Ho Wo Cout kh kw stride pad")
+
+
+def conv_geom(x_shape, w_shape, stride, pad):
+    n, cin, h, w = x_shape
+    cout, cin_w, kh, kw = w_shape
+    if cin != cin_w:
+        raise ValueError("conv: input has %d channels, weight expects %d" % (cin, cin_w))
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    return ConvGeom(n, h, w, cin, ho, wo, cout, kh, kw, stride, pad)
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared object (once). Raises RuntimeError with the build hint when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "sradsgan_b200: %s not found — build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no fallback compute path" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    lib.sr_last_error.restype = ctypes.c_char_p
+    lib.sr_last_error.argtypes = []
+    lib.sr_version.restype = i32
+    lib.sr_device_check.restype = i32
+    lib.sr_launch_count.restype = i64
+    lib.sr_conv_uses_tcgen05.argtypes = [ctypes.POINTER(ConvDesc), i32]
+    lib.sr_conv_uses_tcgen05.restype = i32
+    lib.sr_pack_weights.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.sr_conv2d_fwd.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]
+    lib.sr_conv2d_dgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp]
+    lib.sr_conv2d_wgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, i32, vp]
+    lib.sr_colsum.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp]
+    lib.sr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, f32, f32, vp]
+    for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
+        getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("sradsgan_b200.%s failed (%d): %s" % (what, rc, _lib.sr_last_error().decode()))
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return SR_F32
+    if t.dtype == torch.bfloat16:
+        return SR_BF16
+    raise TypeError("sradsgan_b200: unsupported dtype %s (float32 / bfloat16 only)" % t.dtype)
+
+
+def _tdtype(code):
+    return torch.float32 if code == SR_F32 else torch.bfloat16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _nhwc(t):
+    """(N,C,H,W)-shaped tensor with NHWC memory (torch channels_last)."""
+    if t.dim() != 4:
+        raise ValueError("expected a 4-d tensor")
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sradsgan_b200: tensors must live on a CUDA device (sm_100); there is no CPU path")
+
+
+class CudaBackend:
+    """Thin tensor-level wrapper over the C ABI. Every method launches on torch's current stream."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = load()
+        self.prof = None      # bench.py: list of (kernel class, flops, bytes, start event, end event)
+
+    def _timed(self, kind, d, dgrad, call):
+        """optional per-launch CUDA-event timing on the launching stream (bench.py roofline attribution)"""
+        if self.prof is None or torch.cuda.is_current_stream_capturing():
+            return call()
+        tc = self.lib.sr_conv_uses_tcgen05(ctypes.byref(d), 1 if dgrad else 0) if kind != "wgrad" else 0
+        m = d.N * d.Ho * d.Wo
+        flops = 2.0 * m * d.Cout * d.Cin * d.kh * d.kw
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = call()
+        e1.record()
+        self.prof.append(("conv_%s_%s" % (kind, "tcgen05" if tc else "simt"), flops, e0, e1))
+        return out
+
+    def launch_count(self):
+        return int(self.lib.sr_launch_count())
+
+    def device_check(self):
+        _check(self.lib.sr_device_check(), "device_check")
+
+    # -- weights -------------------------------------------------------------------------------
+    def pack_weights(self, w, mode, dtype, shuffle_r=0):
+        _require_cuda(w)
+        w = w.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        cout, cin, kh, kw = w.shape
+        out = torch.empty((kh * kw, cout, cin) if mode == 0 else (kh * kw, cin, cout), dtype=dtype, device=w.device)
+        _check(self.lib.sr_pack_weights(_ptr(w), _ptr(out), cout, cin, kh, kw, mode, _dt(out), int(shuffle_r), _stream()),
+               "pack_weights")
+        return out
+
+    # -- convolution ---------------------------------------------------------------------------
+    def _desc(self, g, in_dtype, out_dtype, act=ACT_NONE, slope=0.0, shuffle_r=0, impl=IMPL_AUTO):
+        return ConvDesc(g.N, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.kh, g.kw, g.stride, g.pad, in_dtype, out_dtype,
+                        act, float(slope), int(shuffle_r), int(impl))
+
+    def conv_fwd(self, x, w_packed, bias, residual, g, act=ACT_NONE, slope=0.0, shuffle_r=0, out_dtype=None, impl=IMPL_AUTO):
+        _require_cuda(x, w_packed)
+        x = _nhwc(x)
+        out_dtype = x.dtype if out_dtype is None else out_dtype
+        r = shuffle_r if shuffle_r and shuffle_r > 1 else 1
+        y = torch.empty((g.N, g.Cout // (r * r), g.Ho * r, g.Wo * r), dtype=out_dtype, device=x.device,
+                        memory_format=torch.channels_last)
+        if residual is not None:
+            residual = _nhwc(residual)
+            if residual.dtype != out_dtype or residual.shape != y.shape:
+                raise ValueError("conv_fwd: residual must match the output shape/dtype")
+        if bias is not None:
+            bias = bias.detach().float().contiguous()
+        if w_packed.dtype != x.dtype:
+            raise TypeError("conv_fwd: packed weights must have the activation dtype")
+        d = self._desc(g, _dt(x), _dt(y), act, slope, shuffle_r, impl)
+        self._timed("fwd", d, False, lambda: _check(
+            self.lib.sr_conv2d_fwd(ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(residual), _ptr(y), _stream()),
+            "conv2d_fwd"))
+        return y
+
+    def conv_dgrad(self, dy, w_packed_t, g, out_dtype=None, impl=IMPL_AUTO):
+        _require_cuda(dy, w_packed_t)
+        dy = _nhwc(dy)
+        out_dtype = dy.dtype if out_dtype is None else out_dtype
+        dx = torch.empty((g.N, g.Cin, g.H, g.W), dtype=out_dtype, device=dy.device, memory_format=torch.channels_last)
+        if w_packed_t.dtype != dy.dtype:
+            raise TypeError("conv_dgrad: packed weights must have the gradient dtype")
+        d = self._desc(g, _dt(dy), _dt(dx), impl=impl)
+        self._timed("dgrad", d, True, lambda: _check(
+            self.lib.sr_conv2d_dgrad(ctypes.byref(d), _ptr(dy), _ptr(w_packed_t), _ptr(dx), _stream()), "conv2d_dgrad"))
+        return dx
+
+    def conv_wgrad(self, x, dy, g, want_bias=True, impl=IMPL_AUTO):
+        _require_cuda(x, dy)
+        x = _nhwc(x)
+        dy = _nhwc(dy)
+        if x.dtype != dy.dtype:
+            dy = dy.to(x.dtype)
+        dw = torch.empty((g.Cout, g.Cin, g.kh, g.kw), dtype=torch.float32, device=x.device)
+        db = torch.empty((g.Cout,), dtype=torch.float32, device=x.device) if want_bias else None
+        d = self._desc(g, _dt(x), SR_F32, impl=impl)
+        self._timed("wgrad", d, False, lambda: _check(
+            self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 0, _stream()), "conv2d_wgrad"))
+        return dw, db
+
+    # -- reductions / optimiser ----------------------------------------------------------------
+    def colsum(self, x2d, want_sq=False):
+        _require_cuda(x2d)
+        x2d = x2d.contiguous()
+        rows, c = x2d.shape
+        s = torch.empty((c,), dtype=torch.float32, device=x2d.device)
+        q = torch.empty((c,), dtype=torch.float32, device=x2d.device) if want_sq else None
+        _check(self.lib.sr_colsum(_ptr(x2d), _dt(x2d), rows, c, _ptr(s), _ptr(q), 0, _stream()), "colsum")
+        return s, q
+
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, clamp=None):
+        _require_cuda(param, grad, exp_avg, exp_avg_sq)
+        for t in (param, grad, exp_avg, exp_avg_sq):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
+                raise ValueError("adam_step: flat contiguous fp32 buffers of equal length required")
+        lo, hi = (clamp if clamp is not None else (0.0, 0.0))
+        _check(self.lib.sr_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1,
+                                     beta2, eps, int(step), float(grad_scale), float(lo), float(hi), _stream()), "adam_step")
+
+
+_backend = None
+
+
+def backend():
+    """The process-wide compute backend. Tests may install an emulation with set_backend()."""
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(b):
+    """TEST HOOK: replace the backend (tests/ install oracle.ops_emu.EmuBackend to check the autograd
+    wiring on CPU). The product never calls this."""
+    global _backend
+    prev = _backend
+    _backend = b
+    return prev

@@ -1,0 +1,159 @@
+// extern "C" surface of libsradsgan_b200.so (see include/sradsgan_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace sr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return SR_ERR_CUDA;
+    }
+    return SR_OK;
+}
+
+// conv_simt.cu
+int conv_fwd_simt(const sr_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+int conv_dgrad_simt(const sr_conv_desc*, const void*, const void*, void*, cudaStream_t);
+int conv_wgrad_simt(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
+// conv_tc.cu
+bool conv_tc_supported(const sr_conv_desc*, bool dgrad);
+int conv_tc_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+// elementwise.cu
+int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
+int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, float, float, float, cudaStream_t);
+
+static int g_arch_ok = -1;
+static int arch_check() {
+    if (g_arch_ok < 0) {
+        int dev = 0, major = 0, minor = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return SR_ERR_CUDA; }
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+        g_arch_ok = (major == 10) ? 1 : 0;
+        if (!g_arch_ok) set_error("device is sm_%d%d; this library is built for sm_100a only", major, minor);
+    }
+    if (!g_arch_ok) {
+        set_error("device is not sm_100 (B200); no fallback path exists");
+        return SR_ERR_ARCH;
+    }
+    return SR_OK;
+}
+
+static int check_desc(const sr_conv_desc* d) {
+    SR_REQUIRE(d != nullptr, "conv desc is NULL");
+    SR_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: non-positive dims");
+    SR_REQUIRE(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->pad >= 0, "conv: bad kernel/stride/pad");
+    const int ho = (d->H + 2 * d->pad - d->kh) / d->stride + 1, wo = (d->W + 2 * d->pad - d->kw) / d->stride + 1;
+    SR_REQUIRE(ho == d->Ho && wo == d->Wo, "conv: Ho/Wo (%d,%d) inconsistent with geometry (%d,%d)", d->Ho, d->Wo, ho, wo);
+    SR_REQUIRE((d->in_dtype == SR_F32 || d->in_dtype == SR_BF16) && (d->out_dtype == SR_F32 || d->out_dtype == SR_BF16), "conv: bad dtype");
+    if (d->shuffle_r > 1) SR_REQUIRE(d->Cout % (d->shuffle_r * d->shuffle_r) == 0, "conv: Cout %% r^2 != 0");
+    return SR_OK;
+}
+
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" {
+
+const char* sr_last_error(void) { return g_err; }
+int sr_version(void) { return 100; }
+int sr_device_check(void) { return arch_check(); }
+int64_t sr_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sr_conv_uses_tcgen05(const sr_conv_desc* d, int dgrad) {
+    if (!d || d->impl == SR_IMPL_SIMT) return 0;
+    return conv_tc_supported(d, dgrad != 0) ? 1 : 0;
+}
+
+int sr_pack_weights(const float* w, void* packed, int Cout, int Cin, int kh, int kw, int mode, int dtype,
+                    int shuffle_r, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(w && packed && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "pack_weights: bad arguments");
+    SR_REQUIRE(mode == 0 || mode == 1, "pack_weights: mode must be 0 or 1");
+    SR_REQUIRE(dtype == SR_F32 || dtype == SR_BF16, "pack_weights: bad dtype");
+    SR_REQUIRE(shuffle_r <= 1 || (mode == 0 && Cout % (shuffle_r * shuffle_r) == 0), "pack_weights: bad shuffle_r");
+    return pack_weights(w, packed, Cout, Cin, kh, kw, mode, dtype, shuffle_r, (cudaStream_t)stream);
+}
+
+int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
+                  void* y, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    rc = check_desc(d);
+    if (rc) return rc;
+    SR_REQUIRE(x && w && y, "conv2d_fwd: NULL pointer");
+    const bool tc_ok = conv_tc_supported(d, false);
+    if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
+        set_error("conv2d_fwd: tcgen05 path does not support this shape (Cin=%d Cout=%d k=%d s=%d dtype=%d)", d->Cin, d->Cout, d->kh, d->stride, d->in_dtype);
+        return SR_ERR_UNSUPPORTED;
+    }
+    if (tc_ok && d->impl != SR_IMPL_SIMT) return conv_tc_run(d, false, x, w, bias, residual, y, (cudaStream_t)stream);
+    return conv_fwd_simt(d, x, w, bias, residual, y, (cudaStream_t)stream);
+}
+
+int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* wt, void* dx, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    rc = check_desc(d);
+    if (rc) return rc;
+    SR_REQUIRE(dy && wt && dx, "conv2d_dgrad: NULL pointer");
+    const bool tc_ok = conv_tc_supported(d, true);
+    if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
+        set_error("conv2d_dgrad: tcgen05 path does not support this shape");
+        return SR_ERR_UNSUPPORTED;
+    }
+    if (tc_ok && d->impl != SR_IMPL_SIMT) return conv_tc_run(d, true, dy, wt, nullptr, nullptr, dx, (cudaStream_t)stream);
+    return conv_dgrad_simt(d, dy, wt, dx, (cudaStream_t)stream);
+}
+
+int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, int accumulate,
+                    void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    rc = check_desc(d);
+    if (rc) return rc;
+    SR_REQUIRE(x && dy && dw, "conv2d_wgrad: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * d->kh * d->kw, st);
+    rc = conv_wgrad_simt(d, x, dy, dw, st);
+    if (rc) return rc;
+    if (dbias) rc = colsum(dy, d->in_dtype, (long long)d->N * d->Ho * d->Wo, d->Cout, dbias, nullptr, accumulate, st);
+    return rc;
+}
+
+int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && sum && C > 0 && rows >= 0, "colsum: bad arguments");
+    return colsum(x, dtype, rows, C, sum, sq, accumulate, (cudaStream_t)stream);
+}
+
+int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_scale, float clamp_lo, float clamp_hi, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam_step: bad arguments");
+    return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, clamp_lo, clamp_hi,
+                     (cudaStream_t)stream);
+}
+
+}  // extern "C"

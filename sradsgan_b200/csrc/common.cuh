@@ -1,0 +1,62 @@
+// Shared helpers for the sradsgan_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sradsgan_b200.h"
+
+namespace sr {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);   // cudaGetLastError -> SR_OK / SR_ERR_CUDA
+
+#define SR_REQUIRE(cond, ...)                \
+    do {                                     \
+        if (!(cond)) {                       \
+            sr::set_error(__VA_ARGS__);      \
+            return SR_ERR_ARG;               \
+        }                                    \
+    } while (0)
+
+__host__ __device__ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements -> float[4] (requires 4-element alignment of p)
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&o)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&o)[4]) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[4]) {
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&v.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v.y);
+    o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    switch (act) {
+        case SR_ACT_LRELU: return v > 0.f ? v : v * slope;
+        case SR_ACT_RELU: return v > 0.f ? v : 0.f;
+        case SR_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace sr

@@ -1,0 +1,108 @@
+// Bandwidth-bound helper kernels: weight packing, column reductions, fused Adam(+clamp).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace sr {
+
+// OIHW fp32 -> [tap][Cout][Cin] (mode 0) or [tap][Cin][Cout] (mode 1)
+// shuffle_r > 1 (mode 0 only): output rows are permuted subpixel-major, row n' = sub*(Cout/r^2) + c holds
+// original output channel c*r^2 + sub, so that PixelShuffle becomes a contiguous store per sub-pixel.
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int taps, int mode, int shuffle_r) {
+    const long long total = (long long)Cout * Cin * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // i indexes the OUTPUT (coalesced writes)
+        int tap, co, ci;
+        if (mode == 0) {
+            ci = (int)(i % Cin); long long q = i / Cin; co = (int)(q % Cout); tap = (int)(q / Cout);
+        } else {
+            co = (int)(i % Cout); long long q = i / Cout; ci = (int)(q % Cin); tap = (int)(q / Cin);
+        }
+        if (shuffle_r > 1) {
+            const int r2 = shuffle_r * shuffle_r, cq = Cout / r2;
+            const int sub = co / cq, c = co - sub * cq;
+            co = c * r2 + sub;
+        }
+        out[i] = from_f32<T>(w[((long long)co * Cin + ci) * taps + tap]);
+    }
+}
+
+// sum (and sum of squares) over rows of x[rows][C]; block = 32 channels x 8 row-lanes
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, long long rows, int C, float* __restrict__ sum, float* __restrict__ sq) {
+    __shared__ float s1[8][33], s2[8][33];
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + lane;
+    float a = 0.f, b = 0.f;
+    if (c < C) {
+        for (long long r = (long long)blockIdx.x * 8 + wy; r < rows; r += (long long)gridDim.x * 8) {
+            const float v = to_f32<T>(x[r * C + c]);
+            a += v;
+            b += v * v;
+        }
+    }
+    s1[wy][lane] = a; s2[wy][lane] = b;
+    __syncthreads();
+    if (wy == 0 && c < C) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { a += s1[i][lane]; b += s2[i][lane]; }
+        atomicAdd(sum + c, a);
+        if (sq) atomicAdd(sq + c, b);
+    }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                            float grad_scale, float lo, float hi) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        float pi = p[i] - (lr / bc1) * (mi / denom);
+        if (hi > lo) pi = fminf(fmaxf(pi, lo), hi);
+        p[i] = pi;
+    }
+}
+
+int pack_weights(const float* w, void* out, int Cout, int Cin, int kh, int kw, int mode, int dtype, int shuffle_r, cudaStream_t st) {
+    const long long total = (long long)Cout * Cin * kh * kw;
+    const int blocks = (int)std::min<long long>(148 * 8, (long long)cdiv(total, 256));
+    if (dtype == SR_F32) pack_weights_kernel<float><<<blocks, 256, 0, st>>>(w, (float*)out, Cout, Cin, kh * kw, mode, shuffle_r);
+    else pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)out, Cout, Cin, kh * kw, mode, shuffle_r);
+    count_launch();
+    return check_launch("pack_weights_kernel");
+}
+
+int colsum(const void* x, int dtype, long long rows, int C, float* sum, float* sq, int accumulate, cudaStream_t st) {
+    if (!accumulate) {
+        cudaMemsetAsync(sum, 0, sizeof(float) * C, st);
+        if (sq) cudaMemsetAsync(sq, 0, sizeof(float) * C, st);
+    }
+    if (rows <= 0) return SR_OK;
+    const int cy = (int)cdiv(C, 32);
+    long long bx = cdiv(148 * 8, cy);
+    if (bx > cdiv(rows, 8)) bx = cdiv(rows, 8);
+    dim3 grid((unsigned)bx, (unsigned)cy);
+    if (dtype == SR_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, C, sum, sq);
+    else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, rows, C, sum, sq);
+    count_launch();
+    return check_launch("colsum_kernel");
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+              int step, float grad_scale, float lo, float hi, cudaStream_t st) {
+    if (n <= 0) return SR_OK;
+    const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
+    const int blocks = (int)std::min<long long>(148 * 8, (long long)cdiv(n, 256));
+    adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale, lo, hi);
+    count_launch();
+    return check_launch("adam_kernel");
+}
+
+}  // namespace sr

@@ -1,0 +1,397 @@
+"""Trainer with the reference's entry points — `SRADSGAN(args).train()`, `.gradient_penalty()`,
+`.mfe_test_single()`, `.validate()`, `.mfeNew_validate()`, `.mfeNew_validateByClass()`, `save/load_*`
+(reference model/sradsgan.py:510-1640) — driving the B200-native networks.
+
+What is kept bit-for-bit in structure: loss_G = L1 + 1e-2*L1(VGG) + 1e-3*(-mean D(G(x)));
+loss_D = -mean D(hr) + mean D(G(x).detach()) + lambda*GP with the GP ALSO back-propagated once un-weighted
+(effective weight 1+lambda, reference :639 + :884-886); per-pixel GP norm over the 3 colour channels (:630);
+D always in train mode (4 BatchNorm stat updates per step); Adam(2e-4, .9, .999); clamp of every D
+parameter to +-clip_value (:891-892).
+What is deliberately not reproduced because it changes no result: D / VGG weight gradients during the G
+step (zeroed / never used, :865), the second traversal of the GP double-backward graph (the two
+backward passes are fused into one with weight 1+lambda), per-iteration `.item()` syncs and empty_cache().
+"""
+import math
+import os
+import time
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, dp, ops
+from ..optim import FlatAdam
+from ..utils import CsvLogger, psnr, save_img1, weights_init_normal
+
+
+class SRADSGAN(object):
+    def __init__(self, args):
+        # parameters (reference :513-556)
+        for k in ("model_name", "train_dataset", "test_dataset", "crop_size", "test_crop_size", "hr_height", "hr_width",
+                  "num_threads", "num_channels", "scale_factor", "epoch", "num_epochs", "save_epochs", "batch_size",
+                  "test_batch_size", "lr", "b1", "b2", "data_dir", "root_dir", "save_dir", "gpu_mode", "n_cpu",
+                  "sample_interval", "clip_value", "lambda_gp", "gp", "penalty_type", "grad_penalty_Lp_norm",
+                  "loss_Lp_norm", "weight_gan", "weight_content", "max_train_samples"):
+            setattr(self, k, getattr(args, k))
+        self.relative = args.relativeGan
+        # new flags (defaults keep the reference behaviour)
+        self.precision = getattr(args, "precision", "bf16")
+        self.synthetic_steps = getattr(args, "synthetic_steps", 0)
+        self.log_interval = getattr(args, "log_interval", 50)
+        self.vgg_state = getattr(args, "vgg_state", None)
+        self.seed = getattr(args, "seed", 0)
+        ops.set_precision(self.precision)
+        if self.relative:
+            raise NotImplementedError("relativistic GAN branch (reference :840-844) is unreachable from the CLI and not built")
+        self.cuda = torch.cuda.is_available()
+        if not self.cuda and _lib.backend().name == "cuda":
+            raise RuntimeError("sradsgan_b200 needs a CUDA (sm_100) device; there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu")
+        self.log_dict = OrderedDict()
+        self.logger = None
+        self.generator = self.discriminator = self.feature_extractor = None
+        self.optimizer_G = self.optimizer_D = None
+        self._alpha_override = None
+
+    # ------------------------------------------------------------------------------------------
+    # construction
+    # ------------------------------------------------------------------------------------------
+    def new_generator(self):
+        from .sradsgan import GeneratorResNet, ResGroup
+        return GeneratorResNet(ResGroup, n_residual_blocks=12, n_basic_blocks=3, rla_mode='CA-SA', bla_mode='CA-SA',
+                               ga_mode='CA-SA', pool_mode='Avg|Max', upscale_factor=self.scale_factor)   # :669-671
+
+    def build(self, init=True):
+        """networks, losses and optimisers (reference :669-725)"""
+        from .sradsgan import Discriminator, FeatureExtractor, GANLoss
+        torch.manual_seed(self.seed)
+        self.generator = self.new_generator()
+        self.discriminator = Discriminator()
+        vsd = torch.load(self.vgg_state, map_location="cpu") if isinstance(self.vgg_state, str) else self.vgg_state
+        self.feature_extractor = FeatureExtractor(state_dict=vsd)
+        self.criterion_raGAN = GANLoss(gan_type='wgan-gp', real_label_val=1.0, fake_label_val=0.0)
+        if init and self.epoch == 0:
+            self.generator.apply(weights_init_normal)        # :713-714
+            self.discriminator.apply(weights_init_normal)
+        for m in (self.generator, self.discriminator, self.feature_extractor):
+            m.to(self.device)
+        self._make_optimizers()
+
+    def _make_optimizers(self):
+        self.optimizer_G = FlatAdam(self.generator, lr=self.lr, betas=(self.b1, self.b2), chunk_of=dp.generator_chunk_key)
+        self.optimizer_D = FlatAdam(self.discriminator, lr=self.lr, betas=(self.b1, self.b2),
+                                    clamp=(-self.clip_value, self.clip_value))
+        dp.broadcast_parameters(self.optimizer_G)
+        dp.broadcast_parameters(self.optimizer_D)
+        self.reducer_G = dp.BucketReducer(self.optimizer_G, overlap=True)
+        self.reducer_D = dp.BucketReducer(self.optimizer_D, overlap=False)
+
+    def criterion_content(self, a, b):
+        d = a.float() - b.float()
+        return d.abs().mean() if self.loss_Lp_norm == "L1" else (d * d).mean()     # :685-688
+
+    # ------------------------------------------------------------------------------------------
+    # WGAN-GP (reference :595-641)
+    # ------------------------------------------------------------------------------------------
+    def _gp_graph(self, discriminator, real_samples, fake_samples, grad_penalty_Lp_norm, penalty_type):
+        b = real_samples.size(0)
+        if self._alpha_override is not None:
+            alpha = self._alpha_override.to(real_samples.device, torch.float32).view(b, 1, 1, 1)
+        else:
+            alpha = torch.from_numpy(np.random.random((b, 1, 1, 1))).float().to(real_samples.device)   # :609
+        interpolates = (alpha * real_samples + ((1 - alpha) * fake_samples)).requires_grad_(True)      # :611
+        d_interpolates = discriminator(interpolates)
+        grad_outputs = torch.ones_like(d_interpolates)
+        gradients = torch.autograd.grad(outputs=d_interpolates, inputs=interpolates, grad_outputs=grad_outputs,
+                                        create_graph=True, retain_graph=True, only_inputs=True)[0]     # :621
+        gradients = gradients.float()
+        if grad_penalty_Lp_norm == 'Linf':
+            grad_norm, _ = torch.max(torch.abs(gradients), 1)
+        elif grad_penalty_Lp_norm == 'L1':
+            grad_norm = gradients.norm(1, 1)
+        else:
+            grad_norm = gradients.norm(2, 1)                                                           # :630
+        constraint = (grad_norm - 1).pow(2) if penalty_type == 'LS' else torch.relu(grad_norm - 1)     # :632-635
+        return constraint.mean()
+
+    def gradient_penalty(self, discriminator, real_samples, fake_samples, grad_penalty_Lp_norm='L2', penalty_type='LS'):
+        """Same contract as the reference: back-propagates the un-weighted penalty itself and returns it."""
+        gp = self._gp_graph(discriminator, real_samples, fake_samples, grad_penalty_Lp_norm, penalty_type)
+        gp.backward(retain_graph=True)                                                                 # :639
+        return gp
+
+    # ------------------------------------------------------------------------------------------
+    # one iteration (reference :829-892)
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, imgs_lr, imgs_hr, fuse_gp_backward=True):
+        G, D, Fx = self.generator, self.discriminator, self.feature_extractor
+        # ---- generator ----
+        self.optimizer_G.zero_grad()
+        for p in self.optimizer_D.params:
+            p.requires_grad_(False)          # skip D's weight gradients in the G step (discarded by the reference, :865)
+        gen_hr = G(imgs_lr)                                                         # :832
+        pixel_loss_G = self.criterion_content(gen_hr, imgs_hr)                      # :834
+        gen_features = Fx(gen_hr)                                                   # :836
+        with torch.no_grad():
+            real_features = Fx(imgs_hr)                                             # :837
+        loss_content = self.criterion_content(gen_features, real_features)         # :838
+        loss_gan = self.criterion_raGAN(D(gen_hr), True)                            # :847-848
+        loss_G = pixel_loss_G + self.weight_content * loss_content + self.weight_gan * loss_gan   # :852
+        self.reducer_G.arm()
+        loss_G.backward()
+        scale = self.reducer_G.finish()
+        self.optimizer_G.step(grad_scale=scale)                                     # :857-858
+        for p in self.optimizer_D.params:
+            p.requires_grad_(True)
+        # ---- discriminator ----
+        self.optimizer_D.zero_grad()                                                # :865
+        gen_det = gen_hr.detach()
+        loss_real = self.criterion_raGAN(D(imgs_hr), True)                          # :876
+        loss_fake = self.criterion_raGAN(D(gen_det), False)                         # :877
+        loss_D = loss_real + loss_fake
+        if self.gp:
+            if fuse_gp_backward:
+                gp = self._gp_graph(D, imgs_hr, gen_det, self.grad_penalty_Lp_norm, self.penalty_type)
+                (loss_D + (1.0 + self.lambda_gp) * gp).backward()                   # == :639 followed by :886
+                loss_D = loss_D.detach() + self.lambda_gp * gp.detach()
+            else:
+                gp = self.gradient_penalty(D, imgs_hr, gen_det, self.grad_penalty_Lp_norm, self.penalty_type)
+                loss_D = loss_D + self.lambda_gp * gp                               # :884
+                loss_D.backward()                                                   # :886
+        else:
+            gp = torch.zeros((), device=imgs_hr.device)
+            loss_D.backward()
+        self.reducer_D.arm()
+        scale = self.reducer_D.finish()
+        self.optimizer_D.step(grad_scale=scale)                                     # :887 + clamp :891-892 (fused)
+        return {"loss_G": loss_G.detach(), "loss_D": loss_D.detach(), "pixel": pixel_loss_G.detach(),
+                "content": loss_content.detach(), "adv": loss_gan.detach(), "gp": gp.detach(), "gen_hr": gen_det}
+
+    # ------------------------------------------------------------------------------------------
+    # data
+    # ------------------------------------------------------------------------------------------
+    def load_dataset(self, dataset='train', max_samples=20000):
+        """reference :643-656. Folder datasets are outside the hot path: a synthetic source
+        is used when `synthetic_steps` > 0, otherwise a minimal PIL folder reader."""
+        from ..data import FolderSRDataset, SyntheticSRDataset
+        bs = self.batch_size if dataset == 'train' else self.test_batch_size
+        if self.synthetic_steps:
+            ds = SyntheticSRDataset(self.synthetic_steps * bs, self.crop_size, self.scale_factor, seed=1234 + _rank())
+        else:
+            names = self.train_dataset if dataset == 'train' else self.test_dataset
+            ds = FolderSRDataset(self.data_dir, names, self.crop_size, self.scale_factor, max_samples=max_samples)
+        return torch.utils.data.DataLoader(ds, num_workers=0 if self.synthetic_steps else self.num_threads, batch_size=bs,
+                                           shuffle=(dataset == 'train' and not self.synthetic_steps), drop_last=True,
+                                           pin_memory=True)
+
+    # ------------------------------------------------------------------------------------------
+    # training loop (reference :658-1056)
+    # ------------------------------------------------------------------------------------------
+    def train(self):
+        self.build()
+        model_dir = os.path.join(self.save_dir, 'model')
+        os.makedirs(model_dir, exist_ok=True)
+        if self.epoch != 0:                                                         # :705-710
+            self.load_epoch_network(model_dir + '/generator_param_epoch_%d.pkl' % self.epoch, self.generator, strict=True)
+            self.load_epoch_network(model_dir + '/discriminator_param_epoch_%d.pkl' % self.epoch, self.discriminator, strict=True)
+        self.logger = CsvLogger(os.path.join(self.save_dir, 'logs')) if _rank() == 0 else None
+        lr_sz = self.crop_size // self.scale_factor
+        input_lr = torch.empty(self.batch_size, self.num_channels, lr_sz, lr_sz, device=self.device)      # :739-741
+        input_hr = torch.empty(self.batch_size, self.num_channels, self.crop_size, self.crop_size, device=self.device)
+        dataloader = self.load_dataset('train', max_samples=self.max_train_samples)
+        print('Training is started.')
+        step, start_time = 0, time.time()
+        epoch = self.epoch
+        best = {"psnr": 0.0, "step": 0, "no_improve": 0}
+        avg_loss_G, avg_loss_D = [], []
+        while epoch < self.num_epochs and self.lr >= 0.00001:                       # :804
+            sum_G = torch.zeros((), device=self.device)
+            sum_D = torch.zeros((), device=self.device)
+            n_it = 0
+            for i, batch in enumerate(dataloader):
+                inp, target = batch[0], batch[1]
+                imgs_lr = input_lr.copy_(inp, non_blocking=True)                    # :821-823
+                imgs_hr = input_hr.copy_(target, non_blocking=True)
+                out = self.train_step(imgs_lr, imgs_hr)
+                sum_G += out["loss_G"]; sum_D += out["loss_D"]; n_it += 1
+                step += 1
+                if self.logger is not None and (step % self.log_interval == 0 or step == 1):
+                    lg, ld = out["loss_G"].item(), out["loss_D"].item()             # the only host sync, every N steps
+                    print("[Epoch %d/%d] [Batch %d/%d] [D loss: %f] [G loss: %f]" % (epoch, self.num_epochs, i, len(dataloader), ld, lg))
+                    self.logger.scalar_summary('loss_G', lg, step)
+                    self.logger.scalar_summary('loss_D', ld, step)
+                    if step % self.sample_interval == 0 or step == 1:
+                        self.logger.print_format_results('train', OrderedDict(
+                            model=self.model_name, epoch=epoch, iters=step, G_lr=self.optimizer_G.param_groups[0]['lr'],
+                            D_lr=self.optimizer_D.param_groups[0]['lr'], time=time.time() - start_time, G_loss=lg, D_loss=ld,
+                            srwgan_psnr=psnr(out["gen_hr"][0].float().cpu(), imgs_hr[0].cpu())))
+            avg_loss_G.append((sum_G / max(n_it, 1)).item())
+            avg_loss_D.append((sum_D / max(n_it, 1)).item())
+            val_psnr = self.validate(epoch=epoch, mode='train', save_img=((epoch + 1) % self.save_epochs == 0))[0]
+            if val_psnr > best["psnr"]:
+                best.update(psnr=val_psnr, step=epoch, no_improve=0)
+            else:
+                best["no_improve"] += 1
+            if _rank() == 0:
+                self.save_epoch_network(model_dir, self.generator, 'generator', epoch + 1)          # :1005-1008
+                self.save_epoch_network(model_dir, self.discriminator, 'discriminator', epoch + 1)
+            epoch += 1
+            if best["no_improve"] >= 5:                                              # :1011-1036 LR halving heuristic
+                self.load_epoch_network(model_dir + '/generator_param_epoch_%d.pkl' % (best["step"] + 1), self.generator)
+                for g in self.optimizer_G.param_groups:
+                    g["lr"] /= 2.0
+                if self.lr < 0.0001:
+                    for g in self.optimizer_D.param_groups:
+                        g["lr"] /= 2.0
+                self.lr /= 2.0
+                epoch = best["step"] + 1
+                best["no_improve"] = 0
+        print("Training is finished.")
+        if _rank() == 0:
+            self.save_model(epoch=None)                                              # :1056
+        return avg_loss_G, avg_loss_D
+
+    # ------------------------------------------------------------------------------------------
+    # evaluation / inference (reference :1058-1194, :1259-1640)
+    # ------------------------------------------------------------------------------------------
+    def _eval_loader(self):
+        try:
+            return self.load_dataset('test')
+        except (FileNotFoundError, OSError):
+            return None
+
+    @torch.no_grad()
+    def validate(self, epoch=0, mode='test', save_img=False):
+        """PSNR on the test set (SSIM / ERGAS / LPIPS need skimage/sewar/AlexNet weights, absent offline:
+        returned as 0). Returns (psnr, ssim, ergas, lpips) like the reference."""
+        if self.generator is None:
+            self.build(init=False)
+            self.load_model()
+        loader = self._eval_loader() if not self.synthetic_steps else None
+        if loader is None:
+            return 0.0, 0.0, 0.0, 0.0
+        self.generator.eval()
+        vals = []
+        for batch in loader:
+            rec = self.generator(batch[0].to(self.device)).float().cpu()
+            vals += [psnr(rec[j], batch[1][j]) for j in range(rec.shape[0])]
+        return (float(np.mean(vals)) if vals else 0.0), 0.0, 0.0, 0.0
+
+    def mfeNew_validate(self, epoch=100, modelpath=None):
+        self.build(init=False)
+        if modelpath is not None:
+            self.generator.load_state_dict(torch.load(modelpath, map_location=self.device), strict=False)   # :1270
+        return self.validate(epoch=epoch, mode='test')
+
+    def mfeNew_validateByClass(self, epoch=100, save_img=False, modelpath=None):
+        return self.mfeNew_validate(epoch=epoch, modelpath=modelpath)
+
+    def mfe_test_single(self, img_fn, modelpath=None, tile=None, overlap=16):
+        """reference :1603-1640: CenterCrop(test_crop_size) -> batch of `batch_size` identical copies ->
+        G -> save [0] as uint8 (truncation).  `tile` (new): run large inputs as overlapped LR tiles of that
+        size, which the reference cannot do because SGAM materialises an (HW)x(HW) attention."""
+        from PIL import Image
+        import torchvision.transforms as transforms
+        self.generator = self.new_generator()
+        if modelpath is not None:
+            self.generator.load_state_dict(torch.load(modelpath, map_location="cpu"), strict=False)   # :1612-1613
+        self.generator.to(self.device).eval()
+        img = transforms.Compose([transforms.CenterCrop(self.test_crop_size), transforms.ToTensor()])(Image.open(img_fn))
+        input_img = img.unsqueeze(0).expand(self.batch_size, -1, -1, -1).contiguous().to(self.device)   # :1628-1629
+        with torch.no_grad():
+            if tile:
+                recon = tiled_forward(self.generator, input_img[:1], self.scale_factor, tile, overlap)
+            else:
+                recon = self.generator(input_img)
+        img_name = img_fn.split("/")[-1]
+        out_path = os.path.join(self.save_dir, 'SR_SRADSGAN_%s' % img_name)
+        save_img1(recon[0].float().cpu(), self.save_dir, out_path)                   # :1637
+        return recon[0]
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoints (reference :1197-1256) — plain state_dicts, NCHW fp32, reference key names
+    # ------------------------------------------------------------------------------------------
+    def save_epoch_network(self, save_dir, network, network_label, iter_label):
+        os.makedirs(save_dir, exist_ok=True)
+        path = os.path.join(save_dir, '{}_param_epoch_{}.pkl'.format(network_label, iter_label))
+        torch.save({k: v.detach().cpu().clone() for k, v in network.state_dict().items()}, path)
+
+    def load_epoch_network(self, load_path, network, strict=True):
+        network.load_state_dict(torch.load(load_path, map_location=self.device), strict=strict)
+        ops.bump_weight_generation()
+        print('Trained model is loaded.')
+
+    def save_model(self, epoch=None):
+        model_dir = os.path.join(self.save_dir, 'model')
+        os.makedirs(model_dir, exist_ok=True)
+        suffix = '_param_epoch_%d.pkl' % epoch if epoch is not None else '_param.pkl'
+        torch.save({k: v.detach().cpu().clone() for k, v in self.generator.state_dict().items()}, model_dir + '/generator' + suffix)
+        torch.save({k: v.detach().cpu().clone() for k, v in self.discriminator.state_dict().items()}, model_dir + '/discriminator' + suffix)
+        print('Trained model is saved.')
+
+    def load_model(self):
+        name = os.path.join(self.save_dir, 'model') + '/generator_param.pkl'
+        if os.path.exists(name):
+            self.generator.load_state_dict(torch.load(name, map_location=self.device), strict=False)
+            ops.bump_weight_generation()
+            print('Trained model is loaded.')
+            return True
+        print('No model exists to load.')
+        return False
+
+    def load_epoch_model(self, epoch):
+        name = os.path.join(self.save_dir, 'model') + '/generator_param_epoch_%d.pkl' % epoch
+        if os.path.exists(name):
+            self.generator.load_state_dict(torch.load(name, map_location=self.device))
+            ops.bump_weight_generation()
+            print('Trained model is loaded.')
+            return True
+        print('No model exists to load.')
+        return False
+
+
+def _rank():
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def tile_starts(size, tile, overlap):
+    """start offsets of overlapped tiles covering [0, size)"""
+    if size <= tile:
+        return [0]
+    step = tile - overlap
+    starts = list(range(0, size - tile, step)) + [size - tile]
+    return sorted(set(starts))
+
+
+@torch.no_grad()
+def tiled_forward(generator, lr, scale, tile, overlap=16):
+    """Overlapped-tile inference (new): LR tiles of `tile`^2 with `overlap` LR pixels of
+    overlap, feathered (linear ramp) blending of the SR tiles.  Parity is defined per tile: each tile's
+    output equals the generator run on that tile alone."""
+    n, c, h, w = lr.shape
+    out = torch.zeros(n, c, h * scale, w * scale, device=lr.device, dtype=torch.float32)
+    wsum = torch.zeros(1, 1, h * scale, w * scale, device=lr.device, dtype=torch.float32)
+    for y0 in tile_starts(h, tile, overlap):
+        for x0 in tile_starts(w, tile, overlap):
+            th, tw = min(tile, h), min(tile, w)
+            sr = generator(lr[:, :, y0:y0 + th, x0:x0 + tw].contiguous()).float()
+            wy = _feather(th * scale, overlap * scale, y0 > 0, y0 + th < h, lr.device)
+            wx = _feather(tw * scale, overlap * scale, x0 > 0, x0 + tw < w, lr.device)
+            wgt = wy.view(1, 1, -1, 1) * wx.view(1, 1, 1, -1)
+            ys, xs = y0 * scale, x0 * scale
+            out[:, :, ys:ys + th * scale, xs:xs + tw * scale] += sr * wgt
+            wsum[:, :, ys:ys + th * scale, xs:xs + tw * scale] += wgt
+    return out / wsum
+
+
+def _feather(n, ramp, lo, hi, device):
+    w = torch.ones(n, device=device)
+    if ramp > 0:
+        r = (torch.arange(ramp, device=device, dtype=torch.float32) + 1) / (ramp + 1)
+        if lo:
+            w[:ramp] = r
+        if hi:
+            w[n - ramp:] = r.flip(0)
+    return w

@@ -1,0 +1,199 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels.
+
+The convolution trio (fwd / dgrad / wgrad) is closed under differentiation — each Function's backward is
+written with the other two — so `torch.autograd.grad(..., create_graph=True)` through the discriminator
+(the WGAN-GP penalty, reference model/sradsgan.py:621,639) works unchanged at the call site.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, IMPL_AUTO, conv_geom
+
+
+class Config:
+    """Process-wide numeric configuration of the hot path."""
+    compute_dtype = torch.bfloat16     # activations / MMA operands ("bf16 mode"); torch.float32 = "fp32 mode"
+    conv_impl = IMPL_AUTO              # SR_IMPL_* forced for every conv (tests)
+
+
+config = Config()
+
+
+def set_precision(mode):
+    """'bf16' (tcgen05 path, <=1e-2 per-layer) or 'fp32' (SIMT path, <=1e-4 per-layer)."""
+    config.compute_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[mode]
+
+
+# ----------------------------------------------------------------------------------------------
+# packed-weight cache: OIHW fp32 master -> packed compute-dtype operand, rebuilt when the master changes
+# ----------------------------------------------------------------------------------------------
+_generation = 0
+
+
+def bump_weight_generation():
+    """Called by the fused optimiser (it updates parameters through raw pointers)."""
+    global _generation
+    _generation += 1
+
+
+def _capturing(t):
+    return t.is_cuda and torch.cuda.is_current_stream_capturing()
+
+
+def packed(w, mode, dtype, shuffle_r=0):
+    """Packed operand for weight `w`. Cached ON the nn.Parameter object (never for temporaries such as the
+    double-backward cotangents, whose storage may be recycled), keyed by layout and validated by
+    (optimiser generation, tensor version, storage address)."""
+    if not isinstance(w, torch.nn.Parameter) or _capturing(w):
+        return _lib.backend().pack_weights(w, mode, dtype, shuffle_r)
+    cache = w.__dict__.setdefault("_sr_pack", {})
+    key = (mode, dtype, shuffle_r)
+    ver = (_generation, w._version, w.data_ptr())
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    p = _lib.backend().pack_weights(w, mode, dtype, shuffle_r)
+    cache[key] = (ver, p)
+    return p
+
+
+def to_compute(x):
+    """NCHW-shaped tensor in the compute dtype with NHWC memory."""
+    if x.dtype != config.compute_dtype:
+        x = x.to(config.compute_dtype)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+# ----------------------------------------------------------------------------------------------
+# differentiable-to-any-order convolution primitives
+# ----------------------------------------------------------------------------------------------
+class ConvFwd(Function):
+    """y = conv2d(x, w) + b   (x: NHWC compute dtype; w: OIHW fp32 master; b: fp32 or None)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad):
+        g = conv_geom(x.shape, w.shape, stride, pad)
+        ctx.g = g
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w)
+        return _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, impl=config.conv_impl)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        g = ctx.g
+        gy = gy.to(x.dtype)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgrad.apply(gy, w, g)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = ConvWgrad.apply(x, gy, g)
+            if not ctx.has_bias:
+                gb = None
+        return gx, gw, gb, None, None
+
+
+class ConvDgrad(Function):
+    """dx = conv_transpose2d(dy, w) for the forward geometry g (linear in dy and in w)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, g):
+        ctx.g = g
+        ctx.save_for_backward(gy, w)
+        return _lib.backend().conv_dgrad(gy, packed(w, 1, gy.dtype), g, impl=config.conv_impl)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gy, w = ctx.saved_tensors
+        g = ctx.g
+        ggx = ggx.to(gy.dtype)
+        d_gy = d_w = None
+        if ctx.needs_input_grad[0]:
+            d_gy = ConvFwd.apply(ggx, w, None, g.stride, g.pad)
+        if ctx.needs_input_grad[1]:
+            d_w, _ = ConvWgrad.apply(ggx, gy, g)
+        return d_gy, d_w, None
+
+
+class ConvWgrad(Function):
+    """(dw, db) = (sum_pix dy (x) x, sum_pix dy): OIHW fp32 (linear in x and in dy)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, g):
+        ctx.g = g
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x, gy)
+        dw, db = _lib.backend().conv_wgrad(x, gy, g, want_bias=True, impl=config.conv_impl)
+        return dw, db
+
+    @staticmethod
+    def backward(ctx, ggw, ggb):
+        x, gy = ctx.saved_tensors
+        g = ctx.g
+        d_x = d_gy = None
+        if ctx.needs_input_grad[0] and ggw is not None:
+            d_x = ConvDgrad.apply(gy, ggw, g)
+        if ctx.needs_input_grad[1]:
+            if ggw is not None:
+                d_gy = ConvFwd.apply(x, ggw, ggb, g.stride, g.pad)
+            elif ggb is not None:
+                d_gy = ggb.to(gy.dtype).view(1, -1, 1, 1).expand_as(gy)
+        return d_x, d_gy, None
+
+
+def conv2d(x, w, b=None, stride=1, pad=0):
+    """Plain convolution, differentiable to any order."""
+    return ConvFwd.apply(to_compute(x), w, b, stride, pad)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused first-order convolution: act(conv + bias) (+ residual) (-> PixelShuffle)
+# ----------------------------------------------------------------------------------------------
+class ConvFused(Function):
+    """y = PixelShuffle_r( act(conv(x,w)+b) ) + residual — one kernel forward; backward = act' mask,
+    unshuffle, dgrad, wgrad.  First-order only (generator / VGG path)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, residual, stride, pad, act, slope, shuffle_r, out_dtype):
+        g = conv_geom(x.shape, w.shape, stride, pad)
+        ctx.g, ctx.act, ctx.slope, ctx.r = g, act, slope, shuffle_r
+        ctx.has_bias, ctx.has_res = b is not None, residual is not None
+        if act != ACT_NONE and residual is not None:
+            raise NotImplementedError("ConvFused: activation together with a residual is not used by this model")
+        y = _lib.backend().conv_fwd(x, packed(w, 0, x.dtype, shuffle_r), b, residual, g, act, slope, shuffle_r,
+                                    out_dtype=out_dtype, impl=config.conv_impl)
+        # the activation derivative is recovered from the sign of the output (slope > 0), which is only
+        # possible when no residual was added on top
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        g = ctx.g
+        g_res = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        gpre = gy
+        if ctx.act == ACT_LRELU:
+            gpre = torch.where(y > 0, gy, gy * ctx.slope)
+        elif ctx.act == ACT_RELU:
+            gpre = torch.where(y > 0, gy, torch.zeros_like(gy))
+        if ctx.r and ctx.r > 1:
+            gpre = torch.nn.functional.pixel_unshuffle(gpre, ctx.r)
+        gpre = to_compute(gpre) if gpre.dtype != x.dtype else gpre.contiguous(memory_format=torch.channels_last)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _lib.backend().conv_dgrad(gpre, packed(w, 1, gpre.dtype), g, impl=config.conv_impl)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = _lib.backend().conv_wgrad(x, gpre, g, want_bias=ctx.has_bias, impl=config.conv_impl)
+        return gx, gw, gb, g_res, None, None, None, None, None, None
+
+
+def conv2d_fused(x, w, b=None, residual=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, shuffle_r=0, out_dtype=None):
+    x = to_compute(x)
+    if residual is not None:
+        od = out_dtype or x.dtype
+        residual = residual.to(od).contiguous(memory_format=torch.channels_last)
+    return ConvFused.apply(x, w, b, residual, stride, pad, act, slope, shuffle_r, out_dtype)

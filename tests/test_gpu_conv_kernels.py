@@ -1,0 +1,176 @@
+"""GPU: per-kernel parity of the convolution family through the C ABI (sradsgan_b200._lib.CudaBackend ->
+libsradsgan_b200.so) against torch CPU fp32 on the same (bf16-rounded) operands.
+
+Tolerances: fp32 SIMT path 1e-5 relative L2 (fp32 accumulate, different summation order);
+bf16 paths 4e-3 (one bf16 rounding of the output, 2^-9 = 2e-3, fp32 accumulation in both)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    from sradsgan_b200 import _lib
+    b = _lib.CudaBackend()
+    b.device_check()
+    return b
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _mk(n, cin, h, w, cout, k, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g).to(dtype)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    return x, wt, b
+
+
+def _ref_w(wt, dtype):
+    return wt.to(dtype).float()
+
+
+from sradsgan_b200._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, conv_geom)
+
+SIMT_CASES = [
+    # n, cin, h, w, cout, k, stride, pad
+    (2, 3, 20, 20, 64, 3, 1, 1),       # conv1 / MSB.conv1 / D.model.0 / VGG.0 (K5)
+    (2, 64, 18, 18, 3, 3, 1, 1),       # conv3 (K6)
+    (2, 2, 17, 19, 1, 7, 1, 3),        # SLAM 7x7 (K8)
+    (2, 3, 11, 11, 64, 1, 1, 0),       # MSB 1x1
+    (1, 64, 16, 16, 64, 3, 2, 1),      # D stride-2
+    (1, 64, 15, 15, 8, 1, 1, 0),       # SGAM q/k
+    (1, 512, 6, 6, 1, 3, 1, 1),        # D output conv
+    (1, 192, 9, 9, 64, 1, 1, 0),       # MSB.conv
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_simt_fwd_dgrad_wgrad(be, case, dtype):
+    n, cin, h, w, cout, k, s, p = case
+    x, wt, b = _mk(n, cin, h, w, cout, k, dtype, seed=cin + cout)
+    g = conv_geom(x.shape, wt.shape, s, p)
+    tol = 1e-5 if dtype == torch.float32 else 4e-3
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    wp = be.pack_weights(wt.cuda(), 0, dtype)
+    y = be.conv_fwd(xc, wp, b.cuda(), None, g, ACT_LRELU, 0.2, impl=IMPL_SIMT)
+    y_ref = F.leaky_relu(F.conv2d(x.float(), _ref_w(wt, dtype), b, stride=s, padding=p), 0.2)
+    assert y.shape == y_ref.shape and rel(y, y_ref) < tol
+    gy = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(1)).to(dtype)
+    gyc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, dtype), g, impl=IMPL_SIMT)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, _ref_w(wt, dtype), gy.float(), stride=s, padding=p)
+    assert rel(dx, dx_ref) < tol
+    dw, db = be.conv_wgrad(xc, gyc, g, impl=IMPL_SIMT)
+    dw_ref = torch.nn.grad.conv2d_weight(x.float(), wt.shape, gy.float(), stride=s, padding=p)
+    assert rel(dw, dw_ref) < max(tol, 2e-5) and rel(db, gy.float().sum((0, 2, 3))) < max(tol, 2e-5)
+
+
+def test_simt_residual_shuffle_fp32out(be):
+    n, cin, h, w, cout, k = 2, 64, 9, 9, 256, 3
+    x, wt, b = _mk(n, cin, h, w, cout, k, torch.bfloat16, seed=3)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = be.conv_fwd(xc, be.pack_weights(wt.cuda(), 0, torch.bfloat16, 2), b.cuda(), None, g, ACT_LRELU, 0.01, shuffle_r=2, impl=IMPL_SIMT)
+    y_ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1), 2), 0.01)
+    assert y.shape == y_ref.shape and rel(y, y_ref) < 4e-3
+    res = torch.randn(n, cout, h, w)
+    y2 = be.conv_fwd(xc, be.pack_weights(wt.cuda(), 0, torch.bfloat16), b.cuda(), res.cuda().contiguous(memory_format=torch.channels_last),
+                     g, out_dtype=torch.float32, impl=IMPL_SIMT)
+    assert rel(y2, F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1) + res) < 1e-5
+
+
+TC_CASES = [
+    # n, cin, h, w, cout, k, stride, pad   (x4 generator / D / VGG shapes, incl. non-tile-multiple maps)
+    (3, 64, 54, 54, 256, 3, 1, 1),     # K1  RAB.conv1
+    (3, 256, 54, 54, 64, 3, 1, 1),     # K2  RAB.conv2
+    (2, 64, 27, 27, 64, 1, 1, 0),      # K4  1x1
+    (1, 128, 14, 14, 128, 3, 1, 1),    # D / VGG mid layers, tiny map (196 pixels -> 2 tiles, ragged tail)
+    (1, 64, 24, 24, 576, 3, 1, 1),     # x3/x9 head, BLOCK_N = 192
+    (1, 64, 216, 216, 64, 3, 1, 1),    # 216^2 layers (VGG.2)
+    (2, 512, 7, 7, 512, 3, 1, 1),      # D.22-like, K = 4608
+    (1, 64, 5, 5, 64, 3, 1, 1),        # fewer pixels than one tile
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tcgen05_fwd_matches_cpu_and_simt(be, case):
+    n, cin, h, w, cout, k, s, p = case
+    x, wt, b = _mk(n, cin, h, w, cout, k, torch.bfloat16, seed=cin * 7 + cout)
+    g = conv_geom(x.shape, wt.shape, s, p)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    wp = be.pack_weights(wt.cuda(), 0, torch.bfloat16)
+    y = be.conv_fwd(xc, wp, b.cuda(), None, g, ACT_LRELU, 0.2, impl=IMPL_TCGEN05)
+    torch.cuda.synchronize()
+    y_ref = F.leaky_relu(F.conv2d(x.float(), wt.bfloat16().float(), b, stride=s, padding=p), 0.2)
+    assert y.shape == y_ref.shape
+    assert rel(y, y_ref) < 4e-3
+    y_simt = be.conv_fwd(xc, wp, b.cuda(), None, g, ACT_LRELU, 0.2, impl=IMPL_SIMT)
+    assert rel(y, y_simt) < 4e-3
+    # fp32 output + residual epilogue
+    res = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(2))
+    y2 = be.conv_fwd(xc, wp, b.cuda(), res.cuda().contiguous(memory_format=torch.channels_last), g, out_dtype=torch.float32,
+                     impl=IMPL_TCGEN05)
+    assert rel(y2, F.conv2d(x.float(), wt.bfloat16().float(), b, stride=s, padding=p) + res) < 2e-5
+
+
+@pytest.mark.parametrize("case", TC_CASES[:5])
+def test_tcgen05_dgrad(be, case):
+    n, cin, h, w, cout, k, s, p = case
+    x, wt, _ = _mk(n, cin, h, w, cout, k, torch.bfloat16, seed=cout)
+    g = conv_geom(x.shape, wt.shape, s, p)
+    gy = torch.randn(n, cout, g.Ho, g.Wo, generator=torch.Generator().manual_seed(4)).bfloat16()
+    gyc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, torch.bfloat16), g, impl=IMPL_TCGEN05)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, wt.bfloat16().float(), gy.float(), stride=s, padding=p)
+    assert rel(dx, dx_ref) < 4e-3
+
+
+@pytest.mark.parametrize("r,cout", [(2, 256), (3, 576)])
+def test_tcgen05_pixel_shuffle_epilogue(be, r, cout):
+    x, wt, b = _mk(2, 64, 12, 12, cout, 3, torch.bfloat16, seed=r)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = be.conv_fwd(xc, be.pack_weights(wt.cuda(), 0, torch.bfloat16, r), b.cuda(), None, g, ACT_LRELU, 0.01, shuffle_r=r,
+                    impl=IMPL_TCGEN05)
+    y_ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1), r), 0.01)
+    assert y.shape == y_ref.shape and rel(y, y_ref) < 4e-3
+
+
+@pytest.mark.parametrize("case", [(2, 64, 216, 216, 64, 3, 2, 1), (1, 128, 27, 27, 128, 3, 2, 1), (1, 256, 54, 54, 256, 3, 2, 1)])
+def test_tcgen05_stride2_fwd(be, case):
+    """Discriminator stride-2 blocks through the im2col TMA traversal stride."""
+    n, cin, h, w, cout, k, s, p = case
+    x, wt, b = _mk(n, cin, h, w, cout, k, torch.bfloat16, seed=11)
+    g = conv_geom(x.shape, wt.shape, s, p)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = be.conv_fwd(xc, be.pack_weights(wt.cuda(), 0, torch.bfloat16), b.cuda(), None, g, impl=IMPL_TCGEN05)
+    y_ref = F.conv2d(x.float(), wt.bfloat16().float(), b, stride=s, padding=p)
+    assert y.shape == y_ref.shape and rel(y, y_ref) < 4e-3
+
+
+def test_full_size_linearity_and_impl_agreement(be):
+    """BASELINE config shape (B=16, 64->256 @54^2): size-independent properties instead of a CPU oracle —
+    conv is linear in x (fp32-out epilogue), and the tcgen05 and SIMT paths agree."""
+    g_ = torch.Generator().manual_seed(0)
+    a = torch.randn(16, 64, 54, 54, generator=g_).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    b2 = torch.randn(16, 64, 54, 54, generator=g_).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(256, 64, 3, 3, generator=g_) / 24).cuda()
+    g = conv_geom(a.shape, wt.shape, 1, 1)
+    wp = be.pack_weights(wt, 0, torch.bfloat16)
+    ya = be.conv_fwd(a, wp, None, None, g, out_dtype=torch.float32, impl=IMPL_TCGEN05)
+    yb = be.conv_fwd(b2, wp, None, None, g, out_dtype=torch.float32, impl=IMPL_TCGEN05)
+    s = (a.float() + b2.float())
+    s_bf = s.bfloat16()
+    exact = (s_bf.float() == s).all().item()
+    ys = be.conv_fwd(s_bf, wp, None, None, g, out_dtype=torch.float32, impl=IMPL_TCGEN05)
+    if exact:
+        assert rel(ys, ya + yb) < 1e-5
+    y_simt = be.conv_fwd(a, wp, None, None, g, out_dtype=torch.float32, impl=IMPL_SIMT)
+    assert rel(ya, y_simt) < 1e-5

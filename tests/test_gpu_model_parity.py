@@ -1,0 +1,208 @@
+"""GPU: parity of the product path (modules -> autograd Functions -> C ABI -> CUDA kernels) against the
+CPU oracle on identical seeded inputs/weights, and against the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): per-layer relative L2 error <= 1e-4 in fp32 mode, <= 1e-2 in bf16
+mode; generator-output PSNR within 0.01 dB."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sradsgan_oracle as O
+from oracle.make_golden import GEN_CASES, summarize
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture()
+def precision(request):
+    from sradsgan_b200 import ops
+    prev = ops.config.compute_dtype
+    ops.set_precision(request.param)
+    yield request.param
+    ops.config.compute_dtype = prev
+
+
+def _tap_modules(G):
+    """module name -> oracle tap name"""
+    m = {"MSB": "MSB", "conv1": "conv1", "GAB_UP.ca": "GAB_UP.ca", "GAB_UP.sa": "GAB_UP.sa"}
+    for gi, grp in enumerate(G.res_groups):
+        m["res_groups.%d" % gi] = "res_groups.%d" % gi
+        for bi in range(len(grp.RG)):
+            m["res_groups.%d.RG.%d" % (gi, bi)] = "res_groups.%d.RG.%d" % (gi, bi)
+    return m
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"], indirect=True)
+@pytest.mark.parametrize("case", [c for c in GEN_CASES if c[0] != "g_x4_full"], ids=lambda c: c[0])
+def test_generator_per_layer_parity_and_golden(precision, golden, case):
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup
+    name, scale, ng, nb, batch, lrs, init = case
+    gold = golden[name]
+    sd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=gold["cfg"]["wseed"], init=init))
+    G = GeneratorResNet(ResGroup, n_residual_blocks=ng, n_basic_blocks=nb, upscale_factor=scale)
+    G.load_state_dict(sd, strict=True)
+    G.cuda()
+    lr, hr = O.synthetic_batch(batch, scale, lrs * scale, seed=gold["cfg"]["dseed"])
+    got = {}
+    hooks = []
+    names = _tap_modules(G)
+    for mname, mod in G.named_modules():
+        if mname in names:
+            hooks.append(mod.register_forward_hook(lambda m, i, o, k=names[mname]: got.__setitem__(k, o.detach().float().cpu())))
+    with torch.no_grad():
+        y = G(lr.cuda()).float().cpu()
+    for h in hooks:
+        h.remove()
+    taps = {}
+    with torch.no_grad():
+        y_ref = O.generator_forward(sd, lr, scale, ng, nb, taps)
+    tol = TOL[precision]
+    worst = max((rel(v, taps[k]), k) for k, v in got.items())
+    assert worst[0] < tol, "per-layer error %g at %s" % worst
+    assert rel(y, y_ref) < tol
+    assert rel(y, gold["out"]) < tol                                  # the reference's own output
+    assert abs(O.psnr(y, hr) - gold["psnr_vs_hr"]) < 0.01             # PSNR within 0.01 dB of the reference
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"], indirect=True)
+def test_generator_full_architecture_golden(precision, golden):
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup
+    name, scale, ng, nb, batch, lrs, init = [c for c in GEN_CASES if c[0] == "g_x4_full"][0]
+    gold = golden[name]
+    sd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=gold["cfg"]["wseed"], init=init))
+    G = GeneratorResNet(ResGroup, upscale_factor=scale)
+    G.load_state_dict(sd, strict=True)
+    G.cuda()
+    lr, hr = O.synthetic_batch(batch, scale, lrs * scale, seed=gold["cfg"]["dseed"])
+    with torch.no_grad():
+        y = G(lr.cuda()).float().cpu()
+    assert rel(y, gold["out"]) < (2e-4 if precision == "fp32" else 2e-2)     # 12 groups x 3 blocks deep
+    assert abs(O.psnr(y, hr) - gold["psnr_vs_hr"]) < 0.01
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"], indirect=True)
+def test_generator_backward_parity(precision):
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup
+    scale, ng, nb = 4, 2, 1
+    sd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=5, init="fan"))
+    G = GeneratorResNet(ResGroup, n_residual_blocks=ng, n_basic_blocks=nb, upscale_factor=scale)
+    G.load_state_dict(sd, strict=True)
+    G.cuda()
+    lr, hr = O.synthetic_batch(2, scale, 64, seed=9)
+    y = G(lr.cuda())
+    (y.float() - hr.cuda()).abs().mean().backward()
+    mine = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.tie_upsampling(mine)
+    (O.generator_forward(mine, lr, scale, ng, nb) - hr).abs().mean().backward()
+    # gradients of an L1 loss flip sign with the output's rounding: bf16 is checked at 5e-2, fp32 at 1e-3
+    tol = 1e-3 if precision == "fp32" else 5e-2
+    bad = [(rel(p.grad, mine[k].grad), k) for k, p in G.named_parameters() if k not in O.NOISE_GRAD_KEYS]
+    worst = max(bad)
+    assert worst[0] < tol, "gradient error %g at %s" % worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"], indirect=True)
+def test_discriminator_and_vgg_forward_golden(precision, golden):
+    from sradsgan_b200.model.sradsgan import Discriminator, FeatureExtractor
+    tol = TOL[precision]
+    sd = O.make_state(O.discriminator_spec(), seed=11, init="fan")
+    D = Discriminator()
+    D.load_state_dict(sd, strict=True)
+    D.cuda()
+    x = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        y = D(x.cuda()).float().cpu()
+    assert rel(y, golden["d_fwd"]["out"]) < 5 * tol      # 9 convs + 7 train-mode BatchNorms at batch 2
+    for k, v in golden["d_fwd"]["bn"].items():
+        got = D.state_dict()[k].cpu()
+        if v.dtype.is_floating_point:
+            assert rel(got, v) < 5 * tol, k
+        else:
+            assert int(got) == int(v)
+    vsd = O.make_state(O.vgg_spec(), seed=12, init="fan")
+    V = FeatureExtractor(state_dict=vsd).cuda()
+    xv = torch.rand(1, 3, 16, 16, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        f = V(xv.cuda()).float().cpu()
+    assert rel(f, golden["vgg"]["out"]) < tol
+
+
+def _args(**kw):
+    base = dict(model_name="SRADSGAN", train_dataset=[], test_dataset=[], crop_size=32, test_crop_size=32, hr_height=32,
+                hr_width=32, num_threads=0, num_channels=3, scale_factor=4, epoch=0, num_epochs=1, save_epochs=1,
+                batch_size=2, test_batch_size=1, lr=2e-4, b1=0.9, b2=0.999, data_dir="", root_dir="", save_dir="/tmp/sr_t",
+                gpu_mode=True, n_cpu=0, sample_interval=1000, clip_value=0.01, lambda_gp=10, gp=True, penalty_type="LS",
+                grad_penalty_Lp_norm="L2", relativeGan=False, loss_Lp_norm="L1", weight_gan=1e-3, weight_content=1e-2,
+                max_train_samples=10, precision="fp32")
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_two_training_iterations_vs_reference_golden(golden, prec):
+    """Full G+D iterations (L1 + VGG + WGAN-GP with double backward, fused Adam + clamp) on the GPU ==
+    the reference's recorded losses / parameters (fp32 mode tight, bf16 mode loose)."""
+    from sradsgan_b200 import ops
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup, SRADSGAN
+    gcfg = golden["train_steps"]["cfg"]
+    ng, nb, scale = gcfg["n_groups"], gcfg["n_blocks"], gcfg["scale"]
+    Gsd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=gcfg["gseed"], init="fan"))
+    Dsd = O.make_state(O.discriminator_spec(), seed=gcfg["dseed"], init="ref")
+    Vsd = O.make_state(O.vgg_spec(), seed=gcfg["vseed"], init="fan")
+    prev = ops.config.compute_dtype
+    try:
+        net = SRADSGAN(_args(vgg_state=Vsd, precision=prec))
+        net.new_generator = lambda: GeneratorResNet(ResGroup, n_residual_blocks=ng, n_basic_blocks=nb, upscale_factor=scale)
+        net.build(init=False)
+        net.generator.load_state_dict(Gsd, strict=True)
+        net.discriminator.load_state_dict(Dsd, strict=True)
+        ops.bump_weight_generation()
+        ltol = 5e-4 if prec == "fp32" else 3e-2
+        for it, want in enumerate(golden["train_steps"]["steps"]):
+            lr, hr = O.synthetic_batch(gcfg["batch"], scale, gcfg["lr_size"] * scale, seed=gcfg["data_seed"] + it)
+            np.random.seed(gcfg["np_seed"] + it)
+            net._alpha_override = torch.Tensor(np.random.random((gcfg["batch"], 1, 1, 1)))
+            out = net.train_step(lr.cuda(), hr.cuda())
+            for k in ("loss_G", "loss_D", "pixel", "content", "adv", "gp"):
+                assert abs(out[k].item() - want[k]) <= ltol * max(1.0, abs(want[k])), (it, k, out[k].item(), want[k])
+            if prec == "fp32":
+                gsd = net.generator.state_dict()
+                for k, w in want["G_params"].items():
+                    if k not in O.NOISE_GRAD_KEYS:
+                        assert abs(summarize(gsd[k].cpu(), 8)["norm"] - w["norm"]) <= 5e-4 * max(1e-6, w["norm"]), (it, k)
+                dsd = net.discriminator.state_dict()
+                for k, w in want["D_state"].items():
+                    if k not in O.NOISE_GRAD_KEYS:
+                        assert abs(summarize(dsd[k].float().cpu(), 8)["norm"] - w["norm"]) <= 3e-3 * max(1e-6, w["norm"]), (it, k)
+    finally:
+        ops.config.compute_dtype = prev
+
+
+def test_tiled_inference_matches_per_tile_generator():
+    """x9 overlapped tiling (new functionality): every tile equals the generator run on that tile alone,
+    and a single tile covering the image reproduces the un-tiled output."""
+    from sradsgan_b200 import ops
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup
+    from sradsgan_b200.model.trainer import tiled_forward
+    scale, ng, nb = 9, 1, 1
+    sd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=4, init="fan"))
+    G = GeneratorResNet(ResGroup, n_residual_blocks=ng, n_basic_blocks=nb, upscale_factor=scale)
+    G.load_state_dict(sd, strict=True)
+    G.cuda().eval()
+    x = torch.rand(1, 3, 20, 20, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        whole = G(x).float()
+        assert rel(tiled_forward(G, x, scale, tile=20, overlap=4), whole) < 1e-6
+        t = tiled_forward(G, x, scale, tile=12, overlap=4)
+        assert t.shape == whole.shape and torch.isfinite(t).all()
+        corner = G(x[:, :, :12, :12].contiguous()).float()
+        assert rel(t[:, :, :8 * scale, :8 * scale], corner[:, :, :8 * scale, :8 * scale]) < 1e-6   # un-blended region
