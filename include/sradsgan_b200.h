@@ -56,9 +56,9 @@ int sr_device_check(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t sr_launch_count(void);
 
-/* 1 when sr_conv2d_fwd (dgrad=0) / sr_conv2d_dgrad (dgrad=1) will run this geometry on the tcgen05 kernel,
- * 0 when it takes the SIMT kernel (used by bench.py to attribute time per kernel). */
-int sr_conv_uses_tcgen05(const sr_conv_desc* d, int dgrad);
+/* 1 when sr_conv2d_fwd (kind 0) / sr_conv2d_dgrad (kind 1) / sr_conv2d_wgrad (kind 2) will run this
+ * geometry on a tcgen05 kernel, 0 when it takes the SIMT kernel (bench.py attributes time per kernel). */
+int sr_conv_uses_tcgen05(const sr_conv_desc* d, int kind);
 
 /* OIHW fp32 master weights -> packed [kh*kw][Cout][Cin] (mode 0, forward/B-operand K-major) or
  * [kh*kw][Cin][Cout] (mode 1, dgrad) in `dtype`.  shuffle_r > 1 (mode 0, convs followed by

@@ -126,7 +126,7 @@ class CudaBackend:
         """optional per-launch CUDA-event timing on the launching stream (bench.py roofline attribution)"""
         if self.prof is None or torch.cuda.is_current_stream_capturing():
             return call()
-        tc = self.lib.sr_conv_uses_tcgen05(ctypes.byref(d), 1 if dgrad else 0) if kind != "wgrad" else 0
+        tc = self.lib.sr_conv_uses_tcgen05(ctypes.byref(d), {"fwd": 0, "dgrad": 1, "wgrad": 2}[kind])
         m = d.N * d.Ho * d.Wo
         flops = 2.0 * m * d.Cout * d.Cin * d.kh * d.kw
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

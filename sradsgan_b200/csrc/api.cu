@@ -34,6 +34,9 @@ int conv_wgrad_simt(const sr_conv_desc*, const void*, const void*, float*, cudaS
 // conv_tc.cu
 bool conv_tc_supported(const sr_conv_desc*, bool dgrad);
 int conv_tc_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+// conv_tc_wgrad.cu
+bool conv_tc_wgrad_supported(const sr_conv_desc*);
+int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
 // elementwise.cu
 int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
@@ -78,9 +81,10 @@ int sr_version(void) { return 100; }
 int sr_device_check(void) { return arch_check(); }
 int64_t sr_launch_count(void) { return (int64_t)g_launches.load(); }
 
-int sr_conv_uses_tcgen05(const sr_conv_desc* d, int dgrad) {
+int sr_conv_uses_tcgen05(const sr_conv_desc* d, int kind) {
     if (!d || d->impl == SR_IMPL_SIMT) return 0;
-    return conv_tc_supported(d, dgrad != 0) ? 1 : 0;
+    if (kind == 2) return conv_tc_wgrad_supported(d) ? 1 : 0;
+    return conv_tc_supported(d, kind == 1) ? 1 : 0;
 }
 
 int sr_pack_weights(const float* w, void* packed, int Cout, int Cin, int kh, int kw, int mode, int dtype,
@@ -134,7 +138,13 @@ int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float*
     SR_REQUIRE(x && dy && dw, "conv2d_wgrad: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * d->kh * d->kw, st);
-    rc = conv_wgrad_simt(d, x, dy, dw, st);
+    const bool tc_ok = conv_tc_wgrad_supported(d);
+    if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
+        set_error("conv2d_wgrad: tcgen05 path does not support this shape");
+        return SR_ERR_UNSUPPORTED;
+    }
+    if (tc_ok && d->impl != SR_IMPL_SIMT) rc = conv_tc_wgrad_run(d, x, dy, dw, st);
+    else rc = conv_wgrad_simt(d, x, dy, dw, st);
     if (rc) return rc;
     if (dbias) rc = colsum(dy, d->in_dtype, (long long)d->N * d->Ho * d->Wo, d->Cout, dbias, nullptr, accumulate, st);
     return rc;

@@ -195,20 +195,24 @@ def _la_init(mod, planes, la_mode, pool_mode, addconv):
 
 def _la_forward(mod, out, x):
     """local-attention tail shared by RAB (:254-274) and ResGroup (:303-323), ending with `out += x`
-    (fused into the closing 1x1 conv as a residual epilogue when there is one)."""
+    (fused into the closing 1x1 conv as a residual epilogue when there is one).  The residual stream `x`
+    and the block output stay in fp32: only the branch runs in the compute dtype, so rounding errors do not
+    compound along the 36-block trunk (SURVEY.md "bf16 error budget")."""
     m = mod.la_mode
+    x = x.float()
+    f32 = torch.float32
     if m == 'CA':
-        return mod.ca(out) + x
+        return mod.ca(out).float() + x
     if m == 'SA':
-        return mod.sa(out) + x
+        return mod.sa(out).float() + x
     if m in ('CA-SA', 'SA-CA'):
         out = mod.sa(mod.ca(out)) if m == 'CA-SA' else mod.ca(mod.sa(out))
-        return mod.conv.fused(out, residual=x) if mod.addconv else out + x
+        return mod.conv.fused(out, residual=x, out_dtype=f32) if mod.addconv else out.float() + x
     if m == 'CA|SA':
-        return mod.conv.fused(torch.cat([mod.ca(out), mod.sa(out)], dim=1), residual=x)
+        return mod.conv.fused(torch.cat([mod.ca(out), mod.sa(out)], dim=1), residual=x, out_dtype=f32)
     if m == '':
-        return mod.last_conv.fused(out, residual=x)
-    return out + x
+        return mod.last_conv.fused(out, residual=x, out_dtype=f32)
+    return out.float() + x
 
 
 class RAB(nn.Module):
@@ -228,15 +232,15 @@ class RAB(nn.Module):
             self.act = nn.Tanh() if act_type == 'tanh' else nn.Sigmoid()
 
     def forward(self, x):
-        x = ops.to_compute(x)
+        xc = ops.to_compute(x)
         if self.act_type == 'lrelu':
-            out = self.conv1.fused(x, ACT_LRELU, 0.2)
+            out = self.conv1.fused(xc, ACT_LRELU, 0.2)
         elif self.act_type == 'relu':
-            out = self.conv1.fused(x, ACT_RELU)
+            out = self.conv1.fused(xc, ACT_RELU)
         elif self.act_type in ('prelu', 'tanh', 'sigmoid'):
-            out = self.act(self.conv1.fused(x).float()).to(x.dtype)
+            out = self.act(self.conv1.fused(xc).float()).to(xc.dtype)
         else:
-            out = self.conv1.fused(x)
+            out = self.conv1.fused(xc)
         out = self.conv2.fused(out)
         return _la_forward(self, out, x)
 
@@ -254,8 +258,7 @@ class ResGroup(nn.Module):
         _la_init(self, nc, rla_mode, pool_mode, addconv)
 
     def forward(self, x):
-        x = ops.to_compute(x)
-        return _la_forward(self, self.RG(x), x)
+        return _la_forward(self, ops.to_compute(self.RG(x)), x)
 
 
 class MSB(nn.Module):
@@ -275,7 +278,8 @@ class MSB(nn.Module):
         out1 = self.conv1.fused(x)
         out2 = self.conv2[1].fused(self.conv2[0].fused(x))
         out3 = self.conv3.fused(x)
-        return self.conv.fused(torch.cat([out1, out2, out3], dim=1), ACT_LRELU, self.lrelu.negative_slope)
+        return self.conv.fused(torch.cat([out1, out2, out3], dim=1), ACT_LRELU, self.lrelu.negative_slope,
+                               out_dtype=torch.float32)
 
 
 class ACB(nn.Module):
@@ -350,11 +354,11 @@ class GeneratorResNet(nn.Module):
     def forward(self, x):
         x = ops.to_compute(x)
         msb = self.MSB(x)
-        out = self.conv1[0].fused(x, ACT_LRELU, self.conv1[1].negative_slope)
-        out_all = msb.float() + out.float()
+        out = self.conv1[0].fused(x, ACT_LRELU, self.conv1[1].negative_slope, out_dtype=torch.float32)
+        out_all = msb.float() + out
         for res_group in self.res_groups:
-            y = res_group(out)
-            out_all = out_all + y.float()
+            y = res_group(out)            # fp32 residual stream
+            out_all = out_all + y
             out = y
         out_all = self.GAB_UP(out_all)
         return self.conv3[0].fused(out_all, out_dtype=torch.float32)

@@ -120,7 +120,8 @@ def test_tcgen05_fwd_matches_cpu_and_simt(be, case):
     assert rel(y2, F.conv2d(x.float(), wt.bfloat16().float(), b, stride=s, padding=p) + res) < 2e-5
 
 
-@pytest.mark.parametrize("case", TC_CASES[:5])
+@pytest.mark.parametrize("case", TC_CASES[:5] + [(1, 64, 216, 216, 64, 3, 2, 1), (2, 128, 27, 27, 128, 3, 2, 1),
+                                                 (1, 256, 54, 54, 256, 3, 2, 1), (1, 512, 14, 14, 512, 3, 2, 1)])
 def test_tcgen05_dgrad(be, case):
     n, cin, h, w, cout, k, s, p = case
     x, wt, _ = _mk(n, cin, h, w, cout, k, torch.bfloat16, seed=cout)
@@ -130,6 +131,27 @@ def test_tcgen05_dgrad(be, case):
     dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, torch.bfloat16), g, impl=IMPL_TCGEN05)
     dx_ref = torch.nn.grad.conv2d_input(x.shape, wt.bfloat16().float(), gy.float(), stride=s, padding=p)
     assert rel(dx, dx_ref) < 4e-3
+
+
+WGRAD_CASES = TC_CASES + [(2, 64, 216, 216, 64, 3, 2, 1), (1, 256, 54, 54, 256, 3, 2, 1), (2, 128, 27, 27, 256, 3, 1, 1),
+                         (1, 64, 30, 30, 64, 1, 1, 0)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_tcgen05_wgrad(be, case):
+    """MN-major tcgen05 weight gradient (split-K over pixels, fp32 atomics into OIHW) vs torch CPU."""
+    n, cin, h, w, cout, k, s, p = case
+    x, wt, _ = _mk(n, cin, h, w, cout, k, torch.bfloat16, seed=cin + 3 * cout)
+    g = conv_geom(x.shape, wt.shape, s, p)
+    gy = (torch.randn(n, cout, g.Ho, g.Wo, generator=torch.Generator().manual_seed(8)) * 0.1).bfloat16()
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    gyc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    dw, db = be.conv_wgrad(xc, gyc, g, impl=IMPL_TCGEN05)
+    dw_ref = torch.nn.grad.conv2d_weight(x.float(), wt.shape, gy.float(), stride=s, padding=p)
+    assert rel(dw, dw_ref) < 2e-5        # bf16 operands are exact products; fp32 accumulation both sides
+    assert rel(db, gy.float().sum((0, 2, 3))) < 2e-5
+    dw2, _ = be.conv_wgrad(xc, gyc, g, impl=IMPL_SIMT)
+    assert rel(dw, dw2) < 2e-5
 
 
 @pytest.mark.parametrize("r,cout", [(2, 256), (3, 576)])
