@@ -87,10 +87,12 @@ int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* 
               void* stream);
 
 /* Fused Adam (torch.optim.Adam semantics, model/sradsgan.py:724-725,858,887) over a flat fp32 buffer,
- * optionally followed by the WGAN weight clamp (model/sradsgan.py:891-892) when clamp_hi > clamp_lo. */
+ * optionally followed by the WGAN weight clamp (model/sradsgan.py:891-892) when clamp_hi > clamp_lo.
+ * The bias-correction step count is `step` (host, >= 1) or, when step_dev != NULL, the int32 read from
+ * device memory at execution time (so a captured CUDA graph can be replayed step after step). */
 int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                 float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                 float clamp_lo, float clamp_hi, void* stream);
+                 float lr, float beta1, float beta2, float eps, int step, const int32_t* step_dev,
+                 float grad_scale, float clamp_lo, float clamp_hi, void* stream);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,7 @@ GEN_CASES = [
     ("g_x9_small", 9, 1, 1, 1, 5, "fan"),
     ("g_x4_refinit", 4, 2, 1, 1, 12, "ref"),
     ("g_x4_full", 4, 12, 3, 1, 16, "fan"),
+    ("g_x4_full_refinit", 4, 12, 3, 1, 16, "ref"),     # the init train() really applies (utils.py:97-114)
 ]
 
 

@@ -94,8 +94,11 @@ class EmuBackend:
         f = x2d.float()
         return f.sum(0), (f * f).sum(0) if want_sq else None
 
-    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, clamp=None):
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, clamp=None,
+                  step_tensor=None):
         self.launches += 1
+        if step_tensor is not None:
+            step = int(step_tensor.item())
         g = grad * grad_scale
         exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
         exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)

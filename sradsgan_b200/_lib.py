@@ -68,7 +68,7 @@ def load():
     lib.sr_conv2d_dgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp]
     lib.sr_conv2d_wgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, i32, vp]
     lib.sr_colsum.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp]
-    lib.sr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, f32, f32, vp]
+    lib.sr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, f32, f32, vp]
     for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -215,14 +215,16 @@ class CudaBackend:
         _check(self.lib.sr_colsum(_ptr(x2d), _dt(x2d), rows, c, _ptr(s), _ptr(q), 0, _stream()), "colsum")
         return s, q
 
-    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, clamp=None):
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, clamp=None,
+                  step_tensor=None):
         _require_cuda(param, grad, exp_avg, exp_avg_sq)
         for t in (param, grad, exp_avg, exp_avg_sq):
             if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
                 raise ValueError("adam_step: flat contiguous fp32 buffers of equal length required")
         lo, hi = (clamp if clamp is not None else (0.0, 0.0))
         _check(self.lib.sr_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1,
-                                     beta2, eps, int(step), float(grad_scale), float(lo), float(hi), _stream()), "adam_step")
+                                     beta2, eps, int(step), _ptr(step_tensor), float(grad_scale), float(lo), float(hi),
+                                     _stream()), "adam_step")
 
 
 _backend = None

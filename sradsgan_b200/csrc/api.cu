@@ -40,7 +40,7 @@ int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cud
 // elementwise.cu
 int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
-int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, float, float, float, cudaStream_t);
+int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, const int*, float, float, float, cudaStream_t);
 
 static int g_arch_ok = -1;
 static int arch_check() {
@@ -158,12 +158,13 @@ int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* 
 }
 
 int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                 float beta2, float eps, int step, float grad_scale, float clamp_lo, float clamp_hi, void* stream) {
+                 float beta2, float eps, int step, const int32_t* step_dev, float grad_scale, float clamp_lo, float clamp_hi,
+                 void* stream) {
     int rc = arch_check();
     if (rc) return rc;
-    SR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam_step: bad arguments");
-    return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, clamp_lo, clamp_hi,
-                     (cudaStream_t)stream);
+    SR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
+    return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step < 1 ? 1 : step, step_dev, grad_scale,
+                     clamp_lo, clamp_hi, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -56,7 +56,12 @@ colsum_kernel(const T* __restrict__ x, long long rows, int C, float* __restrict_
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                            float grad_scale, float lo, float hi) {
+                            const int* __restrict__ step_dev, float grad_scale, float lo, float hi) {
+    if (step_dev) {   // CUDA-graph replay: the step counter lives on the device
+        const float t = (float)(*step_dev);
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -95,12 +100,12 @@ int colsum(const void* x, int dtype, long long rows, int C, float* sum, float* s
 }
 
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-              int step, float grad_scale, float lo, float hi, cudaStream_t st) {
+              int step, const int* step_dev, float grad_scale, float lo, float hi, cudaStream_t st) {
     if (n <= 0) return SR_OK;
     const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
     const int blocks = (int)std::min<long long>(148 * 8, (long long)cdiv(n, 256));
-    adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale, lo, hi);
+    adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, step_dev, grad_scale, lo, hi);
     count_launch();
     return check_launch("adam_kernel");
 }

@@ -53,6 +53,7 @@ class SRADSGAN(object):
         self.generator = self.discriminator = self.feature_extractor = None
         self.optimizer_G = self.optimizer_D = None
         self._alpha_override = None
+        self._graph = None
 
     # ------------------------------------------------------------------------------------------
     # construction
@@ -167,6 +168,63 @@ class SRADSGAN(object):
         self.optimizer_D.step(grad_scale=scale)                                     # :887 + clamp :891-892 (fused)
         return {"loss_G": loss_G.detach(), "loss_D": loss_D.detach(), "pixel": pixel_loss_G.detach(),
                 "content": loss_content.detach(), "adv": loss_gan.detach(), "gp": gp.detach(), "gen_hr": gen_det}
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole iteration
+    # ------------------------------------------------------------------------------------------
+    def graphed_step(self, imgs_lr, imgs_hr):
+        """train_step captured ONCE into a CUDA graph (~5k kernel launches -> one cudaGraphLaunch) and
+        replayed; inputs / the GP interpolation factors are staged into static device buffers, the Adam
+        step counters live on the device.  Re-capture happens when the input shape or a learning rate changes."""
+        key = (tuple(imgs_lr.shape), tuple(imgs_hr.shape), self.optimizer_G.param_groups[0]["lr"], self.optimizer_D.param_groups[0]["lr"])
+        if self._graph is None or self._graph["key"] != key:
+            self._capture(imgs_lr, imgs_hr, key)
+        g = self._graph
+        g["lr"].copy_(imgs_lr, non_blocking=True)
+        g["hr"].copy_(imgs_hr, non_blocking=True)
+        g["alpha_host"].copy_(torch.from_numpy(np.random.random((imgs_hr.size(0), 1, 1, 1))).float())   # reference :609
+        g["alpha"].copy_(g["alpha_host"], non_blocking=True)
+        g["graph"].replay()
+        self.optimizer_G.step_count += 1
+        self.optimizer_D.step_count += 1
+        return g["out"]
+
+    def _capture(self, imgs_lr, imgs_hr, key):
+        dev = imgs_lr.device
+        st = {"key": key, "lr": torch.empty_like(imgs_lr), "hr": torch.empty_like(imgs_hr),
+              "alpha": torch.empty(imgs_hr.size(0), 1, 1, 1, device=dev),
+              "alpha_host": torch.empty(imgs_hr.size(0), 1, 1, 1).pin_memory()}
+        st["lr"].copy_(imgs_lr); st["hr"].copy_(imgs_hr); st["alpha"].uniform_()
+        prev_override = self._alpha_override
+        self._alpha_override = st["alpha"]
+        # snapshot everything a step mutates, so that warm-up + capture do not advance the training state
+        snap = [t.clone() for t in self._mutable_state()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.train_step(st["lr"], st["hr"])
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.backend().launch_count()
+        with torch.cuda.graph(graph):
+            st["out"] = self.train_step(st["lr"], st["hr"])
+        st["launches"] = _lib.backend().launch_count() - n0     # library kernels per replay
+        torch.cuda.synchronize()
+        for t, c in zip(self._mutable_state(), snap):
+            t.copy_(c)
+        self.optimizer_G.step_count -= 3
+        self.optimizer_D.step_count -= 3
+        ops.bump_weight_generation()
+        self._alpha_override = prev_override if prev_override is not st["alpha"] else None
+        self._alpha_static = st["alpha"]
+        st["graph"] = graph
+        self._graph = st
+
+    def _mutable_state(self):
+        oG, oD = self.optimizer_G, self.optimizer_D
+        bufs = [b for b in self.discriminator.buffers()]
+        return [oG.flat_param, oG.exp_avg, oG.exp_avg_sq, oG.step_t, oD.flat_param, oD.exp_avg, oD.exp_avg_sq, oD.step_t] + bufs
 
     # ------------------------------------------------------------------------------------------
     # data

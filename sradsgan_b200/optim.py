@@ -40,6 +40,7 @@ class FlatAdam:
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps}]
         self.clamp = clamp
         self.step_count = 0
+        self.step_t = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side copy (graph replay)
         # contiguous chunks (name-prefix -> [start, end)) used by the overlapped all-reduce
         self.chunks = self._make_chunks(chunk_of) if chunk_of is not None else [("all", 0, total, list(self.names))]
 
@@ -75,9 +76,10 @@ class FlatAdam:
     def step(self, grad_scale=1.0):
         self._rebind(copy=True)
         self.step_count += 1
+        self.step_t += 1
         g = self.param_groups[0]
         _lib.backend().adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
-                                 g["betas"][1], g["eps"], self.step_count, grad_scale, self.clamp)
+                                 g["betas"][1], g["eps"], self.step_count, grad_scale, self.clamp, step_tensor=self.step_t)
         ops.bump_weight_generation()
 
     def state_dict(self):
@@ -86,6 +88,7 @@ class FlatAdam:
 
     def load_state_dict(self, sd):
         self.step_count = sd["step"]
+        self.step_t.fill_(sd["step"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.param_groups = [dict(g) for g in sd["param_groups"]]

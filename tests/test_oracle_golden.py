@@ -15,7 +15,7 @@ def _close_summary(got, want, rtol=2e-5):
     torch.testing.assert_close(s["samples"], want["samples"], rtol=1e-4, atol=rtol * max(1e-6, want["norm"] / max(1, got.numel()) ** 0.5) * 10)
 
 
-@pytest.mark.parametrize("case", [c for c in GEN_CASES if c[0] != "g_x4_full"], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", [c for c in GEN_CASES if not c[0].startswith("g_x4_full")], ids=lambda c: c[0])
 def test_generator_forward_matches_reference_golden(golden, case):
     name, scale, ng, nb, batch, lrs, init = case
     g = golden[name]
@@ -34,8 +34,9 @@ def test_generator_forward_matches_reference_golden(golden, case):
     assert checked >= 6
 
 
-def test_generator_full_architecture_golden(golden):
-    name, scale, ng, nb, batch, lrs, init = [c for c in GEN_CASES if c[0] == "g_x4_full"][0]
+@pytest.mark.parametrize("cname", ["g_x4_full", "g_x4_full_refinit"])
+def test_generator_full_architecture_golden(golden, cname):
+    name, scale, ng, nb, batch, lrs, init = [c for c in GEN_CASES if c[0] == cname][0]
     g = golden[name]
     sd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=g["cfg"]["wseed"], init=init))
     n_unique = sum(p.numel() for p in O.unique_params(sd))
