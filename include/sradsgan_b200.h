@@ -81,6 +81,32 @@ int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* w_packed_
 int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float* dw_oihw, float* dbias,
                     int accumulate, void* stream);
 
+/* Fused local-attention tail of RAB / ResGroup (C = 64): z = Conv1x1(SLAM(CLAM(x))) + t, i.e.
+ * nn modules CLAM (model/sradsgan.py:101-127), SLAM (:129-151), the 1x1 `conv` (:233/:297) and the
+ * in-place residual `out += x` (:274/:323) in five kernels.  x: NHWC (x_dtype), t/z32: NHWC fp32,
+ * z16 (nullable): copy of z in x_dtype for the next 3x3 conv.  fc1 [Cr][64], fc2 [64][Cr], w7 [2][7][7],
+ * W [64][64] (OIHW), bias [64], all fp32.  Saved for backward: s, avg, max, pstar [N][64]; m [N][H*W];
+ * q [N][H*W][2]; cstar [N][H*W] (u8).  workspace >= sr_la_chain_workspace_bytes(N,H,W). */
+size_t sr_la_chain_workspace_bytes(int N, int H, int W);
+int sr_la_chain_fwd(const void* x, int x_dtype, const float* t, const float* fc1, const float* fc2, const float* w7,
+                    const float* W, const float* bias, int N, int H, int Wd, int C, int Cr, float* z32, void* z16,
+                    float* s, float* m, float* avg, float* max, int32_t* pstar, float* q, uint8_t* cstar,
+                    void* workspace, void* stream);
+/* Backward of the chain for dz = gz32 + gz16 (either may be NULL).  dx in x_dtype; d_fc1/d_fc2/d_w7/dW/db
+ * are ACCUMULATED into (fp32, reference layouts); dz_out (nullable, fp32 NHWC) receives dz, which is also
+ * the gradient of the residual input t. */
+int sr_la_chain_bwd(const float* gz32, const void* gz16, const void* x, int x_dtype, const float* s, const float* m,
+                    const float* avg, const float* max, const int32_t* pstar, const float* q, const uint8_t* cstar,
+                    const float* fc1, const float* fc2, const float* w7, const float* W, int N, int H, int Wd, int C, int Cr,
+                    void* dx, float* d_fc1, float* d_fc2, float* d_w7, float* dW, float* db, float* dz_out,
+                    void* workspace, void* stream);
+
+/* Backward of the fused conv epilogue: out = PixelUnshuffle_r( gy * act'(y) ), act' recovered from the
+ * sign of the stored output y (LeakyReLU / ReLU; nn.LeakyReLU / nn.PixelShuffle of model/sradsgan.py:242,
+ * :381-386,:428).  gy,y: (N, Ho*r, Wo*r, C/r^2) NHWC; out: (N, Ho, Wo, C) NHWC with channel c*r^2+sub. */
+int sr_act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act, float slope, int shuffle_r,
+               int N, int Ho, int Wo, int C, void* out, int out_dtype, void* stream);
+
 /* out[c] = sum over rows of x[rows][C] (fp32 accumulate); sq (may be NULL) = sum of squares.
  * BatchNorm2d batch statistics (model/sradsgan.py:478) and bias gradients. */
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate,

@@ -89,6 +89,49 @@ class EmuBackend:
         db = dy.float().sum(dim=(0, 2, 3)) if want_bias else None
         return dw.contiguous(), db
 
+    # fused local-attention chain: emulated with the oracle's own building blocks + torch autograd
+    @staticmethod
+    def _la_math(x, t, fc1, fc2, w7, W, b):
+        xf = x.float()
+        avg = F.adaptive_avg_pool2d(xf, 1)
+        mx = F.adaptive_max_pool2d(xf, 1)
+        gate = torch.sigmoid(F.conv2d(F.relu(F.conv2d(avg, fc1)), fc2) + F.conv2d(F.relu(F.conv2d(mx, fc1)), fc2))
+        u = gate * xf
+        q = torch.cat([u.mean(1, keepdim=True), u.max(1, keepdim=True)[0]], 1)
+        m = torch.sigmoid(F.conv2d(q, w7, padding=3))
+        return F.conv2d(m * u, W, b) + t.float()
+
+    def la_chain_fwd(self, x, t, fc1, fc2, w7, W, b, want_lowp=True):
+        self.launches += 5
+        with torch.no_grad():
+            z = self._la_math(x, t, fc1.detach().float(), fc2.detach().float(), w7.detach().float(), W.detach().float(), b.detach().float())
+        z32 = z.contiguous(memory_format=torch.channels_last)
+        z16 = z32.to(x.dtype) if want_lowp else None
+        return z32, z16, {"t_shape": t.shape, "b": b.detach().float()}
+
+    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True):
+        self.launches += 6
+        dz = (gz32.float() if gz32 is not None else 0) + (gz16.float() if gz16 is not None else 0)
+        with torch.enable_grad():
+            xs = x.detach().float().requires_grad_(True)
+            ps = [p.detach().float().clone().requires_grad_(True) for p in (fc1, fc2, w7, W)]
+            bs = sv["b"].clone().requires_grad_(True)
+            z = self._la_math(xs, torch.zeros(sv["t_shape"]), ps[0], ps[1], ps[2], ps[3], bs)
+            grads = torch.autograd.grad(z, [xs] + ps + [bs], dz)
+        return (grads[0].to(x.dtype).contiguous(memory_format=torch.channels_last), grads[1], grads[2], grads[3], grads[4], grads[5],
+                dz.contiguous(memory_format=torch.channels_last) if want_dz else None)
+
+    def act_bwd(self, gy, y, act, slope, shuffle_r, g, out_dtype):
+        self.launches += 1
+        gp = gy.float()
+        if act == ACT_LRELU:
+            gp = torch.where(y.float() > 0, gp, gp * slope)
+        elif act == ACT_RELU:
+            gp = torch.where(y.float() > 0, gp, torch.zeros_like(gp))
+        if shuffle_r and shuffle_r > 1:
+            gp = F.pixel_unshuffle(gp, shuffle_r)
+        return gp.to(out_dtype).contiguous(memory_format=torch.channels_last)
+
     def colsum(self, x2d, want_sq=False):
         self.launches += 1
         f = x2d.float()

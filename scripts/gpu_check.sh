@@ -7,6 +7,7 @@ if [ "$1" != "quick" ]; then
 echo "== simt kernels"; timeout -s KILL 600 python -W ignore -m pytest tests/test_gpu_conv_kernels.py -m gpu -q -k "simt" -x --timeout 300 2>&1 | tail -15 | tee gpurun_out/t_simt.log
 echo "== tcgen05 kernels"; timeout -s KILL 600 python -W ignore -m pytest tests/test_gpu_conv_kernels.py -m gpu -q -k "tcgen05 or full_size" --timeout 120 2>&1 | tail -40 | tee gpurun_out/t_tc.log
 fi
+echo "== fused kernels"; timeout -s KILL 600 python -W ignore -m pytest tests/test_gpu_fused_kernels.py -m gpu -q --timeout 120 2>&1 | tail -30 | tee gpurun_out/t_fused.log
 echo "== model parity"; timeout -s KILL 900 python -W ignore -m pytest tests/test_gpu_model_parity.py -m gpu -q --timeout 300 2>&1 | tail -40 | tee gpurun_out/t_model.log
 echo "== smoke"; timeout -s KILL 300 python -W ignore __graft_entry__.py --smoke 2>&1 | tail -5 | tee gpurun_out/smoke.log
 echo "== bench"; timeout -s KILL 900 python -W ignore bench.py --steps 4 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log

@@ -19,6 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
+    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd",
 ]
 
 
@@ -69,6 +70,13 @@ def load():
     lib.sr_conv2d_wgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, i32, vp]
     lib.sr_colsum.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp]
     lib.sr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, f32, f32, vp]
+    lib.sr_la_chain_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.sr_la_chain_workspace_bytes.restype = ctypes.c_size_t
+    lib.sr_la_chain_fwd.argtypes = [vp, i32] + [vp] * 6 + [i32] * 5 + [vp] * 11
+    lib.sr_la_chain_bwd.argtypes = [vp, vp, vp, i32] + [vp] * 11 + [i32] * 5 + [vp] * 9
+    lib.sr_act_bwd.argtypes = [vp, i32, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp, i32, vp]
+    for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd"):
+        getattr(lib, name).restype = i32
     for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -204,6 +212,68 @@ class CudaBackend:
         self._timed("wgrad", d, False, lambda: _check(
             self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 0, _stream()), "conv2d_wgrad"))
         return dw, db
+
+    # -- fused local-attention chain ---------------------------------------------------------------
+    def la_chain_fwd(self, x, t, fc1, fc2, w7, W, b, want_lowp=True):
+        """z = Conv1x1(SLAM(CLAM(x))) + t  ->  (z32, z16 | None, saved)"""
+        _require_cuda(x, t)
+        x = _nhwc(x)
+        t = _nhwc(t.float())
+        n, c, h, w = x.shape
+        cr = fc1.shape[0]
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        z32 = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
+        z16 = torch.empty((n, c, h, w), dtype=x.dtype, device=dev, memory_format=torch.channels_last) if want_lowp else None
+        sv = {"s": torch.empty((n, c), **f32), "m": torch.empty((n, h * w), **f32), "avg": torch.empty((n, c), **f32),
+              "max": torch.empty((n, c), **f32), "pstar": torch.empty((n, c), dtype=torch.int32, device=dev),
+              "q": torch.empty((n, h * w, 2), **f32), "cstar": torch.empty((n, h * w), dtype=torch.uint8, device=dev)}
+        ws = torch.empty(self.lib.sr_la_chain_workspace_bytes(n, h, w), dtype=torch.uint8, device=dev)
+        args = [fc1, fc2, w7, W, b]
+        args = [a.detach().float().contiguous() for a in args]
+        _check(self.lib.sr_la_chain_fwd(_ptr(x), _dt(x), _ptr(t), *[_ptr(a) for a in args], n, h, w, c, cr, _ptr(z32), _ptr(z16),
+                                        _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]), _ptr(sv["max"]), _ptr(sv["pstar"]),
+                                        _ptr(sv["q"]), _ptr(sv["cstar"]), _ptr(ws), _stream()), "la_chain_fwd")
+        return z32, z16, sv
+
+    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True):
+        """-> (dx, d_fc1, d_fc2, d_w7, dW, db, dz)"""
+        x = _nhwc(x)
+        n, c, h, w = x.shape
+        cr = fc1.shape[0]
+        dev = x.device
+        if gz32 is not None:
+            gz32 = _nhwc(gz32.float())
+        if gz16 is not None:
+            gz16 = _nhwc(gz16.to(x.dtype))
+        f32 = dict(dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        d_fc1 = torch.zeros(fc1.shape, **f32); d_fc2 = torch.zeros(fc2.shape, **f32); d_w7 = torch.zeros(w7.shape, **f32)
+        dW = torch.zeros(W.shape, **f32); db = torch.zeros((c,), **f32)
+        if want_dz and gz32 is not None and gz16 is None:
+            dz, dz_ptr = gz32, None             # the residual gradient is the incoming gradient itself
+        elif want_dz:
+            dz = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
+            dz_ptr = dz
+        else:
+            dz, dz_ptr = None, None
+        ws = torch.empty(self.lib.sr_la_chain_workspace_bytes(n, h, w), dtype=torch.uint8, device=dev)
+        wts = [a.detach().float().contiguous() for a in (fc1, fc2, w7, W)]
+        _check(self.lib.sr_la_chain_bwd(_ptr(gz32), _ptr(gz16), _ptr(x), _dt(x), _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]),
+                                        _ptr(sv["max"]), _ptr(sv["pstar"]), _ptr(sv["q"]), _ptr(sv["cstar"]),
+                                        *[_ptr(a) for a in wts], n, h, w, c, cr, _ptr(dx), _ptr(d_fc1), _ptr(d_fc2), _ptr(d_w7),
+                                        _ptr(dW), _ptr(db), _ptr(dz_ptr), _ptr(ws), _stream()), "la_chain_bwd")
+        return dx, d_fc1, d_fc2, d_w7, dW, db, dz
+
+    def act_bwd(self, gy, y, act, slope, shuffle_r, g, out_dtype):
+        """gpre = PixelUnshuffle_r(gy * act'(y)) in out_dtype, shape (N, Cout, Ho, Wo)"""
+        _require_cuda(gy, y)
+        gy = _nhwc(gy)
+        y = _nhwc(y)
+        out = torch.empty((g.N, g.Cout, g.Ho, g.Wo), dtype=out_dtype, device=gy.device, memory_format=torch.channels_last)
+        _check(self.lib.sr_act_bwd(_ptr(gy), _dt(gy), _ptr(y), _dt(y), int(act), float(slope), int(shuffle_r or 0), g.N, g.Ho, g.Wo,
+                                   g.Cout, _ptr(out), _dt(out), _stream()), "act_bwd")
+        return out
 
     # -- reductions / optimiser ----------------------------------------------------------------
     def colsum(self, x2d, want_sq=False):

@@ -37,6 +37,14 @@ int conv_tc_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const
 // conv_tc_wgrad.cu
 bool conv_tc_wgrad_supported(const sr_conv_desc*);
 int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
+// la_chain.cu
+size_t la_workspace_bytes(int, int, int);
+int la_chain_fwd(const void*, int, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
+                 int, float*, void*, float*, float*, float*, float*, int*, float*, unsigned char*, float*, cudaStream_t);
+int la_chain_bwd(const float*, const void*, const void*, int, const float*, const float*, const float*, const float*, const int*,
+                 const float*, const unsigned char*, const float*, const float*, const float*, const float*, int, int, int, int,
+                 void*, float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
+int act_bwd(const void*, int, const void*, int, int, float, int, int, int, int, int, void*, int, cudaStream_t);
 // elementwise.cu
 int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
@@ -148,6 +156,42 @@ int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float*
     if (rc) return rc;
     if (dbias) rc = colsum(dy, d->in_dtype, (long long)d->N * d->Ho * d->Wo, d->Cout, dbias, nullptr, accumulate, st);
     return rc;
+}
+
+size_t sr_la_chain_workspace_bytes(int N, int H, int W) { return la_workspace_bytes(N, H, W); }
+
+int sr_la_chain_fwd(const void* x, int x_dtype, const float* t, const float* fc1, const float* fc2, const float* w7, const float* W,
+                    const float* bias, int N, int H, int Wd, int C, int Cr, float* z32, void* z16, float* s, float* m, float* avg,
+                    float* mx, int32_t* pstar, float* q, uint8_t* cstar, void* workspace, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(C == 64 && Cr >= 1 && Cr <= 16, "la_chain: C must be 64 and 1 <= Cr <= 16 (got %d, %d)", C, Cr);
+    SR_REQUIRE(x && t && fc1 && fc2 && w7 && W && bias && z32 && s && m && avg && mx && pstar && q && cstar && workspace, "la_chain_fwd: NULL pointer");
+    SR_REQUIRE(x_dtype == SR_F32 || x_dtype == SR_BF16, "la_chain_fwd: bad dtype");
+    return la_chain_fwd(x, x_dtype, t, fc1, fc2, w7, W, bias, N, H, Wd, Cr, z32, z16, s, m, avg, mx, pstar, q, cstar,
+                        (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_la_chain_bwd(const float* gz32, const void* gz16, const void* x, int x_dtype, const float* s, const float* m, const float* avg,
+                    const float* mx, const int32_t* pstar, const float* q, const uint8_t* cstar, const float* fc1, const float* fc2,
+                    const float* w7, const float* W, int N, int H, int Wd, int C, int Cr, void* dx, float* d_fc1, float* d_fc2,
+                    float* d_w7, float* dW, float* db, float* dz_out, void* workspace, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(C == 64 && Cr >= 1 && Cr <= 16, "la_chain: C must be 64 and 1 <= Cr <= 16 (got %d, %d)", C, Cr);
+    SR_REQUIRE((gz32 || gz16) && x && s && m && avg && mx && pstar && q && cstar && fc1 && fc2 && w7 && W && dx && d_fc1 && d_fc2 && d_w7 && dW && db && workspace,
+               "la_chain_bwd: NULL pointer");
+    return la_chain_bwd(gz32, gz16, x, x_dtype, s, m, avg, mx, pstar, q, cstar, fc1, fc2, w7, W, N, H, Wd, Cr, dx, d_fc1, d_fc2,
+                        d_w7, dW, db, dz_out, (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act, float slope, int shuffle_r, int N, int Ho, int Wo,
+               int C, void* out, int out_dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(gy && y && out && N > 0 && Ho > 0 && Wo > 0 && C > 0, "act_bwd: bad arguments");
+    SR_REQUIRE(shuffle_r <= 1 || C % (shuffle_r * shuffle_r) == 0, "act_bwd: C %% r^2 != 0");
+    return act_bwd(gy, gy_dtype, y, y_dtype, act, slope, shuffle_r, N, Ho, Wo, C, out, out_dtype, (cudaStream_t)stream);
 }
 
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate, void* stream) {

@@ -74,6 +74,48 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+template <typename TG, typename TY, typename TO>
+__global__ void act_bwd_kernel(const TG* __restrict__ gy, const TY* __restrict__ y, int act, float slope, int r, int N, int Ho, int Wo,
+                               int C, TO* __restrict__ out) {
+    const long long total = (long long)N * Ho * Wo * C;
+    const int r2 = r * r, cq = C / r2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long src = i;
+        if (r > 1) {      // i indexes out (n, oy, ox, c = cc*r2 + sub) <- shuffled (n, oy*r+si, ox*r+sj, cc)
+            const int c = (int)(i % C); long long q = i / C;
+            const int ox = (int)(q % Wo); q /= Wo;
+            const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+            const int cc = c / r2, sub = c - cc * r2, si = sub / r, sj = sub - si * r;
+            src = ((((long long)n * Ho * r + (oy * r + si)) * ((long long)Wo * r)) + (ox * r + sj)) * cq + cc;
+        }
+        float g = to_f32<TG>(gy[src]);
+        if (act == SR_ACT_LRELU) { if (!(to_f32<TY>(y[src]) > 0.f)) g *= slope; }
+        else if (act == SR_ACT_RELU) { if (!(to_f32<TY>(y[src]) > 0.f)) g = 0.f; }
+        out[i] = from_f32<TO>(g);
+    }
+}
+
+template <typename TG, typename TY>
+static void act_bwd_launch(const void* gy, const void* y, int act, float slope, int r, int N, int Ho, int Wo, int C, void* out,
+                           int out_dtype, int blocks, cudaStream_t st) {
+    if (out_dtype == SR_F32) act_bwd_kernel<TG, TY, float><<<blocks, 256, 0, st>>>((const TG*)gy, (const TY*)y, act, slope, r, N, Ho, Wo, C, (float*)out);
+    else act_bwd_kernel<TG, TY, __nv_bfloat16><<<blocks, 256, 0, st>>>((const TG*)gy, (const TY*)y, act, slope, r, N, Ho, Wo, C, (__nv_bfloat16*)out);
+}
+
+int act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act, float slope, int r, int N, int Ho, int Wo, int C,
+            void* out, int out_dtype, cudaStream_t st) {
+    const long long total = (long long)N * Ho * Wo * C;
+    if (total <= 0) return SR_OK;
+    const int blocks = (int)std::min<long long>(148 * 16, (long long)cdiv(total, 256));
+    if (r < 1) r = 1;
+    if (gy_dtype == SR_F32 && y_dtype == SR_F32) act_bwd_launch<float, float>(gy, y, act, slope, r, N, Ho, Wo, C, out, out_dtype, blocks, st);
+    else if (gy_dtype == SR_F32) act_bwd_launch<float, __nv_bfloat16>(gy, y, act, slope, r, N, Ho, Wo, C, out, out_dtype, blocks, st);
+    else if (y_dtype == SR_F32) act_bwd_launch<__nv_bfloat16, float>(gy, y, act, slope, r, N, Ho, Wo, C, out, out_dtype, blocks, st);
+    else act_bwd_launch<__nv_bfloat16, __nv_bfloat16>(gy, y, act, slope, r, N, Ho, Wo, C, out, out_dtype, blocks, st);
+    count_launch();
+    return check_launch("act_bwd_kernel");
+}
+
 int pack_weights(const float* w, void* out, int Cout, int Cin, int kh, int kw, int mode, int dtype, int shuffle_r, cudaStream_t st) {
     const long long total = (long long)Cout * Cin * kh * kw;
     const int blocks = (int)std::min<long long>(148 * 8, (long long)cdiv(total, 256));

@@ -1,0 +1,540 @@
+// Fused local-attention chain of SRADSGAN's RAB / ResGroup tails (C = 64 channels):
+//
+//     z = Conv1x1( SLAM( CLAM(x) ) ) + t
+//       = W . ( m[n,p] * s[n,c] * x[n,p,c] ) + b + t[n,p,:]
+//     s = sigmoid( MLP(avgpool_p x) + MLP(maxpool_p x) )        (CLAM, reference model/sradsgan.py:117-127)
+//     m = sigmoid( conv7x7( [mean_c(s*x), max_c(s*x)] ) )       (SLAM, :141-151)
+//     + 1x1 conv (:233,:262 / :297,:311) + residual (:274 / :323)
+//
+// The reference issues ~25 ATen kernels and ~15 full-tensor passes per chain (48 chains per generator
+// forward, x3 in backward).  Here: 5 small kernels forward (x is read 3 times, z written once in fp32
+// for the residual trunk and once in the compute dtype for the next 3x3 conv) and 6 backward.
+// All reductions are warp-shuffle / shared-memory based with fp32 accumulation; every kernel is HBM/L2
+// bound.
+#include "common.cuh"
+
+namespace sr {
+
+constexpr int LA_C = 64;
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+
+// per (image, pixel slice): channel sums / maxima / first arg-max.  block = 8 warps, lane = 2 channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+la_pool_partial_kernel(const T* __restrict__ x, int P, int S, float* __restrict__ psum, float* __restrict__ pmax, int* __restrict__ pidx) {
+    const int n = blockIdx.y, sl = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (P + S - 1) / S;
+    const int p0 = sl * per, p1 = min(P, p0 + per);
+    float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
+    int i0 = 0x7fffffff, i1 = 0x7fffffff;
+    const T* base = x + (long long)n * P * LA_C + lane * 2;
+    for (int p = p0 + warp; p < p1; p += 8) {
+        const float a = to_f32<T>(base[(long long)p * LA_C]), b = to_f32<T>(base[(long long)p * LA_C + 1]);
+        s0 += a; s1 += b;
+        if (a > m0) { m0 = a; i0 = p; }
+        if (b > m1) { m1 = b; i1 = p; }
+    }
+    __shared__ float sh_s[8][LA_C], sh_m[8][LA_C];
+    __shared__ int sh_i[8][LA_C];
+    sh_s[warp][lane * 2] = s0; sh_s[warp][lane * 2 + 1] = s1;
+    sh_m[warp][lane * 2] = m0; sh_m[warp][lane * 2 + 1] = m1;
+    sh_i[warp][lane * 2] = i0; sh_i[warp][lane * 2 + 1] = i1;
+    __syncthreads();
+    if (threadIdx.x < LA_C) {
+        const int c = threadIdx.x;
+        float s = 0.f, m = -INFINITY; int idx = 0x7fffffff;
+        for (int w = 0; w < 8; ++w) {
+            s += sh_s[w][c];
+            const float mv = sh_m[w][c]; const int iv = sh_i[w][c];
+            if (mv > m || (mv == m && iv < idx)) { m = mv; idx = iv; }
+        }
+        const long long o = ((long long)n * S + sl) * LA_C + c;
+        psum[o] = s; pmax[o] = m; pidx[o] = idx;
+    }
+}
+
+// per image: finish the pooling, run the bias-free MLP on both pooled vectors, gate = sigmoid(sum)
+__global__ void __launch_bounds__(LA_C)
+la_gate_fwd_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, const int* __restrict__ pidx, int P, int S,
+                   const float* __restrict__ fc1, const float* __restrict__ fc2, int Cr,
+                   float* __restrict__ s_out, float* __restrict__ avg_out, float* __restrict__ max_out, int* __restrict__ pstar) {
+    const int n = blockIdx.x, c = threadIdx.x;
+    __shared__ float a[LA_C], mx[LA_C], ha[16], hm[16];
+    float s = 0.f, m = -INFINITY; int idx = 0x7fffffff;
+    for (int sl = 0; sl < S; ++sl) {
+        const long long o = ((long long)n * S + sl) * LA_C + c;
+        s += psum[o];
+        const float mv = pmax[o]; const int iv = pidx[o];
+        if (mv > m || (mv == m && iv < idx)) { m = mv; idx = iv; }
+    }
+    a[c] = s / (float)P; mx[c] = m;
+    avg_out[n * LA_C + c] = a[c]; max_out[n * LA_C + c] = m; pstar[n * LA_C + c] = idx;
+    __syncthreads();
+    if (c < Cr) {
+        float u = 0.f, v = 0.f;
+        for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * mx[k]; }
+        ha[c] = fmaxf(u, 0.f); hm[c] = fmaxf(v, 0.f);
+    }
+    __syncthreads();
+    float o = 0.f;
+    for (int j = 0; j < Cr; ++j) o += fc2[c * Cr + j] * (ha[j] + hm[j]);
+    s_out[n * LA_C + c] = 1.f / (1.f + __expf(-o));
+}
+
+// per pixel (one warp): mean / max / first arg-max over channels of u = s*x
+template <typename T>
+__global__ void __launch_bounds__(256)
+la_stats_kernel(const T* __restrict__ x, const float* __restrict__ s, int P, long long NP, float* __restrict__ q, unsigned char* __restrict__ cstar) {
+    const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pix >= NP) return;
+    const int lane = threadIdx.x & 31;
+    const int n = (int)(pix / P);
+    const float u0 = to_f32<T>(x[pix * LA_C + lane * 2]) * s[n * LA_C + lane * 2];
+    const float u1 = to_f32<T>(x[pix * LA_C + lane * 2 + 1]) * s[n * LA_C + lane * 2 + 1];
+    float sum = u0 + u1;
+    float mv = u0; int mi = lane * 2;
+    if (u1 > mv) { mv = u1; mi = lane * 2 + 1; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
+    }
+    if (lane == 0) {
+        q[pix * 2] = sum * (1.f / LA_C);
+        q[pix * 2 + 1] = mv;
+        cstar[pix] = (unsigned char)mi;
+    }
+}
+
+// m = sigmoid(conv7x7(q)), q = [mean, max] planes stored interleaved [N][H][W][2]
+__global__ void __launch_bounds__(256)
+la_conv7_fwd_kernel(const float* __restrict__ q, const float* __restrict__ w7, int N, int H, int W, float* __restrict__ m) {
+    __shared__ float ws[98];
+    if (threadIdx.x < 98) ws[threadIdx.x] = w7[threadIdx.x];     // [ch][ky][kx]
+    __syncthreads();
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long long)N * H * W) return;
+    const int x = (int)(pix % W); const long long r = pix / W;
+    const int y = (int)(r % H); const int n = (int)(r / H);
+    float e = 0.f;
+    for (int ky = 0; ky < 7; ++ky) {
+        const int yy = y + ky - 3;
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 7; ++kx) {
+            const int xx = x + kx - 3;
+            if (xx < 0 || xx >= W) continue;
+            const float2 v = *reinterpret_cast<const float2*>(q + (((long long)n * H + yy) * W + xx) * 2);
+            e += ws[ky * 7 + kx] * v.x + ws[49 + ky * 7 + kx] * v.y;
+        }
+    }
+    m[pix] = 1.f / (1.f + __expf(-e));
+}
+
+// z = W.(m*s*x) + b + t   (64 pixels x 64 channels per block; 4x4 register tile per thread)
+template <typename T>
+__global__ void __launch_bounds__(256)
+la_apply_kernel(const T* __restrict__ x, const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ t_res,
+                const float* __restrict__ Wm, const float* __restrict__ bias, int P, long long NP,
+                float* __restrict__ z32, T* __restrict__ z16) {
+    __shared__ __align__(16) float ws[LA_C][LA_C + 4];   // ws[ci][co] = W[co][ci]
+    __shared__ __align__(16) float vs[LA_C][LA_C + 4];   // vs[ci][pixel]
+    const int t = threadIdx.x;
+    for (int i = t; i < LA_C * LA_C; i += 256) ws[i % LA_C][i / LA_C] = Wm[i];
+    const long long p0 = (long long)blockIdx.x * 64;
+    {
+        const int pl = t >> 2, cb = (t & 3) * 4;
+        const long long pix = p0 + pl;
+        if (pix < NP) {
+            const int n = (int)(pix / P);
+            const float mp = m[pix];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c = cb + 16 * jj;
+                float v[4];
+                load4<T>(x + pix * LA_C + c, v);
+                const float4 sv = *reinterpret_cast<const float4*>(s + n * LA_C + c);
+                vs[c][pl] = v[0] * mp * sv.x; vs[c + 1][pl] = v[1] * mp * sv.y;
+                vs[c + 2][pl] = v[2] * mp * sv.z; vs[c + 3][pl] = v[3] * mp * sv.w;
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) vs[cb + 16 * jj + k][pl] = 0.f;
+        }
+    }
+    __syncthreads();
+    const int tp = t >> 4, tc = t & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int ci = 0; ci < LA_C; ++ci) {
+        const float4 a = *reinterpret_cast<const float4*>(&vs[ci][tp * 4]);
+        const float4 w = *reinterpret_cast<const float4*>(&ws[ci][tc * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    const float4 bv = *reinterpret_cast<const float4*>(bias + tc * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long pix = p0 + tp * 4 + i;
+        if (pix >= NP) continue;
+        const float4 r = *reinterpret_cast<const float4*>(t_res + pix * LA_C + tc * 4);
+        float4 o = make_float4(acc[i][0] + bv.x + r.x, acc[i][1] + bv.y + r.y, acc[i][2] + bv.z + r.z, acc[i][3] + bv.w + r.w);
+        *reinterpret_cast<float4*>(z32 + pix * LA_C + tc * 4) = o;
+        if (z16) store4<T>(z16 + pix * LA_C + tc * 4, o.x, o.y, o.z, o.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+
+// Persistent over 64-pixel tiles.  dz = gz32 + gz16 (either may be null);  dv = W^T dz;  g = m*dv;
+// dm = sum_c dv*u (u = s*x);  dW += (m*dz) (x) u;  db += sum dz;  optionally writes dz (the residual gradient).
+template <typename T>
+__global__ void __launch_bounds__(256)
+la_bwd_apply_kernel(const float* __restrict__ gz32, const T* __restrict__ gz16, const T* __restrict__ x, const float* __restrict__ s,
+                    const float* __restrict__ m, const float* __restrict__ Wm, int P, long long NP, int tiles,
+                    float* __restrict__ g, float* __restrict__ dm, float* __restrict__ dW, float* __restrict__ db,
+                    float* __restrict__ dz_out) {
+    extern __shared__ __align__(16) float la_smem[];
+    float (*ws)[LA_C + 4] = reinterpret_cast<float (*)[LA_C + 4]>(la_smem);                        // ws[co][ci] = W[co][ci]
+    float (*dzs)[LA_C + 4] = reinterpret_cast<float (*)[LA_C + 4]>(la_smem + LA_C * (LA_C + 4));   // dzs[co][pixel]
+    float (*us)[LA_C + 4] = reinterpret_cast<float (*)[LA_C + 4]>(la_smem + 2 * LA_C * (LA_C + 4)); // us[ci][pixel] = s*x
+    float* ms = la_smem + 3 * LA_C * (LA_C + 4);                                                   // m per pixel of the tile
+    const int t = threadIdx.x;
+    for (int i = t; i < LA_C * LA_C; i += 256) ws[i / LA_C][i % LA_C] = Wm[i];
+    const int tp = t >> 4, tc = t & 15;
+    float wacc[4][4];      // dW[co = tp*4+i][ci = tc + 16*j]
+    float bacc = 0.f;      // db[co = t] for t < 64
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wacc[i][j] = 0.f;
+
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long p0 = (long long)tile * 64;
+        __syncthreads();
+        {
+            const int pl = t >> 2, cb = (t & 3) * 4;
+            const long long pix = p0 + pl;
+            if (pix < NP) {
+                const int n = (int)(pix / P);
+                if ((t & 3) == 0) ms[pl] = m[pix];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c = cb + 16 * jj;
+                    float xv[4], d[4] = {0.f, 0.f, 0.f, 0.f};
+                    load4<T>(x + pix * LA_C + c, xv);
+                    if (gz32) { const float4 a = *reinterpret_cast<const float4*>(gz32 + pix * LA_C + c); d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; }
+                    if (gz16) { float b[4]; load4<T>(gz16 + pix * LA_C + c, b); d[0] += b[0]; d[1] += b[1]; d[2] += b[2]; d[3] += b[3]; }
+                    if (dz_out) *reinterpret_cast<float4*>(dz_out + pix * LA_C + c) = make_float4(d[0], d[1], d[2], d[3]);
+                    const float4 sv = *reinterpret_cast<const float4*>(s + n * LA_C + c);
+                    const float svv[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        dzs[c + k][pl] = d[k];
+                        us[c + k][pl] = xv[k] * svv[k];
+                    }
+                }
+            } else {
+                if ((t & 3) == 0) ms[pl] = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { dzs[cb + 16 * jj + k][pl] = 0.f; us[cb + 16 * jj + k][pl] = 0.f; }
+            }
+        }
+        __syncthreads();
+        // GEMM 1: dv[pixel = tp*4+i][ci = tc*4+j] = sum_co dz[pixel][co] * W[co][ci]
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+        for (int co = 0; co < LA_C; ++co) {
+            const float4 a = *reinterpret_cast<const float4*>(&dzs[co][tp * 4]);
+            const float4 w = *reinterpret_cast<const float4*>(&ws[co][tc * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long pix = p0 + tp * 4 + i;
+            const bool ok = pix < NP;
+            const float mp = ms[tp * 4 + i];
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part += acc[i][j] * us[tc * 4 + j][tp * 4 + i];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (ok) {
+                *reinterpret_cast<float4*>(g + pix * LA_C + tc * 4) = make_float4(mp * acc[i][0], mp * acc[i][1], mp * acc[i][2], mp * acc[i][3]);
+                if (tc == 0) dm[pix] = part;
+            }
+        }
+        // GEMM 2: dW[co = tp*4+i][ci = tc+16*j] += sum_pixel (m*dz)[pixel][co] * u[pixel][ci]
+#pragma unroll 4
+        for (int p = 0; p < 64; p += 4) {
+            const float4 mv = *reinterpret_cast<const float4*>(&ms[p]);
+            float4 dzv[4], uv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dzv[i] = *reinterpret_cast<const float4*>(&dzs[tp * 4 + i][p]);
+                dzv[i].x *= mv.x; dzv[i].y *= mv.y; dzv[i].z *= mv.z; dzv[i].w *= mv.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) uv[j] = *reinterpret_cast<const float4*>(&us[tc + 16 * j][p]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    wacc[i][j] += dzv[i].x * uv[j].x + dzv[i].y * uv[j].y + dzv[i].z * uv[j].z + dzv[i].w * uv[j].w;
+        }
+        if (t < LA_C) {
+            float sacc = 0.f;
+#pragma unroll 8
+            for (int p = 0; p < 64; ++p) sacc += dzs[t][p];
+            bacc += sacc;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(dW + (tp * 4 + i) * LA_C + tc + 16 * j, wacc[i][j]);
+    if (t < LA_C) atomicAdd(db + t, bacc);
+}
+
+// dq[p][ch] = sum_taps w7[ch][tap] * de[p - off],  de = dm * m * (1 - m)
+__global__ void __launch_bounds__(256)
+la_conv7_dgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m, const float* __restrict__ w7, int N, int H, int W,
+                      float* __restrict__ dq) {
+    __shared__ float ws[98];
+    if (threadIdx.x < 98) ws[threadIdx.x] = w7[threadIdx.x];
+    __syncthreads();
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long long)N * H * W) return;
+    const int x = (int)(pix % W); const long long r = pix / W;
+    const int y = (int)(r % H); const int n = (int)(r / H);
+    float a = 0.f, b = 0.f;
+    for (int ky = 0; ky < 7; ++ky) {
+        const int yy = y - (ky - 3);
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 7; ++kx) {
+            const int xx = x - (kx - 3);
+            if (xx < 0 || xx >= W) continue;
+            const long long o = ((long long)n * H + yy) * W + xx;
+            const float mv = m[o];
+            const float de = dm[o] * mv * (1.f - mv);
+            a += ws[ky * 7 + kx] * de;
+            b += ws[49 + ky * 7 + kx] * de;
+        }
+    }
+    dq[pix * 2] = a; dq[pix * 2 + 1] = b;
+}
+
+// dw7[ch][ky][kx] += sum_p de[p] * q[p + off][ch]   (one block per filter element)
+__global__ void __launch_bounds__(256)
+la_conv7_wgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m, const float* __restrict__ q, int N, int H, int W,
+                      float* __restrict__ dw7) {
+    const int idx = blockIdx.x, ch = idx / 49, ky = (idx % 49) / 7, kx = idx % 7;
+    const long long NP = (long long)N * H * W;
+    float acc = 0.f;
+    for (long long pix = threadIdx.x; pix < NP; pix += blockDim.x) {
+        const int x = (int)(pix % W); const long long r = pix / W;
+        const int y = (int)(r % H); const int n = (int)(r / H);
+        const int yy = y + ky - 3, xx = x + kx - 3;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float mv = m[pix];
+        acc += dm[pix] * mv * (1.f - mv) * q[(((long long)n * H + yy) * W + xx) * 2 + ch];
+    }
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        atomicAdd(dw7 + idx, s);
+    }
+}
+
+// per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x
+template <typename T>
+__global__ void __launch_bounds__(256)
+la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, const unsigned char* __restrict__ cstar,
+                    const T* __restrict__ x, const float* __restrict__ s, int P, int S, T* __restrict__ dx, float* __restrict__ ds) {
+    const int n = blockIdx.y, sl = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (P + S - 1) / S;
+    const int p0 = sl * per, p1 = min(P, p0 + per);
+    const float s0 = s[n * LA_C + lane * 2], s1 = s[n * LA_C + lane * 2 + 1];
+    float a0 = 0.f, a1 = 0.f;
+    for (int p = p0 + warp; p < p1; p += 8) {
+        const long long pix = (long long)n * P + p;
+        const float2 gv = *reinterpret_cast<const float2*>(g + pix * LA_C + lane * 2);
+        const float2 dqv = *reinterpret_cast<const float2*>(dq + pix * 2);
+        const int cs = cstar[pix];
+        const float du0 = gv.x + dqv.x * (1.f / LA_C) + (cs == lane * 2 ? dqv.y : 0.f);
+        const float du1 = gv.y + dqv.x * (1.f / LA_C) + (cs == lane * 2 + 1 ? dqv.y : 0.f);
+        const float x0 = to_f32<T>(x[pix * LA_C + lane * 2]), x1 = to_f32<T>(x[pix * LA_C + lane * 2 + 1]);
+        a0 += du0 * x0; a1 += du1 * x1;
+        dx[pix * LA_C + lane * 2] = from_f32<T>(s0 * du0);
+        dx[pix * LA_C + lane * 2 + 1] = from_f32<T>(s1 * du1);
+    }
+    __shared__ float sh[8][LA_C];
+    sh[warp][lane * 2] = a0; sh[warp][lane * 2 + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < LA_C) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
+        atomicAdd(ds + n * LA_C + threadIdx.x, v);
+    }
+}
+
+// gate backward (tiny): one block, loops over images
+__global__ void __launch_bounds__(LA_C)
+la_gate_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ s, const float* __restrict__ avg, const float* __restrict__ mx,
+                   const float* __restrict__ fc1, const float* __restrict__ fc2, int N, int Cr,
+                   float* __restrict__ d_fc1, float* __restrict__ d_fc2, float* __restrict__ da, float* __restrict__ dmx) {
+    const int c = threadIdx.x;
+    __shared__ float a[LA_C], m[LA_C], dov[LA_C], pa[16], pm[16], dha[16], dhm[16];
+    float acc1[16], acc2[16];
+    for (int j = 0; j < 16; ++j) { acc1[j] = 0.f; acc2[j] = 0.f; }
+    for (int n = 0; n < N; ++n) {
+        __syncthreads();
+        a[c] = avg[n * LA_C + c]; m[c] = mx[n * LA_C + c];
+        const float sv = s[n * LA_C + c];
+        dov[c] = ds[n * LA_C + c] * sv * (1.f - sv);
+        __syncthreads();
+        if (c < Cr) {
+            float u = 0.f, v = 0.f, d = 0.f;
+            for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * m[k]; d += fc2[k * Cr + c] * dov[k]; }
+            pa[c] = u; pm[c] = v;
+            dha[c] = u > 0.f ? d : 0.f;
+            dhm[c] = v > 0.f ? d : 0.f;
+        }
+        __syncthreads();
+        float dav = 0.f, dmv = 0.f;
+        for (int j = 0; j < Cr; ++j) {
+            acc2[j] += dov[c] * (fmaxf(pa[j], 0.f) + fmaxf(pm[j], 0.f));     // d_fc2[c][j]
+            acc1[j] += dha[j] * a[c] + dhm[j] * m[c];                         // d_fc1[j][c]
+            dav += fc1[j * LA_C + c] * dha[j];
+            dmv += fc1[j * LA_C + c] * dhm[j];
+        }
+        da[n * LA_C + c] = dav; dmx[n * LA_C + c] = dmv;
+    }
+    for (int j = 0; j < Cr; ++j) {
+        d_fc2[c * Cr + j] += acc2[j];
+        d_fc1[j * LA_C + c] += acc1[j];
+    }
+}
+
+// dx += da/P  (+ dmx at the arg-max pixel)
+template <typename T>
+__global__ void __launch_bounds__(256)
+la_fix_kernel(T* __restrict__ dx, const float* __restrict__ da, const float* __restrict__ dmx, const int* __restrict__ pstar, int P, long long total) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    const int c = (int)(i % LA_C);
+    const long long pix = i / LA_C;
+    const int n = (int)(pix / P), p = (int)(pix % P);
+    const float invP = 1.f / (float)P;
+    float v[4];
+    load4<T>(dx + i, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] += da[n * LA_C + c + k] * invP;
+        if (pstar[n * LA_C + c + k] == p) v[k] += dmx[n * LA_C + c + k];
+        dx[i + k] = from_f32<T>(v[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static int la_slices(int P) { int s = (P + 255) / 256; return s < 1 ? 1 : (s > 32 ? 32 : s); }
+
+size_t la_workspace_bytes(int N, int H, int W) {
+    const int P = H * W, S = la_slices(P);
+    // fwd: psum, pmax, pidx ; bwd: g, dm, dq, ds, da, dmx
+    size_t fwd = (size_t)N * S * LA_C * 12;
+    size_t bwd = (size_t)N * P * LA_C * 4 + (size_t)N * P * 4 + (size_t)N * P * 8 + (size_t)N * LA_C * 12;
+    return (fwd > bwd ? fwd : bwd) + 256;
+}
+
+template <typename T>
+static int la_fwd_t(const void* x, const float* t_res, const float* fc1, const float* fc2, const float* w7, const float* Wm,
+                    const float* bias, int N, int H, int W, int Cr, float* z32, void* z16, float* s_out, float* m_out,
+                    float* avg_out, float* max_out, int* pstar, float* q, unsigned char* cstar, float* ws, cudaStream_t st) {
+    const int P = H * W, S = la_slices(P);
+    const long long NP = (long long)N * P;
+    float* psum = ws; float* pmax = psum + (size_t)N * S * LA_C; int* pidx = reinterpret_cast<int*>(pmax + (size_t)N * S * LA_C);
+    la_pool_partial_kernel<T><<<dim3(S, N), 256, 0, st>>>((const T*)x, P, S, psum, pmax, pidx);
+    la_gate_fwd_kernel<<<N, LA_C, 0, st>>>(psum, pmax, pidx, P, S, fc1, fc2, Cr, s_out, avg_out, max_out, pstar);
+    la_stats_kernel<T><<<(unsigned)cdiv(NP, 8), 256, 0, st>>>((const T*)x, s_out, P, NP, q, cstar);
+    la_conv7_fwd_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(q, w7, N, H, W, m_out);
+    la_apply_kernel<T><<<(unsigned)cdiv(NP, 64), 256, 0, st>>>((const T*)x, s_out, m_out, t_res, Wm, bias, P, NP, z32, (T*)z16);
+    count_launch(5);
+    return check_launch("la_chain_fwd");
+}
+
+template <typename T>
+static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const float* s, const float* m, const float* avg,
+                    const float* mx, const int* pstar, const float* q, const unsigned char* cstar, const float* fc1,
+                    const float* fc2, const float* w7, const float* Wm, int N, int H, int W, int Cr, void* dx, float* d_fc1,
+                    float* d_fc2, float* d_w7, float* dW, float* db, float* dz_out, float* ws, cudaStream_t st) {
+    const int P = H * W, S = la_slices(P);
+    const long long NP = (long long)N * P;
+    float* g = ws; float* dm = g + (size_t)NP * LA_C; float* dq = dm + NP; float* ds = dq + NP * 2;
+    float* da = ds + (size_t)N * LA_C; float* dmx = da + (size_t)N * LA_C;
+    cudaMemsetAsync(ds, 0, sizeof(float) * N * LA_C, st);
+    const int tiles = (int)cdiv(NP, 64);
+    const int grid = tiles < 296 ? tiles : 296;
+    const size_t smem = sizeof(float) * (3 * LA_C * (LA_C + 4) + 64);
+    static bool attr[2] = {false, false};
+    const int ai = sizeof(T) == 2 ? 1 : 0;
+    if (!attr[ai]) { cudaFuncSetAttribute(la_bwd_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr[ai] = true; }
+    la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
+    la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
+    la_conv7_wgrad_kernel<<<98, 256, 0, st>>>(dm, m, q, N, H, W, d_w7);
+    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds);
+    la_gate_bwd_kernel<<<1, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, N, Cr, d_fc1, d_fc2, da, dmx);
+    la_fix_kernel<T><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((T*)dx, da, dmx, pstar, P, NP * LA_C);
+    count_launch(6);
+    return check_launch("la_chain_bwd");
+}
+
+int la_chain_fwd(const void* x, int dtype, const float* t_res, const float* fc1, const float* fc2, const float* w7, const float* Wm,
+                 const float* bias, int N, int H, int W, int Cr, float* z32, void* z16, float* s_out, float* m_out, float* avg_out,
+                 float* max_out, int* pstar, float* q, unsigned char* cstar, float* ws, cudaStream_t st) {
+    if (dtype == SR_F32) return la_fwd_t<float>(x, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q, cstar, ws, st);
+    return la_fwd_t<__nv_bfloat16>(x, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q, cstar, ws, st);
+}
+
+int la_chain_bwd(const float* gz32, const void* gz16, const void* x, int dtype, const float* s, const float* m, const float* avg,
+                 const float* mx, const int* pstar, const float* q, const unsigned char* cstar, const float* fc1, const float* fc2,
+                 const float* w7, const float* Wm, int N, int H, int W, int Cr, void* dx, float* d_fc1, float* d_fc2, float* d_w7,
+                 float* dW, float* db, float* dz_out, float* ws, cudaStream_t st) {
+    if (dtype == SR_F32) return la_bwd_t<float>(gz32, gz16, x, s, m, avg, mx, pstar, q, cstar, fc1, fc2, w7, Wm, N, H, W, Cr, dx, d_fc1, d_fc2, d_w7, dW, db, dz_out, ws, st);
+    return la_bwd_t<__nv_bfloat16>(gz32, gz16, x, s, m, avg, mx, pstar, q, cstar, fc1, fc2, w7, Wm, N, H, W, Cr, dx, d_fc1, d_fc2, d_w7, dW, db, dz_out, ws, st);
+}
+
+}  // namespace sr

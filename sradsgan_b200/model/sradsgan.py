@@ -205,6 +205,9 @@ def _la_forward(mod, out, x):
         return mod.ca(out).float() + x
     if m == 'SA':
         return mod.sa(out).float() + x
+    if (m == 'CA-SA' and mod.addconv and out.shape[1] == 64 and mod.ca.pool_mode == 'Avg|Max' and mod.sa.pool_mode == 'Avg|Max'
+            and mod.sa.conv1.kernel_size == 7 and mod.ca.fc1.out_channels <= 16):
+        return ops.local_attn_chain(out, x, mod.ca, mod.sa, mod.conv)      # the default configuration: one fused chain
     if m in ('CA-SA', 'SA-CA'):
         out = mod.sa(mod.ca(out)) if m == 'CA-SA' else mod.ca(mod.sa(out))
         return mod.conv.fused(out, residual=x, out_dtype=f32) if mod.addconv else out.float() + x

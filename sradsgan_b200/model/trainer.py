@@ -127,22 +127,29 @@ class SRADSGAN(object):
     # ------------------------------------------------------------------------------------------
     def train_step(self, imgs_lr, imgs_hr, fuse_gp_backward=True):
         G, D, Fx = self.generator, self.discriminator, self.feature_extractor
+        mark = getattr(self, "_phase_mark", None) or (lambda name: None)
+        mark("start")
         # ---- generator ----
         self.optimizer_G.zero_grad()
         for p in self.optimizer_D.params:
             p.requires_grad_(False)          # skip D's weight gradients in the G step (discarded by the reference, :865)
         gen_hr = G(imgs_lr)                                                         # :832
+        mark("G_fwd")
         pixel_loss_G = self.criterion_content(gen_hr, imgs_hr)                      # :834
         gen_features = Fx(gen_hr)                                                   # :836
         with torch.no_grad():
             real_features = Fx(imgs_hr)                                             # :837
         loss_content = self.criterion_content(gen_features, real_features)         # :838
+        mark("VGG_fwd_x2")
         loss_gan = self.criterion_raGAN(D(gen_hr), True)                            # :847-848
         loss_G = pixel_loss_G + self.weight_content * loss_content + self.weight_gan * loss_gan   # :852
+        mark("D_adv_fwd")
         self.reducer_G.arm()
         loss_G.backward()
+        mark("G_step_backward")
         scale = self.reducer_G.finish()
         self.optimizer_G.step(grad_scale=scale)                                     # :857-858
+        mark("adam_G")
         for p in self.optimizer_D.params:
             p.requires_grad_(True)
         # ---- discriminator ----
@@ -151,10 +158,13 @@ class SRADSGAN(object):
         loss_real = self.criterion_raGAN(D(imgs_hr), True)                          # :876
         loss_fake = self.criterion_raGAN(D(gen_det), False)                         # :877
         loss_D = loss_real + loss_fake
+        mark("D_real_fake_fwd")
         if self.gp:
             if fuse_gp_backward:
                 gp = self._gp_graph(D, imgs_hr, gen_det, self.grad_penalty_Lp_norm, self.penalty_type)
+                mark("GP_fwd_and_grad")
                 (loss_D + (1.0 + self.lambda_gp) * gp).backward()                   # == :639 followed by :886
+                mark("D_step_backward")
                 loss_D = loss_D.detach() + self.lambda_gp * gp.detach()
             else:
                 gp = self.gradient_penalty(D, imgs_hr, gen_det, self.grad_penalty_Lp_norm, self.penalty_type)
@@ -166,6 +176,7 @@ class SRADSGAN(object):
         self.reducer_D.arm()
         scale = self.reducer_D.finish()
         self.optimizer_D.step(grad_scale=scale)                                     # :887 + clamp :891-892 (fused)
+        mark("adam_D")
         return {"loss_G": loss_G.detach(), "loss_D": loss_D.detach(), "pixel": pixel_loss_G.detach(),
                 "content": loss_content.detach(), "adv": loss_gan.detach(), "gp": gp.detach(), "gen_hr": gen_det}
 

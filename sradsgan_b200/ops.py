@@ -61,6 +61,9 @@ def packed(w, mode, dtype, shuffle_r=0):
 
 def to_compute(x):
     """NCHW-shaped tensor in the compute dtype with NHWC memory."""
+    lp = getattr(x, "_sr_lowp", None)
+    if lp is not None and lp.dtype == config.compute_dtype:
+        return lp                      # twin written by the producing kernel's epilogue: no cast pass
     if x.dtype != config.compute_dtype:
         x = x.to(config.compute_dtype)
     return x.contiguous(memory_format=torch.channels_last)
@@ -175,14 +178,10 @@ class ConvFused(Function):
         x, w, y = ctx.saved_tensors
         g = ctx.g
         g_res = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
-        gpre = gy
-        if ctx.act == ACT_LRELU:
-            gpre = torch.where(y > 0, gy, gy * ctx.slope)
-        elif ctx.act == ACT_RELU:
-            gpre = torch.where(y > 0, gy, torch.zeros_like(gy))
-        if ctx.r and ctx.r > 1:
-            gpre = torch.nn.functional.pixel_unshuffle(gpre, ctx.r)
-        gpre = to_compute(gpre) if gpre.dtype != x.dtype else gpre.contiguous(memory_format=torch.channels_last)
+        if ctx.act != ACT_NONE or (ctx.r and ctx.r > 1):
+            gpre = _lib.backend().act_bwd(gy, y if y is not None else gy, ctx.act, ctx.slope, ctx.r, g, x.dtype)
+        else:
+            gpre = to_compute(gy) if gy.dtype != x.dtype else gy.contiguous(memory_format=torch.channels_last)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = _lib.backend().conv_dgrad(gpre, packed(w, 1, gpre.dtype), g, impl=config.conv_impl)
@@ -197,3 +196,45 @@ def conv2d_fused(x, w, b=None, residual=None, stride=1, pad=0, act=ACT_NONE, slo
         od = out_dtype or x.dtype
         residual = residual.to(od).contiguous(memory_format=torch.channels_last)
     return ConvFused.apply(x, w, b, residual, stride, pad, act, slope, shuffle_r, out_dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused local-attention chain (CLAM -> SLAM -> 1x1 conv -> + residual), C = 64
+# ----------------------------------------------------------------------------------------------
+class LocalAttnChain(Function):
+    """(z32, z16) = Conv1x1(SLAM(CLAM(x))) + t.  z32 continues the fp32 residual trunk, z16 (same values in
+    the compute dtype) feeds the next 3x3 convolution; their gradients are summed inside the backward kernel.
+    In fp32 mode only z32 is produced."""
+
+    @staticmethod
+    def forward(ctx, x, t, fc1, fc2, w7, W, b, lowp):
+        z32, z16, sv = _lib.backend().la_chain_fwd(x, t, fc1, fc2, w7, W, b, want_lowp=lowp)
+        ctx.sv = sv
+        ctx.lowp = lowp
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x, fc1, fc2, w7, W)
+        return (z32, z16) if lowp else z32
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz32, gz16=None):
+        x, fc1, fc2, w7, W = ctx.saved_tensors
+        if gz32 is None and gz16 is None:
+            return (None,) * 8
+        dx, d_fc1, d_fc2, d_w7, dW, db, dz = _lib.backend().la_chain_bwd(gz32, gz16, x, ctx.sv, fc1, fc2, w7, W,
+                                                                          want_dz=ctx.needs_input_grad[1])
+        return dx, dz, d_fc1, d_fc2, d_w7, dW, db, None
+
+
+def local_attn_chain(x, t, ca, sa, conv):
+    """x: conv output (compute dtype), t: residual (fp32 trunk); ca/sa/conv: CLAM, SLAM, 1x1 Conv2d modules.
+    Returns the fp32 trunk tensor; its compute-dtype twin rides along as `._sr_lowp` (picked up by to_compute)."""
+    x = to_compute(x)
+    t = t.float().contiguous(memory_format=torch.channels_last)
+    lowp = config.compute_dtype != torch.float32
+    out = LocalAttnChain.apply(x, t, ca.fc1.weight, ca.fc2.weight, sa.conv1.weight, conv.weight, conv.bias, lowp)
+    if lowp:
+        z32, z16 = out
+        z32._sr_lowp = z16
+        return z32
+    return out

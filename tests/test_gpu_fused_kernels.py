@@ -1,0 +1,74 @@
+"""GPU: the fused non-convolution kernels through the C ABI vs their documented-semantics emulation
+(oracle/ops_emu.py, which is the oracle's CLAM/SLAM/conv math + torch autograd on CPU)."""
+import pytest
+import torch
+
+from oracle import ops_emu
+from sradsgan_b200._lib import ACT_LRELU, ACT_RELU, conv_geom
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    from sradsgan_b200 import _lib
+    b = _lib.CudaBackend()
+    b.device_check()
+    return b
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _chain_inputs(n, h, w, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 64, h, w, generator=g).to(dtype)
+    t = torch.randn(n, 64, h, w, generator=g)
+    fc1 = torch.randn(4, 64, 1, 1, generator=g) * 0.3
+    fc2 = torch.randn(64, 4, 1, 1, generator=g) * 0.3
+    w7 = torch.randn(1, 2, 7, 7, generator=g) * 0.2
+    W = torch.randn(64, 64, 1, 1, generator=g) * 0.125
+    b = torch.randn(64, generator=g) * 0.1
+    return x, t, fc1, fc2, w7, W, b
+
+
+@pytest.mark.parametrize("shape", [(2, 54, 54), (1, 13, 17), (3, 24, 24), (1, 7, 5)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_la_chain_forward_backward(be, shape, dtype):
+    n, h, w = shape
+    x, t, fc1, fc2, w7, W, b = _chain_inputs(n, h, w, dtype, seed=h * w)
+    emu = ops_emu.EmuBackend()
+    z_ref, _, sv_ref = emu.la_chain_fwd(x, t, fc1, fc2, w7, W, b, want_lowp=False)
+    cu = [v.cuda() for v in (x, t, fc1, fc2, w7, W, b)]
+    cu[0] = cu[0].contiguous(memory_format=torch.channels_last)
+    z32, z16, sv = be.la_chain_fwd(*cu, want_lowp=True)
+    tol = 2e-5 if dtype == torch.float32 else 2e-5     # x is already rounded; all chain math is fp32
+    assert rel(z32, z_ref) < tol
+    assert rel(z16, z_ref) < (1e-6 if dtype == torch.float32 else 4e-3)
+    g = torch.Generator().manual_seed(3)
+    gz32 = torch.randn(n, 64, h, w, generator=g)
+    gz16 = torch.randn(n, 64, h, w, generator=g).to(dtype)
+    ref = emu.la_chain_bwd(gz32, gz16, x, sv_ref, fc1, fc2, w7, W)
+    got = be.la_chain_bwd(gz32.cuda(), gz16.cuda(), cu[0], sv, cu[2], cu[3], cu[4], cu[5])
+    names = ["dx", "d_fc1", "d_fc2", "d_w7", "dW", "db", "dz"]
+    for nm, a, r in zip(names, got, ref):
+        lim = 4e-3 if (nm == "dx" and dtype == torch.bfloat16) else 2e-4
+        assert rel(a, r) < lim, (nm, rel(a, r))
+    # only the fp32 gradient present: dz is the incoming gradient itself
+    got2 = be.la_chain_bwd(gz32.cuda(), None, cu[0], sv, cu[2], cu[3], cu[4], cu[5])
+    ref2 = emu.la_chain_bwd(gz32, None, x, sv_ref, fc1, fc2, w7, W)
+    assert rel(got2[4], ref2[4]) < 2e-4 and rel(got2[0], ref2[0]) < (4e-3 if dtype == torch.bfloat16 else 2e-4)
+
+
+@pytest.mark.parametrize("r,act", [(1, ACT_LRELU), (2, ACT_LRELU), (3, ACT_LRELU), (1, ACT_RELU)])
+def test_act_bwd(be, r, act):
+    emu = ops_emu.EmuBackend()
+    g = conv_geom((2, 64, 10, 12), (64 * r * r, 64, 3, 3), 1, 1)
+    gen = torch.Generator().manual_seed(r)
+    y = torch.randn(2, 64, 10 * r, 12 * r, generator=gen).bfloat16()
+    gy = torch.randn(2, 64, 10 * r, 12 * r, generator=gen)
+    ref = emu.act_bwd(gy, y, act, 0.2, r, g, torch.bfloat16)
+    got = be.act_bwd(gy.cuda(), y.cuda(), act, 0.2, r, g, torch.bfloat16)
+    assert got.shape == ref.shape and rel(got, ref) < 1e-6
