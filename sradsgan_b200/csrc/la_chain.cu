@@ -186,7 +186,7 @@ la_apply_kernel(const T* __restrict__ x, const float* __restrict__ s, const floa
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
-    const float4 bv = *reinterpret_cast<const float4*>(bias + tc * 4);
+    const float4 bv = make_float4(bias[tc * 4], bias[tc * 4 + 1], bias[tc * 4 + 2], bias[tc * 4 + 3]);   // caller pointer: no alignment assumed
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const long long pix = p0 + tp * 4 + i;
@@ -476,7 +476,7 @@ size_t la_workspace_bytes(int N, int H, int W) {
     const int P = H * W, S = la_slices(P);
     // fwd: psum, pmax, pidx ; bwd: g, dm, dq, ds, da, dmx
     size_t fwd = (size_t)N * S * LA_C * 12;
-    size_t bwd = (size_t)N * P * LA_C * 4 + (size_t)N * P * 4 + (size_t)N * P * 8 + (size_t)N * LA_C * 12;
+    size_t bwd = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + ((size_t)N * P + 4) * 8 + (size_t)N * LA_C * 12;
     return (fwd > bwd ? fwd : bwd) + 256;
 }
 
@@ -503,7 +503,8 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
                     float* d_fc2, float* d_w7, float* dW, float* db, float* dz_out, float* ws, cudaStream_t st) {
     const int P = H * W, S = la_slices(P);
     const long long NP = (long long)N * P;
-    float* g = ws; float* dm = g + (size_t)NP * LA_C; float* dq = dm + NP; float* ds = dq + NP * 2;
+    const size_t npa = ((size_t)NP + 3) & ~(size_t)3;           // keep every sub-buffer 16-byte aligned
+    float* g = ws; float* dm = g + (size_t)NP * LA_C; float* dq = dm + npa; float* ds = dq + npa * 2;
     float* da = ds + (size_t)N * LA_C; float* dmx = da + (size_t)N * LA_C;
     cudaMemsetAsync(ds, 0, sizeof(float) * N * LA_C, st);
     const int tiles = (int)cdiv(NP, 64);

@@ -23,8 +23,8 @@ class FlatAdam:
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
-        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        total = sum((p.numel() + 3) // 4 * 4 for p in self.params)     # every parameter starts 16-byte aligned
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -36,7 +36,7 @@ class FlatAdam:
             p.data = self.flat_param[off:off + k].view(p.shape)
             p.grad = self.flat_grad[off:off + k].view(p.shape)
             self.offsets[n] = (off, k)
-            off += k
+            off += (k + 3) // 4 * 4
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps}]
         self.clamp = clamp
         self.step_count = 0
