@@ -4,7 +4,7 @@ set +e
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 if [ "$1" != "quick" ]; then
-echo "== simt kernels"; timeout -s KILL 600 python -W ignore -m pytest tests/test_gpu_conv_kernels.py -m gpu -q -k "simt" -x --timeout 300 2>&1 | tail -15 | tee gpurun_out/t_simt.log
+echo "== simt kernels"; timeout -s KILL 600 python -W ignore -m pytest tests/test_gpu_conv_kernels.py -m gpu -q -k "simt or thin" -x --timeout 300 2>&1 | tail -15 | tee gpurun_out/t_simt.log
 echo "== tcgen05 kernels"; timeout -s KILL 600 python -W ignore -m pytest tests/test_gpu_conv_kernels.py -m gpu -q -k "tcgen05 or full_size" --timeout 120 2>&1 | tail -40 | tee gpurun_out/t_tc.log
 fi
 echo "== fused kernels"; timeout -s KILL 600 python -W ignore -m pytest tests/test_gpu_fused_kernels.py -m gpu -q --timeout 120 2>&1 | tail -30 | tee gpurun_out/t_fused.log

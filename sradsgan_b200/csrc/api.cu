@@ -37,6 +37,11 @@ int conv_tc_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const
 // conv_tc_wgrad.cu
 bool conv_tc_wgrad_supported(const sr_conv_desc*);
 int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
+// conv_thin.cu
+bool thin_fwd_supported(const sr_conv_desc*, bool dgrad);
+bool thin_wgrad_supported(const sr_conv_desc*);
+int thin_fwd_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, void*, cudaStream_t);
+int thin_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
 // la_chain.cu
 size_t la_workspace_bytes(int, int, int);
 int la_chain_fwd(const void*, int, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
@@ -119,6 +124,7 @@ int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w, const flo
         return SR_ERR_UNSUPPORTED;
     }
     if (tc_ok && d->impl != SR_IMPL_SIMT) return conv_tc_run(d, false, x, w, bias, residual, y, (cudaStream_t)stream);
+    if (d->impl == SR_IMPL_AUTO && !residual && thin_fwd_supported(d, false)) return thin_fwd_run(d, false, x, w, bias, y, (cudaStream_t)stream);
     return conv_fwd_simt(d, x, w, bias, residual, y, (cudaStream_t)stream);
 }
 
@@ -134,6 +140,7 @@ int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* wt, void*
         return SR_ERR_UNSUPPORTED;
     }
     if (tc_ok && d->impl != SR_IMPL_SIMT) return conv_tc_run(d, true, dy, wt, nullptr, nullptr, dx, (cudaStream_t)stream);
+    if (d->impl == SR_IMPL_AUTO && thin_fwd_supported(d, true)) return thin_fwd_run(d, true, dy, wt, nullptr, dx, (cudaStream_t)stream);
     return conv_dgrad_simt(d, dy, wt, dx, (cudaStream_t)stream);
 }
 
@@ -152,6 +159,7 @@ int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float*
         return SR_ERR_UNSUPPORTED;
     }
     if (tc_ok && d->impl != SR_IMPL_SIMT) rc = conv_tc_wgrad_run(d, x, dy, dw, st);
+    else if (d->impl == SR_IMPL_AUTO && thin_wgrad_supported(d)) rc = thin_wgrad_run(d, x, dy, dw, st);
     else rc = conv_wgrad_simt(d, x, dy, dw, st);
     if (rc) return rc;
     if (dbias) rc = colsum(dy, d->in_dtype, (long long)d->N * d->Ho * d->Wo, d->Cout, dbias, nullptr, accumulate, st);

@@ -1,0 +1,396 @@
+// "Thin" convolutions: one side of the layer has <= 4 channels (RGB in / RGB out / 1-channel critic map).
+// These layers carry <1 % of the FLOPs but touch the largest tensors (216x216 x batch), so they are HBM
+// bound: an implicit-GEMM tile wastes >90 % of its lanes on them.  Direct kernels:
+//   thin_cin  : Cs <= 4  -> Cd wide   (conv1, MSB.conv1/2.0/3, D.model.0, VGG.0 forward; conv3 dgrad)
+//   thin_cout : Cs wide  -> Cd <= 4   (conv3, D.model.25 forward; D.model.0 / VGG.0 dgrad)
+//   thin_wgrad_ci / thin_wgrad_co : the matching weight gradients (fp32 atomics into OIHW)
+// stride 1 only; k in {1,3,5,7}.  Weights use the same packed layouts as the implicit-GEMM kernels
+// ([tap][Cd][Cs]); `flip` mirrors the tap offsets so that a stride-1 dgrad is the forward kernel on dy.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sr {
+
+struct ThinParams {
+    int N, H, W;          // spatial size (same for source and destination: stride 1, "same" padding handled by pad)
+    int Ho, Wo;
+    int Cs, Cd;           // source / destination channels
+    int k, pad, flip;
+    int act;
+    float slope;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Cs <= 4 -> Cd (multiple of 16). block = 64 pixels x 4 channel groups of 16.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut, int K, int CS>
+__global__ void __launch_bounds__(256)
+thin_cin_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restrict__ wpk, const float* __restrict__ bias,
+                TOut* __restrict__ dst) {
+    extern __shared__ __align__(16) float thin_smem[];     // ws[tap][cs][Cd]
+    constexpr int TAPS = K * K, NIN = TAPS * CS;
+    for (int i = threadIdx.x; i < NIN * p.Cd; i += 256) {
+        const int cd = i % p.Cd; const int r = i / p.Cd; const int cs = r % CS; const int tap = r / CS;
+        thin_smem[i] = to_f32<TIn>(wpk[((long long)tap * p.Cd + cd) * CS + cs]);
+    }
+    __syncthreads();
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
+    if (pix >= M) return;
+    const int cg = threadIdx.x & 3;
+    const int ox = (int)(pix % p.Wo); const long long q = pix / p.Wo;
+    const int oy = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
+    float in[NIN];
+#pragma unroll
+    for (int tap = 0; tap < TAPS; ++tap) {
+        const int ky = tap / K, kx = tap - ky * K;
+        const int oyy = p.flip ? (K - 1 - ky) : ky, oxx = p.flip ? (K - 1 - kx) : kx;
+        const int sy = oy + oyy - p.pad, sx = ox + oxx - p.pad;
+        const bool ok = sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
+        const TIn* sp = src + (((long long)n * p.H + sy) * p.W + sx) * CS;
+#pragma unroll
+        for (int cs = 0; cs < CS; ++cs) in[tap * CS + cs] = ok ? to_f32<TIn>(sp[cs]) : 0.f;
+    }
+    for (int c0 = cg * 16; c0 < p.Cd; c0 += 64) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) {
+            const float v = in[i];
+            const float4* wr = reinterpret_cast<const float4*>(thin_smem + (size_t)i * p.Cd + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = wr[j];
+                acc[j * 4] = fmaf(v, w.x, acc[j * 4]); acc[j * 4 + 1] = fmaf(v, w.y, acc[j * 4 + 1]);
+                acc[j * 4 + 2] = fmaf(v, w.z, acc[j * 4 + 2]); acc[j * 4 + 3] = fmaf(v, w.w, acc[j * 4 + 3]);
+            }
+        }
+        TOut* o = dst + pix * p.Cd + c0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            store4<TOut>(o + j, apply_act(acc[j], p.act, p.slope), apply_act(acc[j + 1], p.act, p.slope),
+                         apply_act(acc[j + 2], p.act, p.slope), apply_act(acc[j + 3], p.act, p.slope));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cs (multiple of 64) -> Cd <= 4.  block = 8 warps, tile = 8 rows x 32 pixels, halo tile of one 64-channel
+// block of the source in shared memory; a warp owns one tile row, lanes split the 64 channels.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_TH = 8, TC_TW = 32;
+
+template <typename TIn, typename TOut, int K>
+__global__ void __launch_bounds__(256)
+thin_cout_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restrict__ wpk, const float* __restrict__ bias,
+                 TOut* __restrict__ dst) {
+    extern __shared__ __align__(16) unsigned char thin_raw[];
+    TIn* tile = reinterpret_cast<TIn*>(thin_raw);                       // [(TH+K-1)][(TW+K-1)][64]
+    constexpr int TAPS = K * K;
+    constexpr int th = TC_TH + K - 1, tw = TC_TW + K - 1;
+    const int tiles_x = (p.Wo + TC_TW - 1) / TC_TW, tiles_y = (p.Ho + TC_TH - 1) / TC_TH;
+    int b = blockIdx.x;
+    const int tx = b % tiles_x; b /= tiles_x;
+    const int ty = b % tiles_y; const int n = b / tiles_y;
+    const int x0 = tx * TC_TW, y0 = ty * TC_TH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float res[4] = {0.f, 0.f, 0.f, 0.f};                                // outputs of pixel (row = warp, col = lane)
+    for (int cb = 0; cb < p.Cs; cb += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < th * tw * 8; i += 256) {         // 8 channels per thread-iteration
+            const int v = i & 7; const int pp = i >> 3;
+            const int c = pp % tw, r = pp / tw;
+            const int sy = y0 + r - p.pad, sx = x0 + c - p.pad;
+            TIn* d = tile + ((size_t)r * tw + c) * 64 + v * 8;
+            if (sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) {
+                const TIn* sp = src + (((long long)n * p.H + sy) * p.W + sx) * p.Cs + cb + v * 8;
+#pragma unroll
+                for (int j = 0; j < 8; j += 4) { float t4[4]; load4<TIn>(sp + j, t4); store4<TIn>(d + j, t4[0], t4[1], t4[2], t4[3]); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j += 4) store4<TIn>(d + j, 0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        // this lane's weights for channels (2*lane, 2*lane+1) of the block: w[tap][cd][cs]
+        float w0[TAPS][4], w1[TAPS][4];
+#pragma unroll
+        for (int tap = 0; tap < TAPS; ++tap)
+#pragma unroll
+            for (int cd = 0; cd < 4; ++cd) {
+                if (cd < p.Cd) {
+                    const TIn* wp = wpk + ((long long)tap * p.Cd + cd) * p.Cs + cb + lane * 2;
+                    w0[tap][cd] = to_f32<TIn>(wp[0]); w1[tap][cd] = to_f32<TIn>(wp[1]);
+                } else { w0[tap][cd] = 0.f; w1[tap][cd] = 0.f; }
+            }
+        __syncthreads();
+        for (int px = 0; px < TC_TW; ++px) {
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int ky = tap / K, kx = tap - ky * K;
+                const int oyy = p.flip ? (K - 1 - ky) : ky, oxx = p.flip ? (K - 1 - kx) : kx;
+                const TIn* tp = tile + ((size_t)(warp + oyy) * tw + (px + oxx)) * 64 + lane * 2;
+                const float v0 = to_f32<TIn>(tp[0]), v1 = to_f32<TIn>(tp[1]);
+#pragma unroll
+                for (int cd = 0; cd < 4; ++cd) a[cd] = fmaf(v0, w0[tap][cd], fmaf(v1, w1[tap][cd], a[cd]));
+            }
+#pragma unroll
+            for (int cd = 0; cd < 4; ++cd) {
+                float v = a[cd];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == px) res[cd] += v;
+            }
+        }
+    }
+    const int oy = y0 + warp, ox = x0 + lane;
+    if (oy < p.Ho && ox < p.Wo) {
+        TOut* o = dst + (((long long)n * p.Ho + oy) * p.Wo + ox) * p.Cd;
+        for (int cd = 0; cd < p.Cd; ++cd) o[cd] = from_f32<TOut>(apply_act(res[cd] + (bias ? bias[cd] : 0.f), p.act, p.slope));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradients
+// ---------------------------------------------------------------------------------------------
+// thin input (Cin <= 4), wide output (Cout multiple of 64): dw[co][ci][tap] += sum_pix dy[pix][co] * x[pix@tap][ci]
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+thin_wgrad_ci_kernel(ThinParams p, const TIn* __restrict__ x, const TIn* __restrict__ dy, float* __restrict__ dw, int chunks_per_block) {
+    // p.Cs = Cin (thin), p.Cd = Cout (wide); blockIdx.y = 64-wide block of output channels
+    __shared__ __align__(16) float xs[64][40];          // per pixel: taps*Cin (<= 36) source values
+    __shared__ float red[4][64];
+    const int taps = p.k * p.k, nin = taps * p.Cs;
+    const int s = threadIdx.x >> 6, c = threadIdx.x & 63;
+    const int co = blockIdx.y * 64 + c;
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    float acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.f;
+    for (int ch = 0; ch < chunks_per_block; ++ch) {
+        const long long p0 = ((long long)blockIdx.x * chunks_per_block + ch) * 64;
+        if (p0 >= M) break;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * nin; i += 256) {
+            const int pl = i / nin, r = i - pl * nin;
+            const int tap = r / p.Cs, ci = r - tap * p.Cs;
+            const long long pix = p0 + pl;
+            float v = 0.f;
+            if (pix < M) {
+                const int ox = (int)(pix % p.Wo); const long long q = pix / p.Wo;
+                const int oy = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
+                const int ky = tap / p.k, kx = tap - ky * p.k;
+                const int sy = oy + ky - p.pad, sx = ox + kx - p.pad;
+                if (sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) v = to_f32<TIn>(x[(((long long)n * p.H + sy) * p.W + sx) * p.Cs + ci]);
+            }
+            xs[pl][r] = v;
+        }
+        for (int i = threadIdx.x; i < 64 * (36 - nin); i += 256) xs[i / (36 - nin)][nin + i % (36 - nin)] = 0.f;
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+            const int pl = s * 16 + j;
+            const long long pix = p0 + pl;
+            const float g = (pix < M) ? to_f32<TIn>(dy[pix * p.Cd + co]) : 0.f;
+            const float4* xr = reinterpret_cast<const float4*>(&xs[pl][0]);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const float4 v = xr[i];
+                acc[i * 4] = fmaf(g, v.x, acc[i * 4]); acc[i * 4 + 1] = fmaf(g, v.y, acc[i * 4 + 1]);
+                acc[i * 4 + 2] = fmaf(g, v.z, acc[i * 4 + 2]); acc[i * 4 + 3] = fmaf(g, v.w, acc[i * 4 + 3]);
+            }
+        }
+    }
+    // combine the 4 pixel streams, then one atomic per output element
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+        if (i < nin) {            // uniform across the block
+            __syncthreads();
+            red[s][c] = acc[i];
+            __syncthreads();
+            if (s == 0) {
+                const float v = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+                const int tap = i / p.Cs, ci = i - tap * p.Cs;
+                atomicAdd(dw + ((long long)co * p.Cs + ci) * taps + tap, v);
+            }
+        }
+    }
+}
+
+// wide input (Cin multiple of 64), thin output (Cout <= 4): same halo tile as thin_cout; thread = (pixel stream, ci)
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+thin_wgrad_co_kernel(ThinParams p, const TIn* __restrict__ x, const TIn* __restrict__ dy, float* __restrict__ dw) {
+    // p.Cs = Cin (wide), p.Cd = Cout (thin); blockIdx.y = 64-wide block of input channels; 3x3 only
+    extern __shared__ __align__(16) unsigned char thin_raw[];
+    constexpr int k = 3, taps = 9;
+    constexpr int th = TC_TH + k - 1, tw = TC_TW + k - 1;
+    TIn* tile = reinterpret_cast<TIn*>(thin_raw);                                  // [th][tw][64]
+    float* gs = reinterpret_cast<float*>(thin_raw + (size_t)th * tw * 64 * sizeof(TIn));   // [TH*TW][4] dy of the tile
+    float* red = gs + TC_TH * TC_TW * 4;                                            // [4][64]
+    const int tiles_x = (p.Wo + TC_TW - 1) / TC_TW, tiles_y = (p.Ho + TC_TH - 1) / TC_TH;
+    const int total_tiles = tiles_x * tiles_y * p.N;
+    const int cb = blockIdx.y * 64;
+    const int s = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float acc[9][4];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int b = blockIdx.x; b < total_tiles; b += gridDim.x) {
+        int bb = b;
+        const int tx = bb % tiles_x; bb /= tiles_x;
+        const int ty = bb % tiles_y; const int n = bb / tiles_y;
+        const int x0 = tx * TC_TW, y0 = ty * TC_TH;
+        __syncthreads();
+        const int vec_per_pix = 8;
+        for (int i = threadIdx.x; i < th * tw * vec_per_pix; i += 256) {
+            const int v = i % vec_per_pix; const int pp = i / vec_per_pix;
+            const int cc = pp % tw, r = pp / tw;
+            const int sy = y0 + r - p.pad, sx = x0 + cc - p.pad;
+            TIn* d = tile + ((size_t)r * tw + cc) * 64 + v * 8;
+            if (sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) {
+                const TIn* sp = x + (((long long)n * p.H + sy) * p.W + sx) * p.Cs + cb + v * 8;
+#pragma unroll
+                for (int j = 0; j < 8; j += 4) { float t4[4]; load4<TIn>(sp + j, t4); store4<TIn>(d + j, t4[0], t4[1], t4[2], t4[3]); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j += 4) store4<TIn>(d + j, 0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        for (int i = threadIdx.x; i < TC_TH * TC_TW; i += 256) {
+            const int r = i / TC_TW, cc = i % TC_TW;
+            const int oy = y0 + r, ox = x0 + cc;
+            for (int cd = 0; cd < 4; ++cd)
+                gs[i * 4 + cd] = (cd < p.Cd && oy < p.Ho && ox < p.Wo) ? to_f32<TIn>(dy[(((long long)n * p.Ho + oy) * p.Wo + ox) * p.Cd + cd]) : 0.f;
+        }
+        __syncthreads();
+        // stream s handles tile rows 2s, 2s+1
+        for (int r = 2 * s; r < 2 * s + 2; ++r) {
+            for (int cc = 0; cc < TC_TW; ++cc) {
+                const float4 g = *reinterpret_cast<const float4*>(gs + (r * TC_TW + cc) * 4);
+#pragma unroll
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int ky = tap / k, kx = tap - ky * k;
+                    const float v = to_f32<TIn>(tile[((size_t)(r + ky) * tw + (cc + kx)) * 64 + c]);
+                    acc[tap][0] = fmaf(g.x, v, acc[tap][0]); acc[tap][1] = fmaf(g.y, v, acc[tap][1]);
+                    acc[tap][2] = fmaf(g.z, v, acc[tap][2]); acc[tap][3] = fmaf(g.w, v, acc[tap][3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int tap = 0; tap < taps; ++tap)
+#pragma unroll
+        for (int cd = 0; cd < 4; ++cd) {
+            if (cd < p.Cd) {       // uniform across the block
+                __syncthreads();
+                red[s * 64 + c] = acc[tap][cd];
+                __syncthreads();
+                if (s == 0) atomicAdd(dw + ((long long)cd * p.Cs + cb + c) * taps + tap, red[c] + red[64 + c] + red[128 + c] + red[192 + c]);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static bool thin_geom_ok(const sr_conv_desc* d) {
+    return d->stride == 1 && d->kh == d->kw && (d->kh == 1 || d->kh == 3) && (d->shuffle_r <= 1);
+}
+
+static bool thin_cin_combo(int k, int cs) { return (k == 3 && (cs == 3 || cs == 1)) || (k == 1 && cs == 3); }
+
+bool thin_fwd_supported(const sr_conv_desc* d, bool dgrad) {
+    if (!thin_geom_ok(d)) return false;
+    const int Cs = dgrad ? d->Cout : d->Cin, Cd = dgrad ? d->Cin : d->Cout;
+    if (Cs <= 4 && Cd % 64 == 0 && Cd <= 512 && thin_cin_combo(d->kh, Cs)) return true;
+    if (Cd <= 4 && Cs % 64 == 0) return true;
+    return false;
+}
+
+bool thin_wgrad_supported(const sr_conv_desc* d) {
+    if (!thin_geom_ok(d)) return false;
+    if (d->Cin <= 4 && d->Cout % 64 == 0 && d->kh * d->kw * d->Cin <= 36) return true;
+    if (d->Cout <= 4 && d->Cin % 64 == 0 && d->kh == 3) return true;
+    return false;
+}
+
+template <typename TIn, typename TOut, int K, int CS>
+static void thin_cin_launch(const ThinParams& p, const void* src, const void* w, const float* bias, void* dst, cudaStream_t st) {
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const size_t smem = sizeof(float) * K * K * CS * p.Cd;
+    thin_cin_kernel<TIn, TOut, K, CS><<<(unsigned)cdiv(M, 64), 256, smem, st>>>(p, (const TIn*)src, (const TIn*)w, bias, (TOut*)dst);
+}
+
+template <typename TIn, typename TOut, int K>
+static void thin_cout_launch(const ThinParams& p, const void* src, const void* w, const float* bias, void* dst, cudaStream_t st) {
+    constexpr int th = TC_TH + K - 1, tw = TC_TW + K - 1;
+    const size_t smem = (size_t)th * tw * 64 * sizeof(TIn);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(thin_cout_kernel<TIn, TOut, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+    const int tiles = (int)(cdiv(p.Wo, TC_TW) * cdiv(p.Ho, TC_TH) * p.N);
+    thin_cout_kernel<TIn, TOut, K><<<tiles, 256, smem, st>>>(p, (const TIn*)src, (const TIn*)w, bias, (TOut*)dst);
+}
+
+template <typename TIn, typename TOut>
+static int thin_fwd_t(const ThinParams& p, const void* src, const void* w, const float* bias, void* dst, cudaStream_t st) {
+    if (p.Cs <= 4) {
+        if (p.k == 3 && p.Cs == 3) thin_cin_launch<TIn, TOut, 3, 3>(p, src, w, bias, dst, st);
+        else if (p.k == 3 && p.Cs == 1) thin_cin_launch<TIn, TOut, 3, 1>(p, src, w, bias, dst, st);
+        else thin_cin_launch<TIn, TOut, 1, 3>(p, src, w, bias, dst, st);
+    } else {
+        if (p.k == 3) thin_cout_launch<TIn, TOut, 3>(p, src, w, bias, dst, st);
+        else thin_cout_launch<TIn, TOut, 1>(p, src, w, bias, dst, st);
+    }
+    count_launch();
+    return check_launch("thin conv kernel");
+}
+
+int thin_fwd_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* w, const float* bias, void* dst, cudaStream_t st) {
+    ThinParams p;
+    p.N = d->N;
+    p.H = dgrad ? d->Ho : d->H; p.W = dgrad ? d->Wo : d->W;
+    p.Ho = dgrad ? d->H : d->Ho; p.Wo = dgrad ? d->W : d->Wo;
+    p.Cs = dgrad ? d->Cout : d->Cin; p.Cd = dgrad ? d->Cin : d->Cout;
+    p.k = d->kh; p.pad = dgrad ? (d->kh - 1 - d->pad) : d->pad; p.flip = dgrad ? 1 : 0;
+    p.act = dgrad ? SR_ACT_NONE : d->act; p.slope = d->slope;
+    const bool in_bf = d->in_dtype == SR_BF16, out_bf = d->out_dtype == SR_BF16;
+    if (in_bf && out_bf) return thin_fwd_t<__nv_bfloat16, __nv_bfloat16>(p, src, w, bias, dst, st);
+    if (in_bf) return thin_fwd_t<__nv_bfloat16, float>(p, src, w, bias, dst, st);
+    if (out_bf) return thin_fwd_t<float, __nv_bfloat16>(p, src, w, bias, dst, st);
+    return thin_fwd_t<float, float>(p, src, w, bias, dst, st);
+}
+
+template <typename TIn>
+static int thin_wgrad_t(const ThinParams& p, bool thin_ci, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    if (thin_ci) {
+        const long long chunks = cdiv(M, 64);
+        const int cpb = (int)std::max<long long>(1, cdiv(chunks, 148 * 4));
+        dim3 grid((unsigned)cdiv(chunks, cpb), (unsigned)(p.Cd / 64));
+        thin_wgrad_ci_kernel<TIn><<<grid, 256, 0, st>>>(p, (const TIn*)x, (const TIn*)dy, dw, cpb);
+    } else {
+        const int th = TC_TH + p.k - 1, tw = TC_TW + p.k - 1;
+        const size_t smem = (size_t)th * tw * 64 * sizeof(TIn) + sizeof(float) * (TC_TH * TC_TW * 4 + 256);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(thin_wgrad_co_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); attr = true; }
+        const int tiles = (int)(cdiv(p.Wo, TC_TW) * cdiv(p.Ho, TC_TH) * p.N);
+        dim3 grid((unsigned)std::min(tiles, 148 * 2), (unsigned)(p.Cs / 64));
+        thin_wgrad_co_kernel<TIn><<<grid, 256, smem, st>>>(p, (const TIn*)x, (const TIn*)dy, dw);
+    }
+    count_launch();
+    return check_launch("thin wgrad kernel");
+}
+
+int thin_wgrad_run(const sr_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    ThinParams p;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Ho = d->Ho; p.Wo = d->Wo;
+    p.Cs = d->Cin; p.Cd = d->Cout; p.k = d->kh; p.pad = d->pad; p.flip = 0; p.act = 0; p.slope = 0.f;
+    const bool thin_ci = d->Cin <= 4;
+    if (d->in_dtype == SR_BF16) return thin_wgrad_t<__nv_bfloat16>(p, thin_ci, x, dy, dw, st);
+    return thin_wgrad_t<float>(p, thin_ci, x, dy, dw, st);
+}
+
+}  // namespace sr

@@ -11,6 +11,8 @@
 // for the residual trunk and once in the compute dtype for the next 3x3 conv) and 6 backward.
 // All reductions are warp-shuffle / shared-memory based with fp32 accumulation; every kernel is HBM/L2
 // bound.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sr {
@@ -350,14 +352,14 @@ la_conv7_dgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m,
     dq[pix * 2] = a; dq[pix * 2 + 1] = b;
 }
 
-// dw7[ch][ky][kx] += sum_p de[p] * q[p + off][ch]   (one block per filter element)
+// dw7[ch][ky][kx] += sum_p de[p] * q[p + off][ch]   (grid: filter element x pixel slice)
 __global__ void __launch_bounds__(256)
 la_conv7_wgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m, const float* __restrict__ q, int N, int H, int W,
                       float* __restrict__ dw7) {
     const int idx = blockIdx.x, ch = idx / 49, ky = (idx % 49) / 7, kx = idx % 7;
     const long long NP = (long long)N * H * W;
     float acc = 0.f;
-    for (long long pix = threadIdx.x; pix < NP; pix += blockDim.x) {
+    for (long long pix = (long long)blockIdx.y * blockDim.x + threadIdx.x; pix < NP; pix += (long long)gridDim.y * blockDim.x) {
         const int x = (int)(pix % W); const long long r = pix / W;
         const int y = (int)(r % H); const int n = (int)(r / H);
         const int yy = y + ky - 3, xx = x + kx - 3;
@@ -409,42 +411,33 @@ la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, c
     }
 }
 
-// gate backward (tiny): one block, loops over images
+// gate backward (tiny): one block per image; weight gradients via fp32 atomics
 __global__ void __launch_bounds__(LA_C)
 la_gate_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ s, const float* __restrict__ avg, const float* __restrict__ mx,
                    const float* __restrict__ fc1, const float* __restrict__ fc2, int N, int Cr,
                    float* __restrict__ d_fc1, float* __restrict__ d_fc2, float* __restrict__ da, float* __restrict__ dmx) {
-    const int c = threadIdx.x;
+    const int c = threadIdx.x, n = blockIdx.x;
     __shared__ float a[LA_C], m[LA_C], dov[LA_C], pa[16], pm[16], dha[16], dhm[16];
-    float acc1[16], acc2[16];
-    for (int j = 0; j < 16; ++j) { acc1[j] = 0.f; acc2[j] = 0.f; }
-    for (int n = 0; n < N; ++n) {
-        __syncthreads();
-        a[c] = avg[n * LA_C + c]; m[c] = mx[n * LA_C + c];
-        const float sv = s[n * LA_C + c];
-        dov[c] = ds[n * LA_C + c] * sv * (1.f - sv);
-        __syncthreads();
-        if (c < Cr) {
-            float u = 0.f, v = 0.f, d = 0.f;
-            for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * m[k]; d += fc2[k * Cr + c] * dov[k]; }
-            pa[c] = u; pm[c] = v;
-            dha[c] = u > 0.f ? d : 0.f;
-            dhm[c] = v > 0.f ? d : 0.f;
-        }
-        __syncthreads();
-        float dav = 0.f, dmv = 0.f;
-        for (int j = 0; j < Cr; ++j) {
-            acc2[j] += dov[c] * (fmaxf(pa[j], 0.f) + fmaxf(pm[j], 0.f));     // d_fc2[c][j]
-            acc1[j] += dha[j] * a[c] + dhm[j] * m[c];                         // d_fc1[j][c]
-            dav += fc1[j * LA_C + c] * dha[j];
-            dmv += fc1[j * LA_C + c] * dhm[j];
-        }
-        da[n * LA_C + c] = dav; dmx[n * LA_C + c] = dmv;
+    a[c] = avg[n * LA_C + c]; m[c] = mx[n * LA_C + c];
+    const float sv = s[n * LA_C + c];
+    dov[c] = ds[n * LA_C + c] * sv * (1.f - sv);
+    __syncthreads();
+    if (c < Cr) {
+        float u = 0.f, v = 0.f, d = 0.f;
+        for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * m[k]; d += fc2[k * Cr + c] * dov[k]; }
+        pa[c] = u; pm[c] = v;
+        dha[c] = u > 0.f ? d : 0.f;
+        dhm[c] = v > 0.f ? d : 0.f;
     }
+    __syncthreads();
+    float dav = 0.f, dmv = 0.f;
     for (int j = 0; j < Cr; ++j) {
-        d_fc2[c * Cr + j] += acc2[j];
-        d_fc1[j * LA_C + c] += acc1[j];
+        atomicAdd(d_fc2 + c * Cr + j, dov[c] * (fmaxf(pa[j], 0.f) + fmaxf(pm[j], 0.f)));
+        atomicAdd(d_fc1 + j * LA_C + c, dha[j] * a[c] + dhm[j] * m[c]);
+        dav += fc1[j * LA_C + c] * dha[j];
+        dmv += fc1[j * LA_C + c] * dhm[j];
     }
+    da[n * LA_C + c] = dav; dmx[n * LA_C + c] = dmv;
 }
 
 // dx += da/P  (+ dmx at the arg-max pixel)
@@ -515,9 +508,9 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
     if (!attr[ai]) { cudaFuncSetAttribute(la_bwd_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr[ai] = true; }
     la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
     la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
-    la_conv7_wgrad_kernel<<<98, 256, 0, st>>>(dm, m, q, N, H, W, d_w7);
+    la_conv7_wgrad_kernel<<<dim3(98, (unsigned)std::min<long long>(24, cdiv(NP, 1024))), 256, 0, st>>>(dm, m, q, N, H, W, d_w7);
     la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds);
-    la_gate_bwd_kernel<<<1, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, N, Cr, d_fc1, d_fc2, da, dmx);
+    la_gate_bwd_kernel<<<N, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, N, Cr, d_fc1, d_fc2, da, dmx);
     la_fix_kernel<T><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((T*)dx, da, dmx, pstar, P, NP * LA_C);
     count_launch(6);
     return check_launch("la_chain_bwd");

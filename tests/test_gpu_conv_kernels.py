@@ -72,6 +72,40 @@ def test_simt_fwd_dgrad_wgrad(be, case, dtype):
     assert rel(dw, dw_ref) < max(tol, 2e-5) and rel(db, gy.float().sum((0, 2, 3))) < max(tol, 2e-5)
 
 
+THIN_CASES = [
+    (2, 3, 40, 40, 64, 3, 1, 1),      # RGB -> 64 (conv1, MSB.conv1, D.model.0, VGG.0)
+    (2, 3, 30, 31, 64, 1, 1, 0),      # MSB 1x1 from RGB
+    (2, 64, 40, 45, 3, 3, 1, 1),      # conv3: 64 -> RGB
+    (1, 512, 14, 14, 1, 3, 1, 1),     # D.model.25: 512 -> 1
+    (1, 64, 216, 216, 3, 3, 1, 1),    # conv3 at the real output size
+    (1, 3, 216, 216, 64, 3, 1, 1),    # D.model.0 at the real input size
+]
+
+
+@pytest.mark.parametrize("case", THIN_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_thin_channel_paths(be, case, dtype):
+    """direct kernels for layers with <= 4 channels on one side (auto dispatch) vs torch CPU"""
+    n, cin, h, w, cout, k, s, p = case
+    x, wt, b = _mk(n, cin, h, w, cout, k, dtype, seed=cin * 3 + cout)
+    g = conv_geom(x.shape, wt.shape, s, p)
+    tol = 1e-5 if dtype == torch.float32 else 4e-3
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = be.conv_fwd(xc, be.pack_weights(wt.cuda(), 0, dtype), b.cuda(), None, g, ACT_LRELU, 0.01, out_dtype=torch.float32)
+    y_ref = F.leaky_relu(F.conv2d(x.float(), _ref_w(wt, dtype), b, stride=s, padding=p), 0.01)
+    assert y.shape == y_ref.shape and rel(y, y_ref) < 1e-5
+    y2 = be.conv_fwd(xc, be.pack_weights(wt.cuda(), 0, dtype), b.cuda(), None, g, ACT_LRELU, 0.01)
+    assert rel(y2, y_ref) < tol
+    gy = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(1)).to(dtype)
+    gyc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, dtype), g)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, _ref_w(wt, dtype), gy.float(), stride=s, padding=p)
+    assert rel(dx, dx_ref) < tol
+    dw, db = be.conv_wgrad(xc, gyc, g)
+    dw_ref = torch.nn.grad.conv2d_weight(x.float(), wt.shape, gy.float(), stride=s, padding=p)
+    assert rel(dw, dw_ref) < 5e-5 and rel(db, gy.float().sum((0, 2, 3))) < 5e-5
+
+
 def test_simt_residual_shuffle_fp32out(be):
     n, cin, h, w, cout, k = 2, 64, 9, 9, 256, 3
     x, wt, b = _mk(n, cin, h, w, cout, k, torch.bfloat16, seed=3)
