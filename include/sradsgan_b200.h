@@ -107,6 +107,18 @@ int sr_la_chain_bwd(const float* gz32, const void* gz16, const void* x, int x_dt
 int sr_act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act, float slope, int shuffle_r,
                int N, int Ho, int Wo, int C, void* out, int out_dtype, void* stream);
 
+/* Train-mode BatchNorm2d + LeakyReLU(slope) over x viewed as [rows = N*H*W][C] (C % 4 == 0), first-order only
+ * (nn.BatchNorm2d + nn.LeakyReLU(0.2) of the discriminator blocks, model/sradsgan.py:476-479).
+ * Normalises with the batch mean / biased variance; running_mean / running_var (nullable) are updated in place
+ * with `momentum` and the unbiased variance, as torch does.  save: [4][C] fp32 (mean, rstd, scale, shift) for
+ * the backward; workspace: >= 2*C floats. */
+int sr_bn_act_fwd(const void* x, int dtype, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                  float momentum, float slope, float* running_mean, float* running_var, void* y, float* save,
+                  void* workspace, void* stream);
+/* dx, dgamma, dbeta (overwritten) from gy and the forward input x. */
+int sr_bn_act_bwd(const void* gy, const void* x, int dtype, int64_t rows, int C, const float* save, float slope,
+                  void* dx, float* dgamma, float* dbeta, void* stream);
+
 /* out[c] = sum over rows of x[rows][C] (fp32 accumulate); sq (may be NULL) = sum of squares.
  * BatchNorm2d batch statistics (model/sradsgan.py:478) and bias gradients. */
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate,

@@ -132,6 +132,33 @@ class EmuBackend:
             gp = F.pixel_unshuffle(gp, shuffle_r)
         return gp.to(out_dtype).contiguous(memory_format=torch.channels_last)
 
+    def bn_act_fwd(self, x, gamma, beta, running_mean, running_var, eps, momentum, slope):
+        self.launches += 3
+        xf = x.float()
+        mean = xf.mean((0, 2, 3)); var = xf.var((0, 2, 3), unbiased=False)
+        n = xf.numel() / xf.shape[1]
+        if running_mean is not None:
+            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+            running_var.mul_(1 - momentum).add_(var * (n / max(n - 1, 1)), alpha=momentum)
+        rstd = torch.rsqrt(var + eps)
+        scale = gamma.detach().float() * rstd
+        shift = beta.detach().float() - mean * scale
+        y = F.leaky_relu(xf * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), slope)
+        return y.to(x.dtype).contiguous(memory_format=torch.channels_last), torch.stack([mean, rstd, scale, shift])
+
+    def bn_act_bwd(self, gy, x, save, slope):
+        self.launches += 2
+        mean, rstd, scale, shift = save[0], save[1], save[2], save[3]
+        xf, g = x.float(), gy.float()
+        v = lambda t: t.view(1, -1, 1, 1)
+        z = xf * v(scale) + v(shift)
+        g = torch.where(z > 0, g, g * slope)
+        xh = (xf - v(mean)) * v(rstd)
+        m = xf.numel() / xf.shape[1]
+        dbeta = g.sum((0, 2, 3)); dgamma = (g * xh).sum((0, 2, 3))
+        dx = v(scale) * (g - v(dbeta) / m - xh * v(dgamma) / m)
+        return dx.to(x.dtype).contiguous(memory_format=torch.channels_last), dgamma, dbeta
+
     def colsum(self, x2d, want_sq=False):
         self.launches += 1
         f = x2d.float()

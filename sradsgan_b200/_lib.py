@@ -19,7 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
-    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd",
+    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd",
 ]
 
 
@@ -75,7 +75,9 @@ def load():
     lib.sr_la_chain_fwd.argtypes = [vp, i32] + [vp] * 6 + [i32] * 5 + [vp] * 11
     lib.sr_la_chain_bwd.argtypes = [vp, vp, vp, i32] + [vp] * 11 + [i32] * 5 + [vp] * 9
     lib.sr_act_bwd.argtypes = [vp, i32, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp, i32, vp]
-    for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd"):
+    lib.sr_bn_act_fwd.argtypes = [vp, i32, i64, i32, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp, vp]
+    lib.sr_bn_act_bwd.argtypes = [vp, vp, i32, i64, i32, vp, f32, vp, vp, vp, vp]
+    for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
         getattr(lib, name).restype = i32
     for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
         getattr(lib, name).restype = i32
@@ -274,6 +276,30 @@ class CudaBackend:
         _check(self.lib.sr_act_bwd(_ptr(gy), _dt(gy), _ptr(y), _dt(y), int(act), float(slope), int(shuffle_r or 0), g.N, g.Ho, g.Wo,
                                    g.Cout, _ptr(out), _dt(out), _stream()), "act_bwd")
         return out
+
+    # -- train-mode BatchNorm + LeakyReLU (first-order) ---------------------------------------------
+    def bn_act_fwd(self, x, gamma, beta, running_mean, running_var, eps, momentum, slope):
+        _require_cuda(x)
+        x = _nhwc(x)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        save = torch.empty((4, c), dtype=torch.float32, device=x.device)
+        ws = torch.empty((2 * c,), dtype=torch.float32, device=x.device)
+        _check(self.lib.sr_bn_act_fwd(_ptr(x), _dt(x), n * h * w, c, _ptr(gamma.detach().float().contiguous()),
+                                      _ptr(beta.detach().float().contiguous()), float(eps), float(momentum), float(slope),
+                                      _ptr(running_mean), _ptr(running_var), _ptr(y), _ptr(save), _ptr(ws), _stream()), "bn_act_fwd")
+        return y, save
+
+    def bn_act_bwd(self, gy, x, save, slope):
+        x = _nhwc(x)
+        gy = _nhwc(gy.to(x.dtype))
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
+        dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
+        _check(self.lib.sr_bn_act_bwd(_ptr(gy), _ptr(x), _dt(x), n * h * w, c, _ptr(save), float(slope), _ptr(dx), _ptr(dgamma),
+                                      _ptr(dbeta), _stream()), "bn_act_bwd")
+        return dx, dgamma, dbeta
 
     # -- reductions / optimiser ----------------------------------------------------------------
     def colsum(self, x2d, want_sq=False):

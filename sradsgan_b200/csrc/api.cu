@@ -50,6 +50,9 @@ int la_chain_bwd(const float*, const void*, const void*, int, const float*, cons
                  const float*, const unsigned char*, const float*, const float*, const float*, const float*, int, int, int, int,
                  void*, float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
 int act_bwd(const void*, int, const void*, int, int, float, int, int, int, int, int, void*, int, cudaStream_t);
+// bn.cu
+int bn_act_fwd(const void*, int, long long, int, const float*, const float*, float, float, float, float*, float*, void*, float*, float*, cudaStream_t);
+int bn_act_bwd(const void*, const void*, int, long long, int, const float*, float, void*, float*, float*, cudaStream_t);
 // elementwise.cu
 int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
@@ -200,6 +203,24 @@ int sr_act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act
     SR_REQUIRE(gy && y && out && N > 0 && Ho > 0 && Wo > 0 && C > 0, "act_bwd: bad arguments");
     SR_REQUIRE(shuffle_r <= 1 || C % (shuffle_r * shuffle_r) == 0, "act_bwd: C %% r^2 != 0");
     return act_bwd(gy, gy_dtype, y, y_dtype, act, slope, shuffle_r, N, Ho, Wo, C, out, out_dtype, (cudaStream_t)stream);
+}
+
+int sr_bn_act_fwd(const void* x, int dtype, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum,
+                  float slope, float* running_mean, float* running_var, void* y, float* save, void* workspace, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && gamma && beta && y && save && workspace && rows > 0 && C > 0 && C % 4 == 0, "bn_act_fwd: bad arguments");
+    SR_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_act_fwd: running stats must both be given or both NULL");
+    return bn_act_fwd(x, dtype, rows, C, gamma, beta, eps, momentum, slope, running_mean, running_var, y, save, (float*)workspace,
+                      (cudaStream_t)stream);
+}
+
+int sr_bn_act_bwd(const void* gy, const void* x, int dtype, int64_t rows, int C, const float* save, float slope, void* dx,
+                  float* dgamma, float* dbeta, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(gy && x && save && dx && dgamma && dbeta && rows > 0 && C > 0 && C % 4 == 0, "bn_act_bwd: bad arguments");
+    return bn_act_bwd(gy, x, dtype, rows, C, save, slope, dx, dgamma, dbeta, (cudaStream_t)stream);
 }
 
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate, void* stream) {

@@ -398,7 +398,31 @@ class Discriminator(nn.Module):
         self.model = nn.Sequential(*layers)
 
     def forward(self, img):
-        return self.model(ops.to_compute(img))
+        x = ops.to_compute(img)
+        # The WGAN-GP pass differentiates D twice (reference :621,:639): it feeds a LEAF that requires grad
+        # (`interpolates.requires_grad_(True)`, :611) and must run on the any-order differentiable ops.  Every
+        # other pass (G-step critic, D real / fake) is first-order and takes the fused kernels.
+        if ops.config.double_backward or (img.requires_grad and img.is_leaf) or not self.training:
+            return self.model(x)
+        mods = list(self.model)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            nxt2 = mods[i + 2] if i + 2 < len(mods) else None
+            if isinstance(m, Conv2d) and isinstance(nxt, BatchNorm2d) and isinstance(nxt2, LeakyReLU):
+                x = ops.bn_leaky_relu(m.fused(x), nxt, nxt2.negative_slope)       # conv -> fused BN+LReLU
+                i += 3
+            elif isinstance(m, Conv2d) and isinstance(nxt, LeakyReLU):
+                x = m.fused(x, ACT_LRELU, nxt.negative_slope)                     # conv + LReLU epilogue
+                i += 2
+            elif isinstance(m, Conv2d):
+                x = m.fused(x)
+                i += 1
+            else:
+                x = m(x)
+                i += 1
+        return x
 
 
 from .trainer import SRADSGAN  # noqa: E402,F401  (reference: class SRADSGAN lives in this module, :510)

@@ -16,6 +16,7 @@ class Config:
     """Process-wide numeric configuration of the hot path."""
     compute_dtype = torch.bfloat16     # activations / MMA operands ("bf16 mode"); torch.float32 = "fp32 mode"
     conv_impl = IMPL_AUTO              # SR_IMPL_* forced for every conv (tests)
+    double_backward = False            # force the any-order differentiable (unfused) discriminator path
 
 
 config = Config()
@@ -238,3 +239,30 @@ def local_attn_chain(x, t, ca, sa, conv):
         z32._sr_lowp = z16
         return z32
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# train-mode BatchNorm2d + LeakyReLU, first-order (discriminator passes that are not the gradient penalty)
+# ----------------------------------------------------------------------------------------------
+class BatchNormLeakyReLU(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, slope):
+        y, save = _lib.backend().bn_act_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, slope)
+        ctx.slope = slope
+        ctx.save_for_backward(x, save)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, save = ctx.saved_tensors
+        dx, dgamma, dbeta = _lib.backend().bn_act_bwd(gy, x, save, ctx.slope)
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def bn_leaky_relu(x, bn, slope):
+    """bn: sradsgan_b200.nn.BatchNorm2d in training mode"""
+    y = BatchNormLeakyReLU.apply(to_compute(x), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, slope)
+    with torch.no_grad():
+        bn.num_batches_tracked += 1
+    return y

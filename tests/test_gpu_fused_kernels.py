@@ -72,3 +72,29 @@ def test_act_bwd(be, r, act):
     ref = emu.act_bwd(gy, y, act, 0.2, r, g, torch.bfloat16)
     got = be.act_bwd(gy.cuda(), y.cuda(), act, 0.2, r, g, torch.bfloat16)
     assert got.shape == ref.shape and rel(got, ref) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 20, 24), (2, 128, 27, 27), (16, 512, 14, 14), (3, 256, 7, 9)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_leaky_relu_forward_backward(be, shape, dtype):
+    """train-mode BatchNorm2d + LeakyReLU(0.2): batch statistics, running-stat update, first-order backward"""
+    emu = ops_emu.EmuBackend()
+    g = torch.Generator().manual_seed(shape[1])
+    n, c, h, w = shape
+    x = (torch.randn(shape, generator=g) * 0.7 + 0.3).to(dtype)
+    gamma = 1 + 0.1 * torch.randn(c, generator=g)
+    beta = 0.1 * torch.randn(c, generator=g)
+    rm, rv = torch.zeros(c), torch.ones(c)
+    y_ref, save_ref = emu.bn_act_fwd(x, gamma, beta, rm, rv, 1e-5, 0.1, 0.2)
+    rm_c, rv_c = torch.zeros(c).cuda(), torch.ones(c).cuda()
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y, save = be.bn_act_fwd(xc, gamma.cuda(), beta.cuda(), rm_c, rv_c, 1e-5, 0.1, 0.2)
+    tol = 1e-5 if dtype == torch.float32 else 4e-3
+    assert rel(y, y_ref) < tol
+    assert rel(save, save_ref) < 1e-4
+    assert rel(rm_c, rm) < 1e-4 and rel(rv_c, rv) < 1e-4
+    gy = torch.randn(shape, generator=g).to(dtype)
+    dx_ref, dg_ref, db_ref = emu.bn_act_bwd(gy, x, save_ref, 0.2)
+    dx, dg, db = be.bn_act_bwd(gy.cuda(), xc, save, 0.2)
+    assert rel(dx, dx_ref) < (1e-4 if dtype == torch.float32 else 6e-3)
+    assert rel(dg, dg_ref) < 2e-4 and rel(db, db_ref) < 2e-4
