@@ -66,6 +66,22 @@ static int make_im2col_map(CUtensorMap* m, const void* ptr, int N, int H, int W,
     return SR_OK;
 }
 
+// NHWC bf16 activation tensor -> plain tiled 4-d map with box [1][box_h][box_w][64 ch], 128B swizzle
+static int make_tiled4d_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(4d) failed (%d) N=%d H=%d W=%d C=%d box=(%d,%d)", (int)r, N, H, W, C, box_w, box_h);
+        return SR_ERR_CUDA;
+    }
+    return SR_OK;
+}
+
 // row-major bf16 matrix [rows][cols] -> tiled map with box [box_rows][64], 128B swizzle.
 static int make_tiled2d_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     cuuint64_t dims[2] = {cols, rows};
@@ -180,6 +196,50 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+
+// 4-d tiled TMA load (coordinates may be negative / out of range: zero filled)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :
+        : "r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// Epilogue of one 32-column accumulator chunk of one output pixel: bias -> activation -> store (16-byte
+// vectors).  `col` is the packed GEMM column of v[0]; with shuffle_r > 1 the weights were packed
+// subpixel-major, so a chunk is 32 consecutive channels of ONE sub-pixel (PixelShuffle = contiguous store).
+struct TcEpilogue {
+    int Cout, Ho, Wo;          // conv output grid (before the shuffle) and channel count
+    int act; float slope; int shuffle_r;
+    const float* bias; void* out;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& e, const uint32_t (&v)[32], int col, int n, int oy, int ox) {
+    const int r = e.shuffle_r > 1 ? e.shuffle_r : 1;
+    long long idx;
+    int sub = 0, ch0 = col, r2 = 1;
+    if (r > 1) {
+        r2 = r * r;
+        const int cq = e.Cout / r2;
+        sub = col / cq; ch0 = col - sub * cq;
+        const int si = sub / r, sj = sub - si * r;
+        idx = ((((long long)n * e.Ho * r + (oy * r + si)) * ((long long)e.Wo * r)) + (ox * r + sj)) * cq + ch0;
+    } else {
+        idx = (((long long)n * e.Ho + oy) * e.Wo + ox) * e.Cout + col;
+    }
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (e.bias) x += e.bias[r > 1 ? (ch0 + j) * r2 + sub : col + j];
+        f[j] = apply_act(x, e.act, e.slope);
+    }
+    OutT* o = reinterpret_cast<OutT*>(e.out) + idx;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) store4<OutT>(o + g * 4, f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+}
 
 // MN-major, 128B-swizzled operand tile ([k rows][64 bf16 of M/N], 8-row groups 1024 B apart, further
 // 64-wide M/N panels `lbo_bytes` apart): UMMA smem descriptor (cute::UMMA canonical MN-major SW128 layout)
