@@ -132,6 +132,13 @@ int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float lr, float beta1, float beta2, float eps, int step, const int32_t* step_dev,
                  float grad_scale, float clamp_lo, float clamp_hi, void* stream);
 
+/* Diagnostics (not on the product path): D[128][64] (fp32) = A_view * B^T on tcgen05, where A is a
+ * [rows_a][64] bf16 matrix staged by TMA with the 128-byte swizzle and A_view row r is smem row
+ * shift_rows + (r/8)*(sbo_bytes/128) + r%8 — probes which shared-memory operand descriptors the tensor core
+ * accepts (shifted start address, non-1024 B group stride, descriptor base_offset field). */
+int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows, int sbo_bytes, int base_offset,
+                        float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

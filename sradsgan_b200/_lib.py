@@ -19,7 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
-    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd",
+    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_debug_umma_shift",
 ]
 
 
@@ -77,6 +77,8 @@ def load():
     lib.sr_act_bwd.argtypes = [vp, i32, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp, i32, vp]
     lib.sr_bn_act_fwd.argtypes = [vp, i32, i64, i32, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp, vp]
     lib.sr_bn_act_bwd.argtypes = [vp, vp, i32, i64, i32, vp, f32, vp, vp, vp, vp]
+    lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
+    lib.sr_debug_umma_shift.restype = i32
     for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
         getattr(lib, name).restype = i32
     for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):

@@ -58,6 +58,9 @@ int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStr
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
 int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, const int*, float, float, float, cudaStream_t);
 
+// debug_probe.cu
+int debug_umma_shift(const void*, int, const void*, int, int, int, float*, cudaStream_t);
+
 static int g_arch_ok = -1;
 static int arch_check() {
     if (g_arch_ok < 0) {
@@ -238,6 +241,14 @@ int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
     SR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
     return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step < 1 ? 1 : step, step_dev, grad_scale,
                      clamp_lo, clamp_hi, (cudaStream_t)stream);
+}
+
+int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows, int sbo_bytes, int base_offset, float* out,
+                        void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && b && out && shift_rows >= 0 && sbo_bytes > 0, "debug_umma_shift: bad arguments");
+    return debug_umma_shift(a, rows_a, b, shift_rows, sbo_bytes, base_offset, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@ namespace sr {
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
     int M_total, Ho, Wo, Cout;
-    int block_n, n_blocks, num_tiles;
+    int block_n, n_blocks, m_tiles, num_tiles;
     int stride, pad_w, pad_h;   // im2col base coordinate of output pixel (oy,ox) = (oy*stride - pad_h, ox*stride - pad_w)
     int c_blocks;      // Cin / 64
     int ntaps;         // filter taps visited (a subset for the parity classes of a strided dgrad)
@@ -37,15 +37,179 @@ struct TcParams {
     float slope;
     int shuffle_r;     // weights rows are packed subpixel-major when > 1
     int num_stages;
+    int resident;      // 1: every CTA keeps the weights of ONE column block in shared memory for all of its tiles
     const float* bias;
     const void* residual;
     void* out;
 };
 
-constexpr int TC_THREADS = 192;
-constexpr int TC_A_BYTES = 128 * 128;   // 128 pixels x 64 bf16
-constexpr int TC_ACC_STRIDE = 256;      // TMEM columns per accumulator stage
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_EPI_WARPS = 8;                      // 2 per TMEM lane quarter
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_A_BYTES = 128 * 128;                // 128 pixels x 64 bf16
+constexpr int TC_ACC_STRIDE = 256;                   // TMEM columns per accumulator stage
+constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_MAX_RES_KB = 36;                    // resident mode: at most this many 64-deep k-blocks
+constexpr int TC_BIAS_MAX = 1024;                    // floats of bias staged in shared memory
+constexpr int TC_TILE_BUDGET = 232448 - 1024 - 1024 - TC_BIAS_MAX * 4;   // bytes available for operand tiles
+
+// tile `it` of this CTA -> (pixel tile, column block).  Resident mode pins the column block to the CTA.
+__device__ __forceinline__ bool tc_tile_at(const TcParams& p, int it, int& m_tile, int& nb) {
+    if (p.resident) {
+        nb = blockIdx.x % p.n_blocks;
+        m_tile = blockIdx.x / p.n_blocks + it * (gridDim.x / p.n_blocks);
+        return m_tile < p.m_tiles;
+    }
+    const int t = blockIdx.x + it * gridDim.x;
+    if (t >= p.num_tiles) return false;
+    m_tile = t / p.n_blocks;
+    nb = t - m_tile * p.n_blocks;
+    return true;
+}
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// waits for every outstanding tcgen05.ld of this thread; the registers are passed through so that the
+// compiler cannot move their first use above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+template <int ACT> __device__ __forceinline__ float tc_act(float x, float slope) {
+    if (ACT == SR_ACT_LRELU) return fmaxf(x, x * slope);          // slope in [0, 1]
+    if (ACT == SR_ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == SR_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+    return x;
+}
+
+// bias (shared memory, already in packed-column order) -> activation -> (+ residual) -> 16-byte stores of one
+// 32-column accumulator chunk of one output row
+template <typename OutT, int ACT>
+__device__ __forceinline__ void tc_store_chunk(const uint32_t (&v)[32], const float* bias_s, float slope, const OutT* res, OutT* o) {
+    float f[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + g * 4);
+        f[g * 4 + 0] = tc_act<ACT>(__uint_as_float(v[g * 4 + 0]) + b.x, slope);
+        f[g * 4 + 1] = tc_act<ACT>(__uint_as_float(v[g * 4 + 1]) + b.y, slope);
+        f[g * 4 + 2] = tc_act<ACT>(__uint_as_float(v[g * 4 + 2]) + b.z, slope);
+        f[g * 4 + 3] = tc_act<ACT>(__uint_as_float(v[g * 4 + 3]) + b.w, slope);
+    }
+    if (sizeof(OutT) == 2) {
+        if (res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint4 rv = rp[g];
+                const __nv_bfloat162* r2p = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    f[g * 8 + h * 2] += __low2float(r2p[h]);
+                    f[g * 8 + h * 2 + 1] += __high2float(r2p[h]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+            w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
+            w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
+            reinterpret_cast<uint4*>(o)[g] = w;
+        }
+    } else {
+        if (res) {
+            const float4* rp = reinterpret_cast<const float4*>(res);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 rv = rp[g];
+                f[g * 4] += rv.x; f[g * 4 + 1] += rv.y; f[g * 4 + 2] += rv.z; f[g * 4 + 3] += rv.w;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(o)[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+    }
+}
+
+// Epilogue warp: TMEM lane quarter `quarter`, every second 32-column chunk starting at `half`; the tcgen05.ld of
+// the next chunk is in flight while the current one is converted and stored.
+template <typename OutT, int ACT>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                            const float* bias_s, int quarter, int half, int lane) {
+    const int row = quarter * 32 + lane;
+    const int r = p.shuffle_r > 1 ? p.shuffle_r : 1;
+    const int cq = p.Cout / (r * r);
+    const int chunks = p.block_n >> 5;
+    OutT* out = reinterpret_cast<OutT*>(p.out);
+    const OutT* res = reinterpret_cast<const OutT*>(p.residual);
+    int acc = 0; uint32_t acc_phase = 0;
+    int m_tile, nb;
+    for (int it = 0; tc_tile_at(p, it, m_tile, nb); ++it) {
+        const long long m = (long long)m_tile * 128 + row;
+        const bool valid = m < p.M_total;
+        int ox = 0, oy = 0, n = 0;
+        if ((r > 1 || p.os > 1) && valid) {
+            ox = (int)(m % p.Wo); const long long q = m / p.Wo;
+            oy = (int)(q % p.Ho); n = (int)(q / p.Ho);
+        }
+        long long row_idx;     // element index of column 0 of this row (plain / strided-scatter modes)
+        if (p.os > 1) row_idx = (((long long)n * p.Hfull + (oy * p.os + p.py)) * p.Wfull + (ox * p.os + p.px)) * p.Cout;
+        else row_idx = m * p.Cout;
+        mbar_wait(acc_full + acc, acc_phase);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_ACC_STRIDE);
+        auto emit = [&](const uint32_t (&v)[32], int c) {
+            if (!valid) return;
+            const int col = nb * p.block_n + c * 32;     // packed (GEMM) output column of v[0]
+            long long idx;
+            if (r > 1) {
+                const int sub = col / cq, ch0 = col - sub * cq;
+                const int si = sub / r, sj = sub - si * r;
+                idx = ((((long long)n * p.Ho * r + (oy * r + si)) * ((long long)p.Wo * r)) + (ox * r + sj)) * cq + ch0;
+            } else {
+                idx = row_idx + col;
+            }
+            tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx);
+        };
+        uint32_t va[32], vb[32];
+        int c = half;
+        if (c < chunks) tmem_ld32_nowait(t_base + (uint32_t)(c * 32), va);
+        while (c < chunks) {
+            tmem_ld_wait(va);
+            if (c + 2 < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + 2) * 32), vb);
+            emit(va, c);
+            c += 2;
+            if (c >= chunks) break;
+            tmem_ld_wait(vb);
+            if (c + 2 < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + 2) * 32), va);
+            emit(vb, c);
+            c += 2;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+}
 
 template <typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -53,25 +217,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.block_n * 128;
-    const int stage_bytes = TC_A_BYTES + b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
+    const int k_blocks = p.ntaps * p.c_blocks;
+    // resident: [k_blocks x B][stages x A] ; streaming: [stages x (A + B)]
+    const int stage_bytes = p.resident ? TC_A_BYTES : TC_A_BYTES + b_bytes;
+    uint8_t* stage_base = smem + (p.resident ? (size_t)k_blocks * b_bytes : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)p.num_stages * stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + TC_MAX_STAGES;
     uint64_t* acc_full = bars + 2 * TC_MAX_STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* b_full = acc_empty + 2;                                    // [TC_MAX_RES_KB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + TC_MAX_RES_KB);
+    float* bias_s = reinterpret_cast<float*>(bars) + 256;                 // 1024 B after the barrier block
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k_blocks = p.ntaps * p.c_blocks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, TC_EPI_WARPS); }
+        if (p.resident) for (int kb = 0; kb < k_blocks; ++kb) mbar_init(b_full + kb, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    {   // bias in packed-column order (subpixel-major when the epilogue does the PixelShuffle)
+        const int r2 = p.shuffle_r > 1 ? p.shuffle_r * p.shuffle_r : 1;
+        const int cq = p.Cout / r2;
+        for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+            float b = 0.f;
+            if (p.bias) { const int sub = i / cq, ch = i - sub * cq; b = p.bias[r2 > 1 ? ch * r2 + sub : i]; }
+            bias_s[i] = b;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -81,8 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_blocks, nb = tile - m_tile * p.n_blocks;
+            int m_tile, nb;
+            for (int it = 0; tc_tile_at(p, it, m_tile, nb); ++it) {
                 const int m0 = m_tile * 128;
                 const int ox = m0 % p.Wo; const int q = m0 / p.Wo;
                 const int oy = q % p.Ho; const int n = q / p.Ho;
@@ -90,11 +268,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     const int ti = kb / p.c_blocks, cb = kb - ti * p.c_blocks;
                     const int tap = p.tap_w[ti], offw = p.tap_ow[ti], offh = p.tap_oh[ti];
+                    if (p.resident && it == 0) {      // weights of this CTA's column block: loaded once, k-block by k-block
+                        mbar_expect_tx(b_full + kb, (uint32_t)b_bytes);
+                        tma_load_2d(smem + (size_t)kb * b_bytes, &map_b, b_full + kb, cb * 64, tap * p.Cout + nb * p.block_n);
+                    }
                     mbar_wait(empty + stage, phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
                     mbar_expect_tx(full + stage, (uint32_t)stage_bytes);
                     tma_load_im2col(sa, &map_a, full + stage, cb * 64, w0, h0, n, (uint16_t)offw, (uint16_t)offh);
-                    tma_load_2d(sa + TC_A_BYTES, &map_b, full + stage, cb * 64, tap * p.Cout + nb * p.block_n);
+                    if (!p.resident) tma_load_2d(sa + TC_A_BYTES, &map_b, full + stage, cb * 64, tap * p.Cout + nb * p.block_n);
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -106,16 +288,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int m_tile, nb;
+            for (int it = 0; tc_tile_at(p, it, m_tile, nb); ++it) {
                 mbar_wait(acc_empty + acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_STRIDE);
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    if (p.resident && it == 0) mbar_wait(b_full + kb, 0);
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t a_addr = smem_u32(stage_base + (size_t)stage * stage_bytes);
+                    const uint32_t b_addr = p.resident ? smem_u32(smem + (size_t)kb * b_bytes) : a_addr + TC_A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + TC_A_BYTES);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(b_addr);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)   // 4 x K=16 per 64-channel block: +32 B per step
                         umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
@@ -127,94 +312,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const int r = p.shuffle_r > 1 ? p.shuffle_r : 1;
-        const int r2 = r * r;
-        const int cq = p.Cout / r2;
-        OutT* out = reinterpret_cast<OutT*>(p.out);
-        const OutT* res = reinterpret_cast<const OutT*>(p.residual);
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_blocks, nb = tile - m_tile * p.n_blocks;
-            const long long m = (long long)m_tile * 128 + row;
-            const bool valid = m < p.M_total;
-            int ox = 0, oy = 0, n = 0;
-            if ((r > 1 || p.os > 1) && valid) {
-                ox = (int)(m % p.Wo); const long long q = m / p.Wo;
-                oy = (int)(q % p.Ho); n = (int)(q / p.Ho);
-            }
-            mbar_wait(acc_full + acc, acc_phase);
-            tc_fence_after();
-            const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_ACC_STRIDE);
-            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(t_base + (uint32_t)c0, v);
-                if (!valid) continue;
-                const int col = nb * p.block_n + c0;     // packed (GEMM) output column of v[0]
-                long long idx;
-                int sub = 0, ch0 = col;
-                if (r > 1) {
-                    sub = col / cq; ch0 = col - sub * cq;
-                    const int si = sub / r, sj = sub - si * r;
-                    idx = ((((long long)n * p.Ho * r + (oy * r + si)) * ((long long)p.Wo * r)) + (ox * r + sj)) * cq + ch0;
-                } else if (p.os > 1) {
-                    idx = (((long long)n * p.Hfull + (oy * p.os + p.py)) * p.Wfull + (ox * p.os + p.px)) * p.Cout + col;
-                } else {
-                    idx = m * p.Cout + col;
-                }
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (p.bias) x += p.bias[r > 1 ? (ch0 + j) * r2 + sub : col + j];
-                    f[j] = apply_act(x, p.act, p.slope);
-                }
-                if (sizeof(OutT) == 2) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + idx;
-                    if (res) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + idx);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 rv = rp[g];
-                            const __nv_bfloat162* r2p = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                f[g * 8 + h * 2] += __low2float(r2p[h]);
-                                f[g * 8 + h * 2 + 1] += __high2float(r2p[h]);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 w;
-                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
-                        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
-                        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-                        w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
-                        w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
-                        reinterpret_cast<uint4*>(o)[g] = w;
-                    }
-                } else {
-                    float* o = reinterpret_cast<float*>(out) + idx;
-                    if (res) {
-                        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + idx);
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float4 rv = rp[g];
-                            f[g * 4] += rv.x; f[g * 4 + 1] += rv.y; f[g * 4 + 2] += rv.z; f[g * 4 + 3] += rv.w;
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        reinterpret_cast<float4*>(o)[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(acc_empty + acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column-chunk parity = (warp - 2) / 4 =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        switch (p.act) {
+            case SR_ACT_LRELU: tc_epilogue<OutT, SR_ACT_LRELU>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, half, lane); break;
+            case SR_ACT_RELU: tc_epilogue<OutT, SR_ACT_RELU>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, half, lane); break;
+            case SR_ACT_SIGMOID: tc_epilogue<OutT, SR_ACT_SIGMOID>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, half, lane); break;
+            default: tc_epilogue<OutT, SR_ACT_NONE>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, half, lane); break;
         }
     }
     tc_fence_before();
@@ -239,7 +343,7 @@ static int pick_block_n(int Cout) {
 bool conv_tc_supported(const sr_conv_desc* d, bool dgrad) {
     if (d->in_dtype != SR_BF16) return false;
     const int Cs = dgrad ? d->Cout : d->Cin, Cd = dgrad ? d->Cin : d->Cout;
-    if (Cs % 64 != 0 || pick_block_n(Cd) == 0) return false;
+    if (Cs % 64 != 0 || pick_block_n(Cd) == 0 || Cd > TC_BIAS_MAX) return false;
     if (d->kh != d->kw || d->kh > 7) return false;
     if (d->stride < 1 || d->stride > 2) return false;
     if (dgrad && d->stride == 2 && !(d->kh == 3 && d->pad == 1)) return false;   // parity decomposition: 3x3/pad 1 only
@@ -249,16 +353,37 @@ bool conv_tc_supported(const sr_conv_desc* d, bool dgrad) {
     return true;
 }
 
-static int launch_tc(const TcParams& p, const CUtensorMap& map_a, const CUtensorMap& map_b, bool out_bf16, cudaStream_t st) {
-    const int stage_bytes = TC_A_BYTES + p.block_n * 128;
-    const size_t smem = 1024 + (size_t)p.num_stages * stage_bytes + 256;
-    const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+// Completes the schedule of one launch (tiles, resident-weights mode, pipeline depth, grid) and launches.
+static int launch_tc(TcParams p, const CUtensorMap& map_a, const CUtensorMap& map_b, bool out_bf16, cudaStream_t st) {
+    const int b_bytes = p.block_n * 128;
+    const int k_blocks = p.ntaps * p.c_blocks;
+    p.m_tiles = (int)cdiv(p.M_total, 128);
+    p.num_tiles = p.m_tiles * p.n_blocks;
+    int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+    // Resident weights: when the [taps x Cin] x block_n slab of one column block fits beside >= 3 activation
+    // stages, each CTA loads it ONCE and streams only activation tiles (halves the L2->SM traffic of Cin=64 convs).
+    const long long res_bytes = (long long)k_blocks * b_bytes;
+    p.resident = (k_blocks <= TC_MAX_RES_KB && res_bytes + 3 * TC_A_BYTES <= TC_TILE_BUDGET && p.num_tiles > grid) ? 1 : 0;
+    int stages;
+    size_t tile_bytes;
+    if (p.resident) {
+        grid -= grid % p.n_blocks;
+        stages = (int)((TC_TILE_BUDGET - res_bytes) / TC_A_BYTES);
+        if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+        tile_bytes = (size_t)res_bytes + (size_t)stages * TC_A_BYTES;
+    } else {
+        stages = TC_TILE_BUDGET / (TC_A_BYTES + b_bytes);
+        if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+        tile_bytes = (size_t)stages * (TC_A_BYTES + b_bytes);
+    }
+    p.num_stages = stages;
+    const size_t smem = 1024 + tile_bytes + 1024 + TC_BIAS_MAX * 4;
     static bool attr_set[2] = {false, false};
     if (out_bf16) {
-        if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[0] = true; }
+        if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[0] = true; }
         conv_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
     } else {
-        if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
+        if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[1] = true; }
         conv_tc_kernel<float><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
     }
     count_launch();
@@ -291,10 +416,6 @@ int conv_tc_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* 
     p.shuffle_r = dgrad ? 0 : d->shuffle_r;
     p.bias = bias; p.residual = residual; p.out = dst;
     p.os = 1; p.Hfull = Hd; p.Wfull = Wd;
-    const int stage_bytes = TC_A_BYTES + p.block_n * 128;
-    int stages = (200 * 1024) / stage_bytes;
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    p.num_stages = stages;
 
     alignas(64) CUtensorMap map_a, map_b;
     rc = make_tiled2d_map(&map_b, w, (uint64_t)taps * Cd, (uint64_t)Cs, (uint32_t)p.block_n);
@@ -305,7 +426,6 @@ int conv_tc_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* 
         const int pad = dgrad ? (k - 1 - d->pad) : d->pad;
         const int stride = dgrad ? 1 : d->stride;
         p.M_total = d->N * Hd * Wd; p.Ho = Hd; p.Wo = Wd;
-        p.num_tiles = (int)cdiv(p.M_total, 128) * p.n_blocks;
         p.stride = stride; p.pad_w = pad; p.pad_h = pad;
         p.ntaps = taps;
         for (int t = 0; t < taps; ++t) {
@@ -330,7 +450,6 @@ int conv_tc_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* 
             if (Hp <= 0 || Wp <= 0) continue;
             TcParams q = p;
             q.M_total = d->N * Hp * Wp; q.Ho = Hp; q.Wo = Wp;
-            q.num_tiles = (int)cdiv(q.M_total, 128) * q.n_blocks;
             q.stride = 1; q.pad_w = 0; q.pad_h = 0;
             q.os = 2; q.py = py; q.px = px; q.Hfull = d->H; q.Wfull = d->W;
             int nt = 0;

@@ -1,0 +1,79 @@
+// Hardware probe (diagnostics, not on the product path): does a tcgen05.mma K-major SWIZZLE_128B operand
+// descriptor accept a start address that is 128-byte- but not 1024-byte-aligned, and a stride between 8-row
+// groups (SBO) other than 1024 B?  A "yes" lets a 3x3 convolution read all nine filter taps as shifted views
+// of ONE halo tile in shared memory instead of nine im2col TMA loads.
+//   A: [rows_a][64] bf16 (row-major) loaded with tiled TMA (128B swizzle) at a 1024-aligned smem base,
+//   B: [64][64] bf16,  D[128][64] = A_view * B^T with A_view row r = A[shift + (r/8)*(sbo/128) + r%8].
+#include "tc_common.cuh"
+
+namespace sr {
+
+__global__ void __launch_bounds__(128, 1)
+umma_shift_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int rows_a,
+                        int shift, int sbo_bytes, int base_offset, float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sa = smem;                               // rows_a x 128 B
+    uint8_t* sb = smem + (size_t)rows_a * 128;        // 64 x 128 B (rows_a is a multiple of 8)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 64 * 128);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bars, 1); mbar_init(bars + 1, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bars, (uint32_t)(rows_a * 128 + 64 * 128));
+        for (int r0 = 0; r0 < rows_a; r0 += 128) tma_load_2d(sa + (size_t)r0 * 128, &map_a, bars, 0, r0);
+        tma_load_2d(sb, &map_b, bars, 0, 0);
+        mbar_wait(bars, 0);
+        tc_fence_after();
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+        uint64_t adesc = 0;
+        const uint32_t a_addr = smem_u32(sa) + (uint32_t)shift * 128u;
+        adesc |= (uint64_t)((a_addr & 0x3FFFF) >> 4);
+        adesc |= (uint64_t)1 << 16;
+        adesc |= (uint64_t)((uint32_t)sbo_bytes >> 4) << 32;
+        adesc |= (uint64_t)1 << 46;
+        adesc |= (uint64_t)(base_offset & 7) << 49;
+        adesc |= (uint64_t)2 << 61;
+        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sb));
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        umma_commit(bars + 1);
+    }
+    __syncthreads();
+    mbar_wait(bars + 1, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+int debug_umma_shift(const void* a, int rows_a, const void* b, int shift, int sbo_bytes, int base_offset, float* out, cudaStream_t st) {
+    int rc = load_driver_fns();
+    if (rc != SR_OK) return rc;
+    SR_REQUIRE(rows_a % 128 == 0 && rows_a >= 128 && rows_a <= 1536, "probe: rows_a must be a multiple of 128 in [128, 1536]");
+    alignas(64) CUtensorMap map_a, map_b;
+    rc = make_tiled2d_map(&map_a, a, (uint64_t)rows_a, 64, 128);
+    if (rc != SR_OK) return rc;
+    rc = make_tiled2d_map(&map_b, b, 64, 64, 64);
+    if (rc != SR_OK) return rc;
+    const size_t smem = 1024 + (size_t)rows_a * 128 + 64 * 128 + 64;
+    cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    umma_shift_probe_kernel<<<1, 128, smem, st>>>(map_a, map_b, rows_a, shift, sbo_bytes, base_offset, out);
+    count_launch();
+    return check_launch("umma_shift_probe_kernel");
+}
+
+}  // namespace sr
