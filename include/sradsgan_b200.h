@@ -119,6 +119,14 @@ int sr_bn_act_fwd(const void* x, int dtype, int64_t rows, int C, const float* ga
 int sr_bn_act_bwd(const void* gy, const void* x, int dtype, int64_t rows, int C, const float* save, float slope,
                   void* dx, float* dgamma, float* dbeta, void* stream);
 
+/* Second-order piece of the WGAN-GP penalty (torch.autograd.grad(..., create_graph=True) through D followed by
+ * .backward(), model/sradsgan.py:621,639,886): with dx = sr_bn_act_bwd(gy, x) and a cotangent u = dL/d(dx), writes
+ * d_gy = dL/d(gy), d_x = dL/d(x) (both in `dtype`) and d_gamma = dL/d(gamma) (fp32, overwritten).  `save`, `dgamma`,
+ * `dbeta` are the outputs of sr_bn_act_fwd / sr_bn_act_bwd for the same (gy, x).  workspace: >= 3*C floats. */
+int sr_bn_act_bwd_bwd(const void* u, const void* gy, const void* x, int dtype, int64_t rows, int C, const float* save,
+                      const float* dgamma, const float* dbeta, float slope, void* d_gy, void* d_x, float* d_gamma,
+                      void* workspace, void* stream);
+
 /* out[c] = sum over rows of x[rows][C] (fp32 accumulate); sq (may be NULL) = sum of squares.
  * BatchNorm2d batch statistics (model/sradsgan.py:478) and bias gradients. */
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate,

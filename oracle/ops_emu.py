@@ -159,6 +159,26 @@ class EmuBackend:
         dx = v(scale) * (g - v(dbeta) / m - xh * v(dgamma) / m)
         return dx.to(x.dtype).contiguous(memory_format=torch.channels_last), dgamma, dbeta
 
+    def bn_act_bwd_bwd(self, u, gy, x, save, dgamma, dbeta, slope):
+        """autograd through a differentiable restatement of bn_act_bwd (independent of the kernel's closed form)"""
+        self.launches += 2
+        with torch.enable_grad():
+            xs = x.detach().float().requires_grad_(True)
+            gs = gy.detach().float().requires_grad_(True)
+            rstd0, scale0, shift0 = save[1], save[2], save[3]
+            gam = (scale0 / rstd0).detach().requires_grad_(True)
+            eps_var = (1.0 / (rstd0 * rstd0)).view(1, -1, 1, 1)               # var + eps of the forward pass
+            v = lambda t: t.view(1, -1, 1, 1)
+            mean = xs.mean((0, 2, 3)); var = xs.var((0, 2, 3), unbiased=False)
+            rstd = torch.rsqrt(v(var) + (eps_var - v(var.detach())))          # same eps, differentiable in x
+            xh = (xs - v(mean)) * rstd
+            mask = torch.where(x.float() * v(scale0) + v(shift0) > 0, 1.0, slope)
+            gz = gs * mask
+            dx = v(gam) * rstd * (gz - gz.mean((0, 2, 3), keepdim=True) - xh * (gz * xh).mean((0, 2, 3), keepdim=True))
+            d_gy, d_x, d_gamma = torch.autograd.grad((dx * u.float()).sum(), [gs, xs, gam])
+        cl = lambda t: t.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        return cl(d_gy), cl(d_x), d_gamma
+
     def colsum(self, x2d, want_sq=False):
         self.launches += 1
         f = x2d.float()

@@ -19,7 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
-    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_debug_umma_shift",
+    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift",
 ]
 
 
@@ -77,6 +77,8 @@ def load():
     lib.sr_act_bwd.argtypes = [vp, i32, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp, i32, vp]
     lib.sr_bn_act_fwd.argtypes = [vp, i32, i64, i32, vp, vp, f32, f32, f32, vp, vp, vp, vp, vp, vp]
     lib.sr_bn_act_bwd.argtypes = [vp, vp, i32, i64, i32, vp, f32, vp, vp, vp, vp]
+    lib.sr_bn_act_bwd_bwd.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
+    lib.sr_bn_act_bwd_bwd.restype = i32
     lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
     lib.sr_debug_umma_shift.restype = i32
     for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
@@ -302,6 +304,20 @@ class CudaBackend:
         _check(self.lib.sr_bn_act_bwd(_ptr(gy), _ptr(x), _dt(x), n * h * w, c, _ptr(save), float(slope), _ptr(dx), _ptr(dgamma),
                                       _ptr(dbeta), _stream()), "bn_act_bwd")
         return dx, dgamma, dbeta
+
+    def bn_act_bwd_bwd(self, u, gy, x, save, dgamma, dbeta, slope):
+        """cotangent u of dx -> (d_gy, d_x, d_gamma)"""
+        x = _nhwc(x)
+        gy = _nhwc(gy.to(x.dtype))
+        u = _nhwc(u.to(x.dtype))
+        n, c, h, w = x.shape
+        d_gy = torch.empty_like(x)
+        d_x = torch.empty_like(x)
+        d_gamma = torch.empty((c,), dtype=torch.float32, device=x.device)
+        ws = torch.empty((3 * c,), dtype=torch.float32, device=x.device)
+        _check(self.lib.sr_bn_act_bwd_bwd(_ptr(u), _ptr(gy), _ptr(x), _dt(x), n * h * w, c, _ptr(save), _ptr(dgamma), _ptr(dbeta),
+                                          float(slope), _ptr(d_gy), _ptr(d_x), _ptr(d_gamma), _ptr(ws), _stream()), "bn_act_bwd_bwd")
+        return d_gy, d_x, d_gamma
 
     # -- reductions / optimiser ----------------------------------------------------------------
     def colsum(self, x2d, want_sq=False):

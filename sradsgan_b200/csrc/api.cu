@@ -53,6 +53,8 @@ int act_bwd(const void*, int, const void*, int, int, float, int, int, int, int, 
 // bn.cu
 int bn_act_fwd(const void*, int, long long, int, const float*, const float*, float, float, float, float*, float*, void*, float*, float*, cudaStream_t);
 int bn_act_bwd(const void*, const void*, int, long long, int, const float*, float, void*, float*, float*, cudaStream_t);
+int bn_act_bwd_bwd(const void*, const void*, const void*, int, long long, int, const float*, const float*, const float*, float, void*, void*,
+                   float*, float*, cudaStream_t);
 // elementwise.cu
 int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
@@ -224,6 +226,16 @@ int sr_bn_act_bwd(const void* gy, const void* x, int dtype, int64_t rows, int C,
     if (rc) return rc;
     SR_REQUIRE(gy && x && save && dx && dgamma && dbeta && rows > 0 && C > 0 && C % 4 == 0, "bn_act_bwd: bad arguments");
     return bn_act_bwd(gy, x, dtype, rows, C, save, slope, dx, dgamma, dbeta, (cudaStream_t)stream);
+}
+
+int sr_bn_act_bwd_bwd(const void* u, const void* gy, const void* x, int dtype, int64_t rows, int C, const float* save,
+                      const float* dgamma, const float* dbeta, float slope, void* d_gy, void* d_x, float* d_gamma, void* workspace,
+                      void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(u && gy && x && save && dgamma && dbeta && d_gy && d_x && d_gamma && workspace && rows > 0 && C > 0 && C % 4 == 0,
+               "bn_act_bwd_bwd: bad arguments");
+    return bn_act_bwd_bwd(u, gy, x, dtype, rows, C, save, dgamma, dbeta, slope, d_gy, d_x, d_gamma, (float*)workspace, (cudaStream_t)stream);
 }
 
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate, void* stream) {

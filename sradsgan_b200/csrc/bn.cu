@@ -131,6 +131,102 @@ bn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Double backward (WGAN-GP: d/d(gy, x, gamma) of <u, dx> where dx = bn_act_bwd(gy, x, gamma), reference
+// model/sradsgan.py:621 create_graph=True + :639/:886).  With N rows per channel, r = rstd, xh = (x-mean) r,
+// m = lrelu'(z), gz = gy m, a = mean(gz), b = mean(gz xh), ub = mean(u), uxb = mean(u xh),
+// S1 = sum u (gz - a - xh b):
+//     t      = u - ub - xh uxb
+//     d_gy   = m gamma r t
+//     d_x    = -gamma r^2 [ (S1/N) xh + b t + uxb (gz - a - xh b) ]
+//     d_gamma= r S1
+// (the LeakyReLU mask is piecewise constant, so it contributes no second derivative).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd2_reduce_kernel(const T* __restrict__ u, const T* __restrict__ gy, const T* __restrict__ x, long long rows, int C,
+                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, float slope, float* __restrict__ sums /* [3][C]: u, u*xh, u*gz */) {
+    __shared__ float s1[8][33], s2[8][33], s3[8][33];
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + lane;
+    float a = 0.f, b = 0.f, d = 0.f;
+    if (c < C) {
+        const float sc = scale[c], sh = shift[c], mu = mean[c], rs = rstd[c];
+        for (long long r = (long long)blockIdx.x * 8 + wy; r < rows; r += (long long)gridDim.x * 8) {
+            const float xv = to_f32<T>(x[r * C + c]);
+            const float uv = to_f32<T>(u[r * C + c]);
+            float g = to_f32<T>(gy[r * C + c]);
+            if (!(xv * sc + sh > 0.f)) g *= slope;
+            a += uv; b += uv * (xv - mu) * rs; d += uv * g;
+        }
+    }
+    s1[wy][lane] = a; s2[wy][lane] = b; s3[wy][lane] = d;
+    __syncthreads();
+    if (wy == 0 && c < C) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { a += s1[i][lane]; b += s2[i][lane]; d += s3[i][lane]; }
+        atomicAdd(sums + c, a);
+        atomicAdd(sums + C + c, b);
+        atomicAdd(sums + 2 * C + c, d);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd2_apply_kernel(const T* __restrict__ u, const T* __restrict__ gy, const T* __restrict__ x, long long total, long long rows, int C,
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                     const float* __restrict__ sums, float slope, T* __restrict__ d_gy, T* __restrict__ d_x, float* __restrict__ d_gamma) {
+    const float invN = 1.f / (float)rows;
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float a = dbeta[c] * invN, b = dgamma[c] * invN;
+            d_gamma[c] = rstd[c] * (sums[2 * C + c] - a * sums[c] - b * sums[C + c]);
+        }
+    }
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
+        const int c = (int)(i % C);
+        float xv[4], g[4], uv[4], og[4], ox[4];
+        load4<T>(x + i, xv);
+        load4<T>(gy + i, g);
+        load4<T>(u + i, uv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ck = c + k;
+            const float sc = scale[ck], rs = rstd[ck];
+            const float a = dbeta[ck] * invN, b = dgamma[ck] * invN;
+            const float ub = sums[ck] * invN, uxb = sums[C + ck] * invN;
+            const float s1n = (sums[2 * C + ck] - a * sums[ck] - b * sums[C + ck]) * invN;
+            const float m = (xv[k] * sc + shift[ck] > 0.f) ? 1.f : slope;
+            const float xh = (xv[k] - mean[ck]) * rs;
+            const float gz = g[k] * m;
+            const float t = uv[k] - ub - xh * uxb;
+            og[k] = m * sc * t;
+            ox[k] = -sc * rs * (s1n * xh + b * t + uxb * (gz - a - xh * b));
+        }
+        store4<T>(d_gy + i, og[0], og[1], og[2], og[3]);
+        store4<T>(d_x + i, ox[0], ox[1], ox[2], ox[3]);
+    }
+}
+
+template <typename T>
+static int bn_bwd2_t(const void* u, const void* gy, const void* x, long long rows, int C, const float* save, const float* dgamma,
+                     const float* dbeta, float slope, void* d_gy, void* d_x, float* d_gamma, float* ws, cudaStream_t st) {
+    const float *mean = save, *rstd = save + C, *scale = save + 2 * C, *shift = save + 3 * C;
+    cudaMemsetAsync(ws, 0, sizeof(float) * 3 * C, st);
+    const int cy = (int)cdiv(C, 32);
+    long long bx = std::min<long long>(cdiv(148 * 8, cy), cdiv(rows, 8));
+    bn_bwd2_reduce_kernel<T><<<dim3((unsigned)bx, (unsigned)cy), 256, 0, st>>>((const T*)u, (const T*)gy, (const T*)x, rows, C, scale, shift,
+                                                                               mean, rstd, slope, ws);
+    const long long total = rows * C;
+    const int blocks = (int)std::min<long long>(148 * 16, cdiv(total, 1024));
+    bn_bwd2_apply_kernel<T><<<blocks, 256, 0, st>>>((const T*)u, (const T*)gy, (const T*)x, total, rows, C, scale, shift, mean, rstd, dgamma,
+                                                    dbeta, ws, slope, (T*)d_gy, (T*)d_x, d_gamma);
+    count_launch(2);
+    return check_launch("bn_act_bwd_bwd");
+}
+
 template <typename T>
 static int bn_fwd_t(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps, float momentum,
                     float slope, float* rm, float* rv, void* y, float* save /* [4][C]: mean, rstd, scale, shift */, float* ws,
@@ -177,6 +273,12 @@ int bn_act_bwd(const void* gy, const void* x, int dtype, long long rows, int C, 
                float* dgamma, float* dbeta, cudaStream_t st) {
     if (dtype == SR_F32) return bn_bwd_t<float>(gy, x, rows, C, save, slope, dx, dgamma, dbeta, st);
     return bn_bwd_t<__nv_bfloat16>(gy, x, rows, C, save, slope, dx, dgamma, dbeta, st);
+}
+
+int bn_act_bwd_bwd(const void* u, const void* gy, const void* x, int dtype, long long rows, int C, const float* save,
+                   const float* dgamma, const float* dbeta, float slope, void* d_gy, void* d_x, float* d_gamma, float* ws, cudaStream_t st) {
+    if (dtype == SR_F32) return bn_bwd2_t<float>(u, gy, x, rows, C, save, dgamma, dbeta, slope, d_gy, d_x, d_gamma, ws, st);
+    return bn_bwd2_t<__nv_bfloat16>(u, gy, x, rows, C, save, dgamma, dbeta, slope, d_gy, d_x, d_gamma, ws, st);
 }
 
 }  // namespace sr

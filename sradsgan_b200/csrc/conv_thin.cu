@@ -22,56 +22,92 @@ struct ThinParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Cs <= 4 -> Cd (multiple of 16). block = 64 pixels x 4 channel groups of 16.
+// Cs <= 4 -> Cd (multiple of 64).  Register tile: one thread = 4 consecutive pixels of a row x 16 channels, so
+// every 16-byte weight read from shared memory feeds 16 FMAs (a 1-pixel tile is shared-memory-bandwidth bound).
+// block = 64 pixel groups x 4 channel groups.
 // ---------------------------------------------------------------------------------------------
-template <typename TIn, typename TOut, int K, int CS>
+constexpr int TCI_PX = 4;
+
+template <int ACT> __device__ __forceinline__ float thin_act(float x, float slope) {
+    if (ACT == SR_ACT_LRELU) return fmaxf(x, x * slope);
+    if (ACT == SR_ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == SR_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+    return x;
+}
+
+template <typename TIn, typename TOut, int K, int CS, int ACT>
 __global__ void __launch_bounds__(256)
 thin_cin_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restrict__ wpk, const float* __restrict__ bias,
                 TOut* __restrict__ dst) {
-    extern __shared__ __align__(16) float thin_smem[];     // ws[tap][cs][Cd]
-    constexpr int TAPS = K * K, NIN = TAPS * CS;
+    extern __shared__ __align__(16) float thin_smem[];     // ws[tap][cs][Cd], then bias[Cd]
+    constexpr int TAPS = K * K, NIN = TAPS * CS, WIN = TCI_PX + K - 1;
     for (int i = threadIdx.x; i < NIN * p.Cd; i += 256) {
         const int cd = i % p.Cd; const int r = i / p.Cd; const int cs = r % CS; const int tap = r / CS;
-        thin_smem[i] = to_f32<TIn>(wpk[((long long)tap * p.Cd + cd) * CS + cs]);
-    }
-    __syncthreads();
-    const long long M = (long long)p.N * p.Ho * p.Wo;
-    const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
-    if (pix >= M) return;
-    const int cg = threadIdx.x & 3;
-    const int ox = (int)(pix % p.Wo); const long long q = pix / p.Wo;
-    const int oy = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
-    float in[NIN];
-#pragma unroll
-    for (int tap = 0; tap < TAPS; ++tap) {
         const int ky = tap / K, kx = tap - ky * K;
-        const int oyy = p.flip ? (K - 1 - ky) : ky, oxx = p.flip ? (K - 1 - kx) : kx;
-        const int sy = oy + oyy - p.pad, sx = ox + oxx - p.pad;
-        const bool ok = sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
-        const TIn* sp = src + (((long long)n * p.H + sy) * p.W + sx) * CS;
+        const int wt = p.flip ? (K - 1 - ky) * K + (K - 1 - kx) : tap;      // window offset (ky,kx) reads weight tap wt
+        thin_smem[i] = to_f32<TIn>(wpk[((long long)wt * p.Cd + cd) * CS + cs]);
+    }
+    float* bias_s = thin_smem + NIN * p.Cd;
+    for (int i = threadIdx.x; i < p.Cd; i += 256) bias_s[i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int groups_x = (p.Wo + TCI_PX - 1) / TCI_PX;
+    const long long G = (long long)p.N * p.Ho * groups_x;
+    const long long grp = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
+    if (grp >= G) return;
+    const int cg = threadIdx.x & 3;
+    const int gx = (int)(grp % groups_x); const long long q = grp / groups_x;
+    const int oy = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
+    const int ox0 = gx * TCI_PX;
+    // input window: K rows x (4 + K - 1) columns x CS channels (zero outside the image)
+    float in[K][WIN][CS];
 #pragma unroll
-        for (int cs = 0; cs < CS; ++cs) in[tap * CS + cs] = ok ? to_f32<TIn>(sp[cs]) : 0.f;
+    for (int r = 0; r < K; ++r) {
+        const int sy = oy + r - p.pad;
+#pragma unroll
+        for (int c = 0; c < WIN; ++c) {
+            const int sx = ox0 + c - p.pad;
+            const bool ok = sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
+            const TIn* sp = src + (((long long)n * p.H + (ok ? sy : 0)) * p.W + (ok ? sx : 0)) * CS;
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) in[r][c][cs] = ok ? to_f32<TIn>(sp[cs]) : 0.f;
+        }
     }
     for (int c0 = cg * 16; c0 < p.Cd; c0 += 64) {
-        float acc[16];
+        float acc[TCI_PX][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
+        for (int j = 0; j < 16; ++j) {
+            const float b = bias_s[c0 + j];
 #pragma unroll
-        for (int i = 0; i < NIN; ++i) {
-            const float v = in[i];
-            const float4* wr = reinterpret_cast<const float4*>(thin_smem + (size_t)i * p.Cd + c0);
+            for (int px = 0; px < TCI_PX; ++px) acc[px][j] = b;
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 w = wr[j];
-                acc[j * 4] = fmaf(v, w.x, acc[j * 4]); acc[j * 4 + 1] = fmaf(v, w.y, acc[j * 4 + 1]);
-                acc[j * 4 + 2] = fmaf(v, w.z, acc[j * 4 + 2]); acc[j * 4 + 3] = fmaf(v, w.w, acc[j * 4 + 3]);
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const float4* wr = reinterpret_cast<const float4*>(thin_smem + (size_t)((ky * K + kx) * CS + cs) * p.Cd + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w = wr[j];
+#pragma unroll
+                        for (int px = 0; px < TCI_PX; ++px) {
+                            const float v = in[ky][px + kx][cs];
+                            acc[px][j * 4] = fmaf(v, w.x, acc[px][j * 4]); acc[px][j * 4 + 1] = fmaf(v, w.y, acc[px][j * 4 + 1]);
+                            acc[px][j * 4 + 2] = fmaf(v, w.z, acc[px][j * 4 + 2]); acc[px][j * 4 + 3] = fmaf(v, w.w, acc[px][j * 4 + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+        for (int px = 0; px < TCI_PX; ++px) {
+            if (ox0 + px < p.Wo) {
+                TOut* o = dst + ((((long long)n * p.Ho + oy) * p.Wo) + ox0 + px) * p.Cd + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    store4<TOut>(o + j, thin_act<ACT>(acc[px][j], p.slope), thin_act<ACT>(acc[px][j + 1], p.slope),
+                                 thin_act<ACT>(acc[px][j + 2], p.slope), thin_act<ACT>(acc[px][j + 3], p.slope));
             }
         }
-        TOut* o = dst + pix * p.Cd + c0;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-            store4<TOut>(o + j, apply_act(acc[j], p.act, p.slope), apply_act(acc[j + 1], p.act, p.slope),
-                         apply_act(acc[j + 2], p.act, p.slope), apply_act(acc[j + 3], p.act, p.slope));
     }
 }
 
@@ -155,29 +191,35 @@ thin_cout_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restric
 // weight gradients
 // ---------------------------------------------------------------------------------------------
 // thin input (Cin <= 4), wide output (Cout multiple of 64): dw[co][ci][tap] += sum_pix dy[pix][co] * x[pix@tap][ci]
+// block = 16 output-channel quads x 16 pixel streams; a thread keeps a [4 co][28] accumulator tile in registers so
+// each 16-byte shared-memory read feeds 16 FMAs; pixel chunks of 64 are staged (dy as fp32, x im2col'ed) in smem.
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 thin_wgrad_ci_kernel(ThinParams p, const TIn* __restrict__ x, const TIn* __restrict__ dy, float* __restrict__ dw, int chunks_per_block) {
     // p.Cs = Cin (thin), p.Cd = Cout (wide); blockIdx.y = 64-wide block of output channels
-    __shared__ __align__(16) float xs[64][40];          // per pixel: taps*Cin (<= 36) source values
-    __shared__ float red[4][64];
+    __shared__ __align__(16) float xs[64][28];          // per pixel: taps*Cin (<= 27) source values, zero padded
+    __shared__ __align__(16) float gs[64][64];          // dy of the chunk
+    __shared__ float red[64][28];
     const int taps = p.k * p.k, nin = taps * p.Cs;
-    const int s = threadIdx.x >> 6, c = threadIdx.x & 63;
-    const int co = blockIdx.y * 64 + c;
+    const int s = threadIdx.x >> 4, cq = threadIdx.x & 15;
+    const int co0 = blockIdx.y * 64;
     const long long M = (long long)p.N * p.Ho * p.Wo;
-    float acc[36];
+    float acc[4][28];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = 0.f;
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 28; ++i) acc[a][i] = 0.f;
+    for (int i = threadIdx.x; i < 64 * 28; i += 256) (&red[0][0])[i] = 0.f;
     for (int ch = 0; ch < chunks_per_block; ++ch) {
         const long long p0 = ((long long)blockIdx.x * chunks_per_block + ch) * 64;
         if (p0 >= M) break;
         __syncthreads();
-        for (int i = threadIdx.x; i < 64 * nin; i += 256) {
-            const int pl = i / nin, r = i - pl * nin;
-            const int tap = r / p.Cs, ci = r - tap * p.Cs;
+        for (int i = threadIdx.x; i < 64 * 28; i += 256) {
+            const int pl = i / 28, r = i - pl * 28;
             const long long pix = p0 + pl;
             float v = 0.f;
-            if (pix < M) {
+            if (pix < M && r < nin) {
+                const int tap = r / p.Cs, ci = r - tap * p.Cs;
                 const int ox = (int)(pix % p.Wo); const long long q = pix / p.Wo;
                 const int oy = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
                 const int ky = tap / p.k, kx = tap - ky * p.k;
@@ -186,35 +228,43 @@ thin_wgrad_ci_kernel(ThinParams p, const TIn* __restrict__ x, const TIn* __restr
             }
             xs[pl][r] = v;
         }
-        for (int i = threadIdx.x; i < 64 * (36 - nin); i += 256) xs[i / (36 - nin)][nin + i % (36 - nin)] = 0.f;
-        __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
-            const int pl = s * 16 + j;
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int pl = i >> 4, v4 = (i & 15) * 4;
             const long long pix = p0 + pl;
-            const float g = (pix < M) ? to_f32<TIn>(dy[pix * p.Cd + co]) : 0.f;
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pix < M) load4<TIn>(dy + pix * p.Cd + co0 + v4, g);
+            *reinterpret_cast<float4*>(&gs[pl][v4]) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pl = s * 4 + j;
+            const float4 g = *reinterpret_cast<const float4*>(&gs[pl][cq * 4]);
             const float4* xr = reinterpret_cast<const float4*>(&xs[pl][0]);
 #pragma unroll
-            for (int i = 0; i < 9; ++i) {
+            for (int i = 0; i < 7; ++i) {
                 const float4 v = xr[i];
-                acc[i * 4] = fmaf(g, v.x, acc[i * 4]); acc[i * 4 + 1] = fmaf(g, v.y, acc[i * 4 + 1]);
-                acc[i * 4 + 2] = fmaf(g, v.z, acc[i * 4 + 2]); acc[i * 4 + 3] = fmaf(g, v.w, acc[i * 4 + 3]);
+                const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    acc[a][i * 4] = fmaf(gv[a], v.x, acc[a][i * 4]); acc[a][i * 4 + 1] = fmaf(gv[a], v.y, acc[a][i * 4 + 1]);
+                    acc[a][i * 4 + 2] = fmaf(gv[a], v.z, acc[a][i * 4 + 2]); acc[a][i * 4 + 3] = fmaf(gv[a], v.w, acc[a][i * 4 + 3]);
+                }
             }
         }
     }
-    // combine the 4 pixel streams, then one atomic per output element
+    // combine the 16 pixel streams in shared memory, then one global atomic per output element
+    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 36; ++i) {
-        if (i < nin) {            // uniform across the block
-            __syncthreads();
-            red[s][c] = acc[i];
-            __syncthreads();
-            if (s == 0) {
-                const float v = red[0][c] + red[1][c] + red[2][c] + red[3][c];
-                const int tap = i / p.Cs, ci = i - tap * p.Cs;
-                atomicAdd(dw + ((long long)co * p.Cs + ci) * taps + tap, v);
-            }
-        }
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 28; ++i)
+            if (i < nin) atomicAdd(&red[cq * 4 + a][i], acc[a][i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * nin; i += 256) {
+        const int c = i / nin, r = i - c * nin;
+        const int tap = r / p.Cs, ci = r - tap * p.Cs;
+        atomicAdd(dw + ((long long)(co0 + c) * p.Cs + ci) * taps + tap, red[c][r]);
     }
 }
 
@@ -312,16 +362,24 @@ bool thin_fwd_supported(const sr_conv_desc* d, bool dgrad) {
 
 bool thin_wgrad_supported(const sr_conv_desc* d) {
     if (!thin_geom_ok(d)) return false;
-    if (d->Cin <= 4 && d->Cout % 64 == 0 && d->kh * d->kw * d->Cin <= 36) return true;
+    if (d->Cin <= 4 && d->Cout % 64 == 0 && d->kh * d->kw * d->Cin <= 27) return true;
     if (d->Cout <= 4 && d->Cin % 64 == 0 && d->kh == 3) return true;
     return false;
 }
 
 template <typename TIn, typename TOut, int K, int CS>
 static void thin_cin_launch(const ThinParams& p, const void* src, const void* w, const float* bias, void* dst, cudaStream_t st) {
-    const long long M = (long long)p.N * p.Ho * p.Wo;
-    const size_t smem = sizeof(float) * K * K * CS * p.Cd;
-    thin_cin_kernel<TIn, TOut, K, CS><<<(unsigned)cdiv(M, 64), 256, smem, st>>>(p, (const TIn*)src, (const TIn*)w, bias, (TOut*)dst);
+    const long long G = (long long)p.N * p.Ho * cdiv(p.Wo, TCI_PX);
+    const size_t smem = sizeof(float) * (K * K * CS * p.Cd + p.Cd);
+    const unsigned grid = (unsigned)cdiv(G, 64);
+#define SR_THIN_CIN(A) thin_cin_kernel<TIn, TOut, K, CS, A><<<grid, 256, smem, st>>>(p, (const TIn*)src, (const TIn*)w, bias, (TOut*)dst)
+    switch (p.act) {
+        case SR_ACT_LRELU: SR_THIN_CIN(SR_ACT_LRELU); break;
+        case SR_ACT_RELU: SR_THIN_CIN(SR_ACT_RELU); break;
+        case SR_ACT_SIGMOID: SR_THIN_CIN(SR_ACT_SIGMOID); break;
+        default: SR_THIN_CIN(SR_ACT_NONE); break;
+    }
+#undef SR_THIN_CIN
 }
 
 template <typename TIn, typename TOut, int K>
@@ -368,7 +426,7 @@ static int thin_wgrad_t(const ThinParams& p, bool thin_ci, const void* x, const 
     const long long M = (long long)p.N * p.Ho * p.Wo;
     if (thin_ci) {
         const long long chunks = cdiv(M, 64);
-        const int cpb = (int)std::max<long long>(1, cdiv(chunks, 148 * 4));
+        const int cpb = (int)std::max<long long>(1, cdiv(chunks, 148 * 2 / std::max(1, p.Cd / 64)));
         dim3 grid((unsigned)cdiv(chunks, cpb), (unsigned)(p.Cd / 64));
         thin_wgrad_ci_kernel<TIn><<<grid, 256, 0, st>>>(p, (const TIn*)x, (const TIn*)dy, dw, cpb);
     } else {

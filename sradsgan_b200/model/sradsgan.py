@@ -399,10 +399,11 @@ class Discriminator(nn.Module):
 
     def forward(self, img):
         x = ops.to_compute(img)
-        # The WGAN-GP pass differentiates D twice (reference :621,:639): it feeds a LEAF that requires grad
-        # (`interpolates.requires_grad_(True)`, :611) and must run on the any-order differentiable ops.  Every
-        # other pass (G-step critic, D real / fake) is first-order and takes the fused kernels.
-        if ops.config.double_backward or (img.requires_grad and img.is_leaf) or not self.training:
+        # Every pass — G-step critic, D real / fake, and the WGAN-GP pass that is differentiated twice (reference
+        # :611-621,:639) — runs the same fused kernels: conv(+bias+LReLU) and train-mode BatchNorm+LReLU Functions
+        # whose backward passes are themselves differentiable Functions.  `ops.config.double_backward` (tests) and
+        # eval mode take the unfused module-by-module path.
+        if ops.config.double_backward or not self.training:
             return self.model(x)
         mods = list(self.model)
         i = 0
@@ -411,14 +412,11 @@ class Discriminator(nn.Module):
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             nxt2 = mods[i + 2] if i + 2 < len(mods) else None
             if isinstance(m, Conv2d) and isinstance(nxt, BatchNorm2d) and isinstance(nxt2, LeakyReLU):
-                x = ops.bn_leaky_relu(m.fused(x), nxt, nxt2.negative_slope)       # conv -> fused BN+LReLU
+                x = ops.bn_leaky_relu(m(x), nxt, nxt2.negative_slope)             # conv -> fused BN+LReLU
                 i += 3
             elif isinstance(m, Conv2d) and isinstance(nxt, LeakyReLU):
-                x = m.fused(x, ACT_LRELU, nxt.negative_slope)                     # conv + LReLU epilogue
+                x = ops.conv2d_act(x, m.weight, m.bias, m.stride, m.padding, ACT_LRELU, nxt.negative_slope)   # conv + LReLU epilogue
                 i += 2
-            elif isinstance(m, Conv2d):
-                x = m.fused(x)
-                i += 1
             else:
                 x = m(x)
                 i += 1

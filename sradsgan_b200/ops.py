@@ -242,21 +242,92 @@ def local_attn_chain(x, t, ca, sa, conv):
 
 
 # ----------------------------------------------------------------------------------------------
-# train-mode BatchNorm2d + LeakyReLU, first-order (discriminator passes that are not the gradient penalty)
+# any-order differentiable fused blocks of the discriminator (first-order passes AND the WGAN-GP double backward
+# run on the same kernels): conv+bias+LeakyReLU, and train-mode BatchNorm2d+LeakyReLU
 # ----------------------------------------------------------------------------------------------
+class ActBwd(Function):
+    """gpre = gy * act'(y).  Linear in gy (y only selects the slope), so its own derivative is ActBwd again."""
+
+    @staticmethod
+    def forward(ctx, gy, y, act, slope, g):
+        ctx.act, ctx.slope, ctx.g = act, slope, g
+        ctx.save_for_backward(y)
+        return _lib.backend().act_bwd(gy, y, act, slope, 0, g, y.dtype)
+
+    @staticmethod
+    def backward(ctx, u):
+        (y,) = ctx.saved_tensors
+        return ActBwd.apply(u.to(y.dtype), y, ctx.act, ctx.slope, ctx.g), None, None, None, None
+
+
+class ConvActFwd(Function):
+    """y = act(conv(x, w) + b) in ONE kernel, differentiable to any order (backward = ActBwd -> ConvDgrad / ConvWgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, act, slope):
+        g = conv_geom(x.shape, w.shape, stride, pad)
+        ctx.g, ctx.act, ctx.slope, ctx.has_bias = g, act, slope, b is not None
+        y = _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, act, slope, impl=config.conv_impl)
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        g = ctx.g
+        gpre = ActBwd.apply(gy.to(x.dtype), y, ctx.act, ctx.slope, g)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgrad.apply(gpre, w, g)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = ConvWgrad.apply(x, gpre, g)
+            if not ctx.has_bias:
+                gb = None
+        return gx, gw, gb, None, None, None, None
+
+
+def conv2d_act(x, w, b, stride, pad, act, slope):
+    return ConvActFwd.apply(to_compute(x), w, b, stride, pad, act, slope)
+
+
+class BNActBwd(Function):
+    """(dx, dgamma, dbeta) of y = lrelu(batchnorm_train(x)); its backward is the fused double-backward kernel
+    (cotangent of dx only — the penalty never differentiates the parameter gradients)."""
+
+    @staticmethod
+    def forward(ctx, gy, x, gamma, save, slope):
+        dx, dgamma, dbeta = _lib.backend().bn_act_bwd(gy, x, save, slope)
+        ctx.slope = slope
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(gy, x, save, dgamma, dbeta)
+        return dx, dgamma, dbeta
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u, u_dgamma, u_dbeta):
+        if u_dgamma is not None or u_dbeta is not None:
+            raise NotImplementedError("BNActBwd: second derivatives through the BatchNorm parameter gradients are not used by WGAN-GP")
+        if u is None:
+            return None, None, None, None, None
+        gy, x, save, dgamma, dbeta = ctx.saved_tensors
+        d_gy, d_x, d_gamma = _lib.backend().bn_act_bwd_bwd(u, gy, x, save, dgamma, dbeta, ctx.slope)
+        return d_gy, d_x, d_gamma, None, None
+
+
 class BatchNormLeakyReLU(Function):
+    """y = lrelu(batchnorm_train(x; gamma, beta)) with running-stat update; differentiable twice."""
+
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, slope):
         y, save = _lib.backend().bn_act_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, slope)
         ctx.slope = slope
-        ctx.save_for_backward(x, save)
+        ctx.save_for_backward(x, gamma, save)
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, gy):
-        x, save = ctx.saved_tensors
-        dx, dgamma, dbeta = _lib.backend().bn_act_bwd(gy, x, save, ctx.slope)
+        x, gamma, save = ctx.saved_tensors
+        dx, dgamma, dbeta = BNActBwd.apply(gy.to(x.dtype), x, gamma, save, ctx.slope)
         return dx, dgamma, dbeta, None, None, None, None, None
 
 

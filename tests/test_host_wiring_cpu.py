@@ -95,6 +95,9 @@ def test_discriminator_double_backward_wiring(emu):
         if ref[k].grad is None:      # e.g. the last bias: the input-gradient does not depend on it
             assert p.grad is None or p.grad.abs().max() == 0, k
             continue
+        if p.grad is None:           # BatchNorm shifts: the penalty's gradient does not depend on them (exact zeros in torch)
+            assert ref[k].grad.abs().max() == 0, k
+            continue
         assert rel(p.grad, ref[k].grad) < 5e-4, k
     for k in sd:
         if "running" in k:
