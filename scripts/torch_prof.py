@@ -21,7 +21,7 @@ def mark(name):
         ctx["cur"].__exit__(None, None, None)
     ctx["cur"] = record_function("PHASE:" + name)
     ctx["cur"].__enter__()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     net._phase_mark = mark
     net.train_step(lr, hr)
     torch.cuda.synchronize()
@@ -44,6 +44,13 @@ for e in evs:
         continue
     for k in e.kernels:
         short = re.sub(r"<.*", "", k.name).replace("void ", "")[:60]
+        if not short.startswith("sr::"):
+            shp = ""
+            try:
+                shp = str([tuple(x) for x in e.input_shapes if x][:2])
+            except Exception:
+                pass
+            short = (short.replace("at::native::", "")[:28] + " <- " + e.name.replace("aten::", "") + " " + shp)[:100]
         a = agg[phase_of(e.time_range.start)][short]
         a[0] += 1; a[1] += k.duration
 seen = set()
@@ -54,5 +61,5 @@ for ph in names[1:] + ["end", "?"]:
     tot = sum(v[1] for v in agg[ph].values())
     ours = sum(v[1] for k, v in agg[ph].items() if k.startswith("sr::"))
     print("== %-18s total %8.2f ms | sr:: %8.2f ms | other %8.2f ms | launches %d" % (ph, tot / 1e3, ours / 1e3, (tot - ours) / 1e3, sum(v[0] for v in agg[ph].values())))
-    for k, v in sorted(agg[ph].items(), key=lambda kv: -kv[1][1])[:14]:
-        print("      %-62s %5d %9.3f ms" % (k, v[0], v[1] / 1e3))
+    for k, v in sorted(agg[ph].items(), key=lambda kv: -kv[1][1])[:24]:
+        print("      %-100s %5d %9.3f ms" % (k, v[0], v[1] / 1e3))

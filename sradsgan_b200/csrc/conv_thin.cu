@@ -192,59 +192,90 @@ thin_cout_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restric
 // ---------------------------------------------------------------------------------------------
 // thin input (Cin <= 4), wide output (Cout multiple of 64): dw[co][ci][tap] += sum_pix dy[pix][co] * x[pix@tap][ci]
 // block = 16 output-channel quads x 16 pixel streams; a thread keeps a [4 co][28] accumulator tile in registers so
-// each 16-byte shared-memory read feeds 16 FMAs; pixel chunks of 64 are staged (dy as fp32, x im2col'ed) in smem.
+// each 16-byte shared-memory read feeds 16 FMAs.  Pixel chunks of 64 are double-buffered in shared memory: the dy
+// tile of chunk k+1 arrives by cp.async and the im2col'ed x values of chunk k+1 sit in registers while chunk k is
+// being multiplied, so global-memory latency is hidden with one block (8 warps) per SM.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = pred ? 16 : 0;       // src-size 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 thin_wgrad_ci_kernel(ThinParams p, const TIn* __restrict__ x, const TIn* __restrict__ dy, float* __restrict__ dw, int chunks_per_block) {
     // p.Cs = Cin (thin), p.Cd = Cout (wide); blockIdx.y = 64-wide block of output channels
-    __shared__ __align__(16) float xs[64][28];          // per pixel: taps*Cin (<= 27) source values, zero padded
-    __shared__ __align__(16) float gs[64][64];          // dy of the chunk
-    __shared__ float red[64][28];
+    constexpr int VEC = 16 / (int)sizeof(TIn);          // dy elements per 16-byte cp.async
+    __shared__ __align__(16) float xs[2][64][28];       // per pixel: taps*Cin (<= 27) source values, zero padded
+    __shared__ __align__(16) TIn gs[2][64][64];         // dy of the chunk
+    float (*red)[28] = xs[0];                           // reused after the main loop for the cross-stream reduction
     const int taps = p.k * p.k, nin = taps * p.Cs;
     const int s = threadIdx.x >> 4, cq = threadIdx.x & 15;
     const int co0 = blockIdx.y * 64;
-    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const int M = p.N * p.Ho * p.Wo;                    // < 2^31 (checked by the caller)
+    // gather role: thread = (pixel gl, 7 consecutive im2col columns starting at gr0)
+    const int gl = threadIdx.x >> 2, gr0 = (threadIdx.x & 3) * 7;
+    int g_dy[7], g_dx[7], g_ci[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const int r = gr0 + j;
+        const int tap = r / p.Cs, ci = r - tap * p.Cs;
+        const int ky = tap / p.k, kx = tap - ky * p.k;
+        g_dy[j] = ky - p.pad; g_dx[j] = kx - p.pad; g_ci[j] = r < nin ? ci : -1;
+    }
     float acc[4][28];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int i = 0; i < 28; ++i) acc[a][i] = 0.f;
-    for (int i = threadIdx.x; i < 64 * 28; i += 256) (&red[0][0])[i] = 0.f;
-    for (int ch = 0; ch < chunks_per_block; ++ch) {
-        const long long p0 = ((long long)blockIdx.x * chunks_per_block + ch) * 64;
-        if (p0 >= M) break;
-        __syncthreads();
-        for (int i = threadIdx.x; i < 64 * 28; i += 256) {
-            const int pl = i / 28, r = i - pl * 28;
-            const long long pix = p0 + pl;
+
+    float xr[7];
+    auto prefetch = [&](int ch, int buf) {
+        const int p0 = (blockIdx.x * chunks_per_block + ch) * 64;
+        const int pix = p0 + gl;
+        const bool okp = pix < M;
+        int ox = 0, oy = 0, base = 0;
+        if (okp) {
+            ox = pix % p.Wo; const int q = pix / p.Wo;
+            oy = q % p.Ho; base = (q / p.Ho) * p.H * p.W;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const int sy = oy + g_dy[j], sx = ox + g_dx[j];
             float v = 0.f;
-            if (pix < M && r < nin) {
-                const int tap = r / p.Cs, ci = r - tap * p.Cs;
-                const int ox = (int)(pix % p.Wo); const long long q = pix / p.Wo;
-                const int oy = (int)(q % p.Ho); const int n = (int)(q / p.Ho);
-                const int ky = tap / p.k, kx = tap - ky * p.k;
-                const int sy = oy + ky - p.pad, sx = ox + kx - p.pad;
-                if (sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) v = to_f32<TIn>(x[(((long long)n * p.H + sy) * p.W + sx) * p.Cs + ci]);
-            }
-            xs[pl][r] = v;
+            if (okp && g_ci[j] >= 0 && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W)
+                v = to_f32<TIn>(x[(long long)(base + sy * p.W + sx) * p.Cs + g_ci[j]]);
+            xr[j] = v;
         }
-        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-            const int pl = i >> 4, v4 = (i & 15) * 4;
-            const long long pix = p0 + pl;
-            float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (pix < M) load4<TIn>(dy + pix * p.Cd + co0 + v4, g);
-            *reinterpret_cast<float4*>(&gs[pl][v4]) = make_float4(g[0], g[1], g[2], g[3]);
+        for (int i = threadIdx.x; i < 64 * (64 / VEC); i += 256) {
+            const int pl = i / (64 / VEC), v0 = (i % (64 / VEC)) * VEC;
+            const int px = p0 + pl;
+            cp_async16(&gs[buf][pl][v0], dy + (long long)(px < M ? px : 0) * p.Cd + co0 + v0, px < M);
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+    const int first_p0 = blockIdx.x * chunks_per_block * 64;
+    int nch = 0;
+    if (first_p0 < M) nch = min(chunks_per_block, (M - first_p0 + 63) / 64);
+    if (nch > 0) prefetch(0, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+        const int buf = ch & 1;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) xs[buf][gl][gr0 + j] = xr[j];
+        cp_async_wait_all();
+        __syncthreads();                                 // chunk `ch` is complete in buffer `buf`; buffer buf^1 is free
+        if (ch + 1 < nch) prefetch(ch + 1, buf ^ 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int pl = s * 4 + j;
-            const float4 g = *reinterpret_cast<const float4*>(&gs[pl][cq * 4]);
-            const float4* xr = reinterpret_cast<const float4*>(&xs[pl][0]);
+            float gv[4];
+            load4<TIn>(&gs[buf][pl][cq * 4], gv);
+            const float4* xrow = reinterpret_cast<const float4*>(&xs[buf][pl][0]);
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
-                const float4 v = xr[i];
-                const float gv[4] = {g.x, g.y, g.z, g.w};
+                const float4 v = xrow[i];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     acc[a][i * 4] = fmaf(gv[a], v.x, acc[a][i * 4]); acc[a][i * 4 + 1] = fmaf(gv[a], v.y, acc[a][i * 4 + 1]);
@@ -254,6 +285,8 @@ thin_wgrad_ci_kernel(ThinParams p, const TIn* __restrict__ x, const TIn* __restr
         }
     }
     // combine the 16 pixel streams in shared memory, then one global atomic per output element
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 28; i += 256) (&red[0][0])[i] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -362,7 +395,7 @@ bool thin_fwd_supported(const sr_conv_desc* d, bool dgrad) {
 
 bool thin_wgrad_supported(const sr_conv_desc* d) {
     if (!thin_geom_ok(d)) return false;
-    if (d->Cin <= 4 && d->Cout % 64 == 0 && d->kh * d->kw * d->Cin <= 27) return true;
+    if (d->Cin <= 4 && d->Cout % 64 == 0 && d->kh * d->kw * d->Cin <= 27 && (long long)d->N * d->Ho * d->Wo < (1ll << 31) - 64) return true;
     if (d->Cout <= 4 && d->Cin % 64 == 0 && d->kh == 3) return true;
     return false;
 }
@@ -426,7 +459,7 @@ static int thin_wgrad_t(const ThinParams& p, bool thin_ci, const void* x, const 
     const long long M = (long long)p.N * p.Ho * p.Wo;
     if (thin_ci) {
         const long long chunks = cdiv(M, 64);
-        const int cpb = (int)std::max<long long>(1, cdiv(chunks, 148 * 2 / std::max(1, p.Cd / 64)));
+        const int cpb = (int)std::max<long long>(1, cdiv(chunks, std::max(1, 148 / std::max(1, p.Cd / 64))));   // one wave, 1 block / SM
         dim3 grid((unsigned)cdiv(chunks, cpb), (unsigned)(p.Cd / 64));
         thin_wgrad_ci_kernel<TIn><<<grid, 256, 0, st>>>(p, (const TIn*)x, (const TIn*)dy, dw, cpb);
     } else {
