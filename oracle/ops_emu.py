@@ -89,6 +89,12 @@ class EmuBackend:
         db = dy.float().sum(dim=(0, 2, 3)) if want_bias else None
         return dw.contiguous(), db
 
+    def conv_wgrad_into(self, x, dy, g, dw, db, impl=0):
+        gw, gb = self.conv_wgrad(x, dy, g, want_bias=db is not None)
+        dw.add_(gw)
+        if db is not None:
+            db.add_(gb)
+
     # fused local-attention chain: emulated with the oracle's own building blocks + torch autograd
     @staticmethod
     def _la_math(x, t, fc1, fc2, w7, W, b):
@@ -109,7 +115,7 @@ class EmuBackend:
         z16 = z32.to(x.dtype) if want_lowp else None
         return z32, z16, {"t_shape": t.shape, "b": b.detach().float()}
 
-    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True):
+    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
         self.launches += 6
         dz = (gz32.float() if gz32 is not None else 0) + (gz16.float() if gz16 is not None else 0)
         with torch.enable_grad():
@@ -118,6 +124,9 @@ class EmuBackend:
             bs = sv["b"].clone().requires_grad_(True)
             z = self._la_math(xs, torch.zeros(sv["t_shape"]), ps[0], ps[1], ps[2], ps[3], bs)
             grads = torch.autograd.grad(z, [xs] + ps + [bs], dz)
+        if into is not None:
+            for t, gr in zip(into, grads[1:]):
+                t.add_(gr)
         return (grads[0].to(x.dtype).contiguous(memory_format=torch.channels_last), grads[1], grads[2], grads[3], grads[4], grads[5],
                 dz.contiguous(memory_format=torch.channels_last) if want_dz else None)
 

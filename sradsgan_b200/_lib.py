@@ -219,6 +219,19 @@ class CudaBackend:
             self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 0, _stream()), "conv2d_wgrad"))
         return dw, db
 
+    def conv_wgrad_into(self, x, dy, g, dw, db, impl=IMPL_AUTO):
+        """dw (+)= wgrad, db (+)= colsum(dy): accumulate into existing fp32 buffers (FlatAdam's flat gradient views)"""
+        _require_cuda(x, dy, dw)
+        x = _nhwc(x)
+        dy = _nhwc(dy)
+        if x.dtype != dy.dtype:
+            dy = dy.to(x.dtype)
+        if dw.dtype != torch.float32 or not dw.is_contiguous() or (db is not None and (db.dtype != torch.float32 or not db.is_contiguous())):
+            raise ValueError("conv_wgrad_into: contiguous fp32 gradient buffers required")
+        d = self._desc(g, _dt(x), SR_F32, impl=impl)
+        self._timed("wgrad", d, False, lambda: _check(
+            self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 1, _stream()), "conv2d_wgrad"))
+
     # -- fused local-attention chain ---------------------------------------------------------------
     def la_chain_fwd(self, x, t, fc1, fc2, w7, W, b, want_lowp=True):
         """z = Conv1x1(SLAM(CLAM(x))) + t  ->  (z32, z16 | None, saved)"""
@@ -242,8 +255,8 @@ class CudaBackend:
                                         _ptr(sv["q"]), _ptr(sv["cstar"]), _ptr(ws), _stream()), "la_chain_fwd")
         return z32, z16, sv
 
-    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True):
-        """-> (dx, d_fc1, d_fc2, d_w7, dW, db, dz)"""
+    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
+        """-> (dx, d_fc1, d_fc2, d_w7, dW, db, dz); `into` = [d_fc1, d_fc2, d_w7, dW, db] fp32 buffers to accumulate into"""
         x = _nhwc(x)
         n, c, h, w = x.shape
         cr = fc1.shape[0]
@@ -254,8 +267,11 @@ class CudaBackend:
             gz16 = _nhwc(gz16.to(x.dtype))
         f32 = dict(dtype=torch.float32, device=dev)
         dx = torch.empty_like(x)
-        d_fc1 = torch.zeros(fc1.shape, **f32); d_fc2 = torch.zeros(fc2.shape, **f32); d_w7 = torch.zeros(w7.shape, **f32)
-        dW = torch.zeros(W.shape, **f32); db = torch.zeros((c,), **f32)
+        if into is not None:
+            d_fc1, d_fc2, d_w7, dW, db = into
+        else:
+            d_fc1 = torch.zeros(fc1.shape, **f32); d_fc2 = torch.zeros(fc2.shape, **f32); d_w7 = torch.zeros(w7.shape, **f32)
+            dW = torch.zeros(W.shape, **f32); db = torch.zeros((c,), **f32)
         if want_dz and gz32 is not None and gz16 is None:
             dz, dz_ptr = gz32, None             # the residual gradient is the incoming gradient itself
         elif want_dz:

@@ -40,7 +40,9 @@ class BucketReducer:
             self.chunk_size = [len(c[3]) for c in opt.chunks]
             for p, n in zip(opt.params, opt.names):
                 ci = name_to_chunk[n]
-                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(ci)))
+                hook = self._make_hook(ci)
+                self._handles.append(p.register_post_accumulate_grad_hook(hook))
+                p._sr_grad_ready = hook    # fired by ops.py when a kernel accumulated this gradient in place
 
     def _make_hook(self, ci):
         def hook(param):

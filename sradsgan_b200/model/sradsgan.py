@@ -318,6 +318,9 @@ class GAB_UP(nn.Module):
             for _ in range(int(math.log(upscale_factor, 3))):
                 upsampling += three
         self.upsampling = nn.Sequential(*upsampling)
+        if len(upsampling) > 3:            # one conv applied at several stages: its gradient is a sum over the uses
+            for p in upsampling[0].parameters():
+                p._sr_shared = True
 
     def forward(self, x):
         out = x

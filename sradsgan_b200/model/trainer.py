@@ -104,8 +104,9 @@ class SRADSGAN(object):
         interpolates = (alpha * real_samples + ((1 - alpha) * fake_samples)).requires_grad_(True)      # :611
         d_interpolates = discriminator(interpolates)
         grad_outputs = torch.ones_like(d_interpolates)
-        gradients = torch.autograd.grad(outputs=d_interpolates, inputs=interpolates, grad_outputs=grad_outputs,
-                                        create_graph=True, retain_graph=True, only_inputs=True)[0]     # :621
+        with ops.input_grad_only():      # only d/d(interpolates) is wanted here; weight gradients come from .backward()
+            gradients = torch.autograd.grad(outputs=d_interpolates, inputs=interpolates, grad_outputs=grad_outputs,
+                                            create_graph=True, retain_graph=True, only_inputs=True)[0]     # :621
         gradients = gradients.float()
         if grad_penalty_Lp_norm == 'Linf':
             grad_norm, _ = torch.max(torch.abs(gradients), 1)

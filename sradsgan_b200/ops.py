@@ -17,9 +17,54 @@ class Config:
     compute_dtype = torch.bfloat16     # activations / MMA operands ("bf16 mode"); torch.float32 = "fp32 mode"
     conv_impl = IMPL_AUTO              # SR_IMPL_* forced for every conv (tests)
     double_backward = False            # force the any-order differentiable (unfused) discriminator path
+    input_grad_only = False            # backward passes skip parameter gradients (see input_grad_only())
+    direct_grad = True                 # first-order backward adds weight gradients straight into FlatAdam's flat buffer
 
 
 config = Config()
+
+
+class input_grad_only:
+    """Context manager for `torch.autograd.grad(outputs, inputs=<activations>)` calls: custom Functions cannot see
+    which of their inputs the engine actually needs (ctx.needs_input_grad is fixed at forward time), so without
+    this the WGAN-GP input-gradient pass (reference model/sradsgan.py:621) would also compute — and discard — every
+    discriminator weight gradient."""
+
+    def __enter__(self):
+        self.prev = config.input_grad_only
+        config.input_grad_only = True
+
+    def __exit__(self, *a):
+        config.input_grad_only = self.prev
+
+
+def _grad_target(p):
+    """flat-buffer gradient view of parameter p when a first-order backward may accumulate into it directly"""
+    if not config.direct_grad or torch.is_grad_enabled() or p is None or getattr(p, "_sr_shared", False):
+        return None                    # weight-tied parameters (used more than once per forward) go through autograd's sum
+    return getattr(p, "_sr_flat_grad", None)
+
+
+def _wgrad(x, gy, g, w, b, has_bias, need_w, need_b):
+    """weight / bias gradient of one convolution inside a backward pass -> (gw, gb) to RETURN to autograd.
+    First-order passes over FlatAdam-owned parameters accumulate in place (no temporary, no memset, no add
+    kernel) and return None; the parameter's `_sr_grad_ready` callback tells the data-parallel reducer."""
+    if config.input_grad_only or not (need_w or (has_bias and need_b)):
+        return None, None
+    tw = _grad_target(w)
+    tb = _grad_target(b) if has_bias else None
+    if tw is not None and (not has_bias or tb is not None):
+        _lib.backend().conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
+        for p in (w, b):
+            cb = getattr(p, "_sr_grad_ready", None) if p is not None else None
+            if cb is not None:
+                cb(p)
+        return None, None
+    if torch.is_grad_enabled():
+        gw, gb = ConvWgrad.apply(x, gy, g)
+    else:
+        gw, gb = _lib.backend().conv_wgrad(x, gy, g, want_bias=has_bias, impl=config.conv_impl)
+    return gw, (gb if has_bias else None)
 
 
 def set_precision(mode):
@@ -81,6 +126,7 @@ class ConvFwd(Function):
         g = conv_geom(x.shape, w.shape, stride, pad)
         ctx.g = g
         ctx.has_bias = b is not None
+        ctx.bias = b                   # only its identity is used (gradient target lookup)
         ctx.save_for_backward(x, w)
         return _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, impl=config.conv_impl)
 
@@ -92,10 +138,7 @@ class ConvFwd(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = ConvDgrad.apply(gy, w, g)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw, gb = ConvWgrad.apply(x, gy, g)
-            if not ctx.has_bias:
-                gb = None
+        gw, gb = _wgrad(x, gy, g, w, ctx.bias, ctx.has_bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, None, None
 
 
@@ -117,7 +160,7 @@ class ConvDgrad(Function):
         if ctx.needs_input_grad[0]:
             d_gy = ConvFwd.apply(ggx, w, None, g.stride, g.pad)
         if ctx.needs_input_grad[1]:
-            d_w, _ = ConvWgrad.apply(ggx, gy, g)
+            d_w, _ = _wgrad(ggx, gy, g, w, None, False, True, False)
         return d_gy, d_w, None
 
 
@@ -164,6 +207,7 @@ class ConvFused(Function):
         g = conv_geom(x.shape, w.shape, stride, pad)
         ctx.g, ctx.act, ctx.slope, ctx.r = g, act, slope, shuffle_r
         ctx.has_bias, ctx.has_res = b is not None, residual is not None
+        ctx.bias = b
         if act != ACT_NONE and residual is not None:
             raise NotImplementedError("ConvFused: activation together with a residual is not used by this model")
         y = _lib.backend().conv_fwd(x, packed(w, 0, x.dtype, shuffle_r), b, residual, g, act, slope, shuffle_r,
@@ -186,8 +230,7 @@ class ConvFused(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = _lib.backend().conv_dgrad(gpre, packed(w, 1, gpre.dtype), g, impl=config.conv_impl)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw, gb = _lib.backend().conv_wgrad(x, gpre, g, want_bias=ctx.has_bias, impl=config.conv_impl)
+        gw, gb = _wgrad(x, gpre, g, w, ctx.bias, ctx.has_bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, g_res, None, None, None, None, None, None
 
 
@@ -212,6 +255,7 @@ class LocalAttnChain(Function):
         z32, z16, sv = _lib.backend().la_chain_fwd(x, t, fc1, fc2, w7, W, b, want_lowp=lowp)
         ctx.sv = sv
         ctx.lowp = lowp
+        ctx.params = (fc1, fc2, w7, W, b)
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, fc1, fc2, w7, W)
         return (z32, z16) if lowp else z32
@@ -222,8 +266,16 @@ class LocalAttnChain(Function):
         x, fc1, fc2, w7, W = ctx.saved_tensors
         if gz32 is None and gz16 is None:
             return (None,) * 8
+        targets = [_grad_target(p) for p in ctx.params]
+        into = targets if all(t is not None for t in targets) else None
         dx, d_fc1, d_fc2, d_w7, dW, db, dz = _lib.backend().la_chain_bwd(gz32, gz16, x, ctx.sv, fc1, fc2, w7, W,
-                                                                          want_dz=ctx.needs_input_grad[1])
+                                                                          want_dz=ctx.needs_input_grad[1], into=into)
+        if into is not None:
+            for p in ctx.params:
+                cb = getattr(p, "_sr_grad_ready", None)
+                if cb is not None:
+                    cb(p)
+            return dx, dz, None, None, None, None, None, None
         return dx, dz, d_fc1, d_fc2, d_w7, dW, db, None
 
 
@@ -267,6 +319,7 @@ class ConvActFwd(Function):
     def forward(ctx, x, w, b, stride, pad, act, slope):
         g = conv_geom(x.shape, w.shape, stride, pad)
         ctx.g, ctx.act, ctx.slope, ctx.has_bias = g, act, slope, b is not None
+        ctx.bias = b
         y = _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, act, slope, impl=config.conv_impl)
         ctx.save_for_backward(x, w, y)
         return y
@@ -279,10 +332,7 @@ class ConvActFwd(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = ConvDgrad.apply(gpre, w, g)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw, gb = ConvWgrad.apply(x, gpre, g)
-            if not ctx.has_bias:
-                gb = None
+        gw, gb = _wgrad(x, gpre, g, w, ctx.bias, ctx.has_bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, None, None, None, None
 
 

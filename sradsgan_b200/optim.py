@@ -35,6 +35,7 @@ class FlatAdam:
             self.flat_param[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + k].view(p.shape)
             p.grad = self.flat_grad[off:off + k].view(p.shape)
+            p._sr_flat_grad = p.grad       # ops.py: first-order backward passes accumulate straight into this view
             self.offsets[n] = (off, k)
             off += (k + 3) // 4 * 4
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps}]
