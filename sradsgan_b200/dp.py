@@ -18,6 +18,29 @@ def is_dist():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+def world_size():
+    return dist.get_world_size() if is_dist() else 1
+
+
+def all_reduce_flat(buf, group=None):
+    """sum all-reduce of a flat gradient buffer on the current stream (no-op for one process)"""
+    if is_dist():
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+
+
+class NullReducer:
+    """stands in for BucketReducer while CUDA graphs are being captured (collectives are issued between replays)"""
+
+    def __init__(self, world=1):
+        self.world = world
+
+    def arm(self):
+        pass
+
+    def finish(self):
+        return 1.0 / self.world
+
+
 class BucketReducer:
     """Overlapped chunked all-reduce of a FlatAdam gradient buffer."""
 
@@ -40,9 +63,9 @@ class BucketReducer:
             self.chunk_size = [len(c[3]) for c in opt.chunks]
             for p, n in zip(opt.params, opt.names):
                 ci = name_to_chunk[n]
-                hook = self._make_hook(ci)
-                self._handles.append(p.register_post_accumulate_grad_hook(hook))
-                p._sr_grad_ready = hook    # fired by ops.py when a kernel accumulated this gradient in place
+                # fires once per backward per parameter — also when a kernel accumulated the gradient in place and
+                # the Function returned None for it (the AccumulateGrad node still runs its post hooks)
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(ci)))
 
     def _make_hook(self, ci):
         def hook(param):

@@ -85,7 +85,10 @@ class SRADSGAN(object):
                                     clamp=(-self.clip_value, self.clip_value))
         dp.broadcast_parameters(self.optimizer_G)
         dp.broadcast_parameters(self.optimizer_D)
-        self.reducer_G = dp.BucketReducer(self.optimizer_G, overlap=True)
+        # The G bucket (44 MB) can be all-reduced chunk by chunk (one chunk per ResGroup) while backward is still
+        # running (SR_DP_OVERLAP=1, eager launches only); at ~0.1 ms per bucket over NVLink the default is one
+        # all-reduce per network after its backward.
+        self.reducer_G = dp.BucketReducer(self.optimizer_G, overlap=os.environ.get("SR_DP_OVERLAP", "0") == "1")
         self.reducer_D = dp.BucketReducer(self.optimizer_D, overlap=False)
 
     def criterion_content(self, a, b):
@@ -126,11 +129,11 @@ class SRADSGAN(object):
     # ------------------------------------------------------------------------------------------
     # one iteration (reference :829-892)
     # ------------------------------------------------------------------------------------------
-    def train_step(self, imgs_lr, imgs_hr, fuse_gp_backward=True):
+    def _g_phase(self, imgs_lr, imgs_hr):
+        """generator forward + loss + backward (reference :829-857): leaves the gradients in optimizer_G.flat_grad"""
         G, D, Fx = self.generator, self.discriminator, self.feature_extractor
         mark = getattr(self, "_phase_mark", None) or (lambda name: None)
         mark("start")
-        # ---- generator ----
         self.optimizer_G.zero_grad()
         for p in self.optimizer_D.params:
             p.requires_grad_(False)          # skip D's weight gradients in the G step (discarded by the reference, :865)
@@ -148,14 +151,16 @@ class SRADSGAN(object):
         self.reducer_G.arm()
         loss_G.backward()
         mark("G_step_backward")
-        scale = self.reducer_G.finish()
-        self.optimizer_G.step(grad_scale=scale)                                     # :857-858
-        mark("adam_G")
         for p in self.optimizer_D.params:
             p.requires_grad_(True)
-        # ---- discriminator ----
+        return {"loss_G": loss_G.detach(), "pixel": pixel_loss_G.detach(), "content": loss_content.detach(),
+                "adv": loss_gan.detach(), "gen_hr": gen_hr.detach()}
+
+    def _d_phase(self, imgs_hr, gen_det, fuse_gp_backward=True):
+        """discriminator losses + WGAN-GP + backward (reference :865-886): gradients in optimizer_D.flat_grad"""
+        D = self.discriminator
+        mark = getattr(self, "_phase_mark", None) or (lambda name: None)
         self.optimizer_D.zero_grad()                                                # :865
-        gen_det = gen_hr.detach()
         loss_real = self.criterion_raGAN(D(imgs_hr), True)                          # :876
         loss_fake = self.criterion_raGAN(D(gen_det), False)                         # :877
         loss_D = loss_real + loss_fake
@@ -174,20 +179,30 @@ class SRADSGAN(object):
         else:
             gp = torch.zeros((), device=imgs_hr.device)
             loss_D.backward()
+        return {"loss_D": loss_D.detach(), "gp": gp.detach()}
+
+    def train_step(self, imgs_lr, imgs_hr, fuse_gp_backward=True):
+        mark = getattr(self, "_phase_mark", None) or (lambda name: None)
+        out = self._g_phase(imgs_lr, imgs_hr)
+        scale = self.reducer_G.finish()
+        self.optimizer_G.step(grad_scale=scale)                                     # :857-858
+        mark("adam_G")
+        out.update(self._d_phase(imgs_hr, out["gen_hr"], fuse_gp_backward))
         self.reducer_D.arm()
         scale = self.reducer_D.finish()
         self.optimizer_D.step(grad_scale=scale)                                     # :887 + clamp :891-892 (fused)
         mark("adam_D")
-        return {"loss_G": loss_G.detach(), "loss_D": loss_D.detach(), "pixel": pixel_loss_G.detach(),
-                "content": loss_content.detach(), "adv": loss_gan.detach(), "gp": gp.detach(), "gen_hr": gen_det}
+        return out
 
     # ------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole iteration
     # ------------------------------------------------------------------------------------------
     def graphed_step(self, imgs_lr, imgs_hr):
-        """train_step captured ONCE into a CUDA graph (~5k kernel launches -> one cudaGraphLaunch) and
-        replayed; inputs / the GP interpolation factors are staged into static device buffers, the Adam
-        step counters live on the device.  Re-capture happens when the input shape or a learning rate changes."""
+        """train_step captured ONCE into CUDA graphs (~6k kernel launches -> a few cudaGraphLaunch) and replayed;
+        inputs / the GP interpolation factors are staged into static device buffers, the Adam step counters live
+        on the device.  One process: a single graph.  Data parallel: three graph segments (G phase | Adam_G + D
+        phase | Adam_D) with the two NCCL gradient all-reduces issued BETWEEN the replays — collectives are never
+        captured.  Re-capture happens when the input shape or a learning rate changes."""
         key = (tuple(imgs_lr.shape), tuple(imgs_hr.shape), self.optimizer_G.param_groups[0]["lr"], self.optimizer_D.param_groups[0]["lr"])
         if self._graph is None or self._graph["key"] != key:
             self._capture(imgs_lr, imgs_hr, key)
@@ -196,13 +211,21 @@ class SRADSGAN(object):
         g["hr"].copy_(imgs_hr, non_blocking=True)
         g["alpha_host"].copy_(torch.from_numpy(np.random.random((imgs_hr.size(0), 1, 1, 1))).float())   # reference :609
         g["alpha"].copy_(g["alpha_host"], non_blocking=True)
-        g["graph"].replay()
+        if len(g["graphs"]) == 1:
+            g["graphs"][0].replay()
+        else:
+            g["graphs"][0].replay()
+            dp.all_reduce_flat(self.optimizer_G.flat_grad)
+            g["graphs"][1].replay()
+            dp.all_reduce_flat(self.optimizer_D.flat_grad)
+            g["graphs"][2].replay()
         self.optimizer_G.step_count += 1
         self.optimizer_D.step_count += 1
         return g["out"]
 
     def _capture(self, imgs_lr, imgs_hr, key):
         dev = imgs_lr.device
+        world = dp.world_size()
         st = {"key": key, "lr": torch.empty_like(imgs_lr), "hr": torch.empty_like(imgs_hr),
               "alpha": torch.empty(imgs_hr.size(0), 1, 1, 1, device=dev),
               "alpha_host": torch.empty(imgs_hr.size(0), 1, 1, 1).pin_memory()}
@@ -211,18 +234,36 @@ class SRADSGAN(object):
         self._alpha_override = st["alpha"]
         # snapshot everything a step mutates, so that warm-up + capture do not advance the training state
         snap = [t.clone() for t in self._mutable_state()]
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(2):
-                self.train_step(st["lr"], st["hr"])
-        torch.cuda.current_stream().wait_stream(s)
-        graph = torch.cuda.CUDAGraph()
-        n0 = _lib.backend().launch_count()
-        with torch.cuda.graph(graph):
-            st["out"] = self.train_step(st["lr"], st["hr"])
-        st["launches"] = _lib.backend().launch_count() - n0     # library kernels per replay
-        torch.cuda.synchronize()
+        red = (self.reducer_G, self.reducer_D)
+        self.reducer_G, self.reducer_D = dp.NullReducer(world), dp.NullReducer(world)     # no collectives while warming up / capturing
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self.train_step(st["lr"], st["hr"])
+            torch.cuda.current_stream().wait_stream(s)
+            n0 = _lib.backend().launch_count()
+            if world == 1:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    st["out"] = self.train_step(st["lr"], st["hr"])
+                graphs = [graph]
+            else:
+                g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, capture_error_mode="thread_local"):
+                    out = self._g_phase(st["lr"], st["hr"])
+                with torch.cuda.graph(g2, pool=g1.pool(), capture_error_mode="thread_local"):
+                    self.optimizer_G.step(grad_scale=1.0 / world)
+                    out.update(self._d_phase(st["hr"], out["gen_hr"]))
+                with torch.cuda.graph(g3, pool=g1.pool(), capture_error_mode="thread_local"):
+                    self.optimizer_D.step(grad_scale=1.0 / world)
+                st["out"] = out
+                graphs = [g1, g2, g3]
+            st["launches"] = _lib.backend().launch_count() - n0     # library kernels per replay
+            torch.cuda.synchronize()
+        finally:
+            self.reducer_G, self.reducer_D = red
         for t, c in zip(self._mutable_state(), snap):
             t.copy_(c)
         self.optimizer_G.step_count -= 3
@@ -230,7 +271,7 @@ class SRADSGAN(object):
         ops.bump_weight_generation()
         self._alpha_override = prev_override if prev_override is not st["alpha"] else None
         self._alpha_static = st["alpha"]
-        st["graph"] = graph
+        st["graphs"] = graphs
         self._graph = st
 
     def _mutable_state(self):

@@ -48,18 +48,14 @@ def _grad_target(p):
 def _wgrad(x, gy, g, w, b, has_bias, need_w, need_b):
     """weight / bias gradient of one convolution inside a backward pass -> (gw, gb) to RETURN to autograd.
     First-order passes over FlatAdam-owned parameters accumulate in place (no temporary, no memset, no add
-    kernel) and return None; the parameter's `_sr_grad_ready` callback tells the data-parallel reducer."""
+    kernel) and return None."""
     if config.input_grad_only or not (need_w or (has_bias and need_b)):
         return None, None
     tw = _grad_target(w)
     tb = _grad_target(b) if has_bias else None
     if tw is not None and (not has_bias or tb is not None):
         _lib.backend().conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
-        for p in (w, b):
-            cb = getattr(p, "_sr_grad_ready", None) if p is not None else None
-            if cb is not None:
-                cb(p)
-        return None, None
+        return None, None              # autograd still runs the parameter's post-accumulate hooks (dp.BucketReducer)
     if torch.is_grad_enabled():
         gw, gb = ConvWgrad.apply(x, gy, g)
     else:
@@ -271,10 +267,6 @@ class LocalAttnChain(Function):
         dx, d_fc1, d_fc2, d_w7, dW, db, dz = _lib.backend().la_chain_bwd(gz32, gz16, x, ctx.sv, fc1, fc2, w7, W,
                                                                           want_dz=ctx.needs_input_grad[1], into=into)
         if into is not None:
-            for p in ctx.params:
-                cb = getattr(p, "_sr_grad_ready", None)
-                if cb is not None:
-                    cb(p)
             return dx, dz, None, None, None, None, None, None
         return dx, dz, d_fc1, d_fc2, d_w7, dW, db, None
 
