@@ -32,7 +32,7 @@ extern "C" {
 
 enum { SR_F32 = 0, SR_BF16 = 1 };
 enum { SR_ACT_NONE = 0, SR_ACT_LRELU = 1, SR_ACT_RELU = 2, SR_ACT_SIGMOID = 3 };
-enum { SR_IMPL_AUTO = 0, SR_IMPL_SIMT = 1, SR_IMPL_TCGEN05 = 2 };
+enum { SR_IMPL_AUTO = 0, SR_IMPL_SIMT = 1, SR_IMPL_TCGEN05 = 2 /* im2col-TMA kernel */, SR_IMPL_HALO = 3 /* halo-tile kernel */ };
 
 /* Geometry of one convolution y = act(conv(x, w) + bias) [+ residual] [-> PixelShuffle(r)].
  * Replaces nn.Conv2d (+ nn.LeakyReLU / nn.ReLU / nn.PixelShuffle / `out += x`) at
@@ -146,6 +146,11 @@ int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  * accepts (shifted start address, non-1024 B group stride, descriptor base_offset field). */
 int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows, int sbo_bytes, int base_offset,
                         float* out, void* stream);
+
+/* Diagnostics: issue-rate of tcgen05.mma (M=128, N=n, K=16 bf16, operands in shared memory).  Each of `grid` CTAs
+ * issues iters x num_acc x k_steps instructions, k_steps consecutive ones into the same of num_acc TMEM accumulators;
+ * cycles[cta] = SM clock ticks from first issue to completion. */
+int sr_debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, int64_t* cycles, void* stream);
 
 #ifdef __cplusplus
 }

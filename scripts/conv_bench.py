@@ -15,6 +15,7 @@ from sradsgan_b200._lib import ACT_LRELU, ACT_NONE, conv_geom
 B = int(os.environ.get("SR_BATCH", "16"))
 ITERS = int(os.environ.get("SR_ITERS", "20"))
 ONLY = os.environ.get("SR_ONLY", "")
+IMPL = int(os.environ.get("SR_IMPL", "0"))              # 0 auto, 2 im2col tcgen05, 3 halo tcgen05
 PROFILE = os.environ.get("SR_PROFILE", "") == "1"     # one launch per kernel, no warm-up (for ncu --set full)
 
 # name, Cin, Cout, k, stride, H(in), act, shuffle_r, calls per training step (fwd, dgrad, wgrad)
@@ -74,8 +75,8 @@ def main():
         wp = be.pack_weights(w, 0, dt, r)
         wt = be.pack_weights(w, 1, dt, 0)
         dy = torch.randn(B, cout, g.Ho, g.Wo, device="cuda").to(dt).contiguous(memory_format=torch.channels_last)
-        t_f = timeit(lambda: be.conv_fwd(x, wp, b, None, g, act, 0.2, r))
-        t_d = timeit(lambda: be.conv_dgrad(dy, wt, g))
+        t_f = timeit(lambda: be.conv_fwd(x, wp, b, None, g, act, 0.2, r, impl=IMPL if (s == 1 and k == 3) else 0))
+        t_d = timeit(lambda: be.conv_dgrad(dy, wt, g, impl=IMPL if (s == 1 and k == 3) else 0))
         t_w = timeit(lambda: be.conv_wgrad(x, dy, g, want_bias=True))
         rec = {"shape": name, "gflop": flops / 1e9, "fwd_us": t_f * 1e6, "dgrad_us": t_d * 1e6, "wgrad_us": t_w * 1e6,
                "fwd_tflops": flops / t_f / 1e12, "dgrad_tflops": flops / t_d / 1e12, "wgrad_tflops": flops / t_w / 1e12,

@@ -14,12 +14,12 @@ LIB_PATH = os.path.join(_HERE, "libsradsgan_b200.so")
 
 SR_F32, SR_BF16 = 0, 1
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
-IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_HALO = 0, 1, 2, 3
 
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
-    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift",
+    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
     lib.sr_bn_act_bwd_bwd.restype = i32
     lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
     lib.sr_debug_umma_shift.restype = i32
+    lib.sr_debug_umma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
+    lib.sr_debug_umma_rate.restype = i32
     for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
         getattr(lib, name).restype = i32
     for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):

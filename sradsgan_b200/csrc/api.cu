@@ -34,6 +34,9 @@ int conv_wgrad_simt(const sr_conv_desc*, const void*, const void*, float*, cudaS
 // conv_tc.cu
 bool conv_tc_supported(const sr_conv_desc*, bool dgrad);
 int conv_tc_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+// conv_halo.cu
+bool conv_halo_supported(const sr_conv_desc*, bool dgrad);
+int conv_halo_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 // conv_tc_wgrad.cu
 bool conv_tc_wgrad_supported(const sr_conv_desc*);
 int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
@@ -62,6 +65,7 @@ int adam_step(float*, const float*, float*, float*, long long, float, float, flo
 
 // debug_probe.cu
 int debug_umma_shift(const void*, int, const void*, int, int, int, float*, cudaStream_t);
+int debug_umma_rate(int, int, int, int, int, long long*, cudaStream_t);
 
 static int g_arch_ok = -1;
 static int arch_check() {
@@ -105,7 +109,7 @@ int64_t sr_launch_count(void) { return (int64_t)g_launches.load(); }
 int sr_conv_uses_tcgen05(const sr_conv_desc* d, int kind) {
     if (!d || d->impl == SR_IMPL_SIMT) return 0;
     if (kind == 2) return conv_tc_wgrad_supported(d) ? 1 : 0;
-    return conv_tc_supported(d, kind == 1) ? 1 : 0;
+    return (conv_tc_supported(d, kind == 1) || conv_halo_supported(d, kind == 1)) ? 1 : 0;
 }
 
 int sr_pack_weights(const float* w, void* packed, int Cout, int Cin, int kh, int kw, int mode, int dtype,
@@ -127,6 +131,12 @@ int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w, const flo
     if (rc) return rc;
     SR_REQUIRE(x && w && y, "conv2d_fwd: NULL pointer");
     const bool tc_ok = conv_tc_supported(d, false);
+    const bool halo_ok = conv_halo_supported(d, false);
+    if (d->impl == SR_IMPL_HALO && !halo_ok) {
+        set_error("conv2d_fwd: the halo-tile tcgen05 path needs 3x3 / stride 1 / pad 1, bf16, Cin %% 64 == 0 (Cin=%d Cout=%d k=%d s=%d)", d->Cin, d->Cout, d->kh, d->stride);
+        return SR_ERR_UNSUPPORTED;
+    }
+    if (halo_ok && (d->impl == SR_IMPL_AUTO || d->impl == SR_IMPL_HALO)) return conv_halo_run(d, false, x, w, bias, residual, y, (cudaStream_t)stream);
     if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
         set_error("conv2d_fwd: tcgen05 path does not support this shape (Cin=%d Cout=%d k=%d s=%d dtype=%d)", d->Cin, d->Cout, d->kh, d->stride, d->in_dtype);
         return SR_ERR_UNSUPPORTED;
@@ -143,6 +153,12 @@ int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* wt, void*
     if (rc) return rc;
     SR_REQUIRE(dy && wt && dx, "conv2d_dgrad: NULL pointer");
     const bool tc_ok = conv_tc_supported(d, true);
+    const bool halo_ok = conv_halo_supported(d, true);
+    if (d->impl == SR_IMPL_HALO && !halo_ok) {
+        set_error("conv2d_dgrad: the halo-tile tcgen05 path does not support this shape");
+        return SR_ERR_UNSUPPORTED;
+    }
+    if (halo_ok && (d->impl == SR_IMPL_AUTO || d->impl == SR_IMPL_HALO)) return conv_halo_run(d, true, dy, wt, nullptr, nullptr, dx, (cudaStream_t)stream);
     if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
         set_error("conv2d_dgrad: tcgen05 path does not support this shape");
         return SR_ERR_UNSUPPORTED;
@@ -261,6 +277,13 @@ int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows
     if (rc) return rc;
     SR_REQUIRE(a && b && out && shift_rows >= 0 && sbo_bytes > 0, "debug_umma_shift: bad arguments");
     return debug_umma_shift(a, rows_a, b, shift_rows, sbo_bytes, base_offset, out, (cudaStream_t)stream);
+}
+
+int sr_debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, int64_t* cycles, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(cycles != nullptr, "debug_umma_rate: NULL output");
+    return debug_umma_rate(n, num_acc, iters, k_steps, grid, (long long*)cycles, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,443 @@
+// tcgen05 halo-tile convolution for sm_100a (B200): 3x3 / stride 1 / pad 1, forward and dgrad.
+//
+// The im2col kernel (conv_tc.cu) re-reads every activation once per filter tap (9x).  Here the activation tile is
+// loaded ONCE per 64-channel block:
+//   * one TILED 4-d TMA box {64 ch, TWp columns, TR+2 rows, 1 image} lands the tile INCLUDING its one-pixel halo
+//     (out-of-range coordinates are zero-filled by the hardware = the convolution padding) as consecutive 128-byte
+//     pixel rows, 128B-swizzled, i.e. directly as a K-major UMMA operand with pixel = M row;
+//   * output positions are numbered in the padded-linear space of the tile, q = r*TWp + cp (cp = 0 / TWp-1 are the
+//     halo columns), MMA row j <-> q = j+1, and the A operand of filter tap (ky,kx) is the SAME shared-memory tile
+//     seen through a descriptor whose start address is shifted by (ky*TWp + kx) pixel rows — the tensor core applies
+//     the 128B swizzle to absolute shared-memory addresses, so any 128 B-aligned start works
+//     (profiles/r01_umma_descriptor_probe.txt).  The 2 halo columns per row (and the rows >= TR*TWp) produce junk
+//     accumulator rows that are never stored: ~84 % of the MMA rows are useful, for 4.5x less L2->SMEM traffic;
+//   * weights: resident in shared memory for the whole kernel when the [9*Cin] x block_n slab fits (Cin = 64),
+//     else streamed tap by tap through their own TMA ring.
+// Warp roles, TMEM double buffering and the epilogue are those of conv_tc.cu.
+// Reference call sites: the 3x3 stride-1 nn.Conv2d layers of model/sradsgan.py (RAB :222-223, GAB_UP :381,
+// Discriminator :476 odd blocks, VGG19 features) and their input gradients.
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace sr {
+
+struct HaloParams {
+    int N, H, W, Cout;
+    int TWp, TW, TR;                 // padded tile width, valid columns (TWp - 2), output rows per tile
+    int tiles_x, tiles_y, p_tiles;   // pixel tiles = N * tiles_y * tiles_x
+    int block_n, n_blocks, c_blocks;
+    int flip;                        // dgrad: filter taps mirrored
+    int act; float slope; int shuffle_r;
+    int a_stage_bytes, a_box_bytes, num_a_stages, num_b_stages, resident;
+    int dual;                        // 1: two MMA-issuer warps work on two pixel tiles at once (shared weights)
+    int n_pair_items, n_items;       // per CTA lane: items [0, n_pair_items) are tile pairs, the rest single tiles
+    const float* bias;
+    const void* residual;
+    void* out;
+};
+
+constexpr int HL_EPI_WARPS = 8;
+constexpr int HL_THREADS = 96 + 32 * HL_EPI_WARPS;   // warp 0 TMA, warps 1-2 MMA issuers, warps 3..10 epilogue
+constexpr int HL_MAX_A = 6, HL_MAX_B = 16, HL_MAX_RES = 36;
+constexpr int HL_BIAS_MAX = 1024;
+constexpr int HL_TILE_BUDGET = 232448 - 1024 - 1024 - HL_BIAS_MAX * 4;
+
+// Work item `it` of this CTA -> pixel tiles (t0, t1; -1 = none) and column block.  Resident mode pins the column
+// block to the CTA (lane = CTAs sharing a column block); dual mode hands out PAIRS of pixel tiles first and the
+// ragged remainder as single tiles, so that the last round costs one tile time, not two.
+__device__ __forceinline__ bool hl_item_at(const HaloParams& p, int it, int& t0, int& t1, int& nb) {
+    int rank, lane_ctas;
+    if (p.resident) { nb = blockIdx.x % p.n_blocks; rank = blockIdx.x / p.n_blocks; lane_ctas = gridDim.x / p.n_blocks; }
+    else { nb = 0; rank = blockIdx.x; lane_ctas = gridDim.x; }
+    const int idx = rank + it * lane_ctas;
+    if (idx >= p.n_items) return false;
+    if (p.dual) {
+        if (idx < p.n_pair_items) { t0 = 2 * idx; t1 = 2 * idx + 1; if (t1 >= p.p_tiles) t1 = -1; }
+        else { t0 = 2 * p.n_pair_items + (idx - p.n_pair_items); t1 = -1; }
+    } else if (p.resident) {
+        t0 = idx; t1 = -1;
+    } else {
+        t0 = idx / p.n_blocks; nb = idx - t0 * p.n_blocks; t1 = -1;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void hl_tile_origin(const HaloParams& p, int p_tile, int& n, int& y0, int& x0) {
+    const int tx = p_tile % p.tiles_x; const int q = p_tile / p.tiles_x;
+    const int ty = q % p.tiles_y; n = q / p.tiles_y;
+    y0 = ty * p.TR; x0 = tx * p.TW;
+}
+
+// Epilogue warp.  dual: serves issuer `grp` (its own double-buffered accumulators), all 32-column chunks.
+// single: both groups serve the one issuer, chunk parity = grp.
+template <typename OutT, int ACT>
+__device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                            const float* bias_s, int quarter, int grp, int lane) {
+    const int j = quarter * 32 + lane;           // MMA row
+    const int q = j + 1;                         // padded-linear position inside the tile
+    const int tr = q / p.TWp, cp = q - tr * p.TWp;
+    const int r = p.shuffle_r > 1 ? p.shuffle_r : 1;
+    const int cq = p.Cout / (r * r);
+    const int chunks = p.block_n >> 5;
+    const int c_first = p.dual ? 0 : grp, c_step = p.dual ? 1 : 2;
+    const int acc_stride = p.dual ? 128 : 256;
+    const int bar0 = p.dual ? grp * 2 : 0;       // this warp's pair of accumulator barriers / TMEM buffers
+    OutT* out = reinterpret_cast<OutT*>(p.out);
+    const OutT* res = reinterpret_cast<const OutT*>(p.residual);
+    int acc = 0; uint32_t acc_phase = 0;
+    int t0, t1, nb;
+    for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
+        const int p_tile = (p.dual && grp == 1) ? t1 : t0;
+        if (p_tile < 0) continue;
+        int n, y0, x0;
+        hl_tile_origin(p, p_tile, n, y0, x0);
+        const int oy = y0 + tr, ox = x0 + cp - 1;
+        const bool valid = tr < p.TR && cp >= 1 && cp <= p.TW && oy < p.H && ox < p.W;
+        const long long row_idx = (((long long)n * p.H + oy) * p.W + ox) * p.Cout;
+        mbar_wait(acc_full + bar0 + acc, acc_phase);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((bar0 + acc) * acc_stride);
+        auto emit = [&](const uint32_t (&v)[32], int c) {
+            if (!valid) return;
+            const int col = nb * p.block_n + c * 32;
+            long long idx;
+            if (r > 1) {
+                const int sub = col / cq, ch0 = col - sub * cq;
+                const int si = sub / r, sj = sub - si * r;
+                idx = ((((long long)n * p.H * r + (oy * r + si)) * ((long long)p.W * r)) + (ox * r + sj)) * cq + ch0;
+            } else {
+                idx = row_idx + col;
+            }
+            tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx);
+        };
+        uint32_t va[32], vb[32];
+        int c = c_first;
+        if (c < chunks) tmem_ld32_nowait(t_base + (uint32_t)(c * 32), va);
+        while (c < chunks) {
+            tmem_ld_wait(va);
+            if (c + c_step < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + c_step) * 32), vb);
+            emit(va, c);
+            c += c_step;
+            if (c >= chunks) break;
+            tmem_ld_wait(vb);
+            if (c + c_step < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + c_step) * 32), va);
+            emit(vb, c);
+            c += c_step;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + bar0 + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.block_n * 128;
+    const int k_blocks = 9 * p.c_blocks;
+    // [resident weights: k_blocks x B] [A ring(s)] [B ring] [barriers] [bias]
+    uint8_t* a_base = smem + (p.resident ? (size_t)k_blocks * b_bytes : 0);
+    uint8_t* b_base = a_base + (size_t)p.num_a_stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.num_b_stages * b_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + HL_MAX_A;
+    uint64_t* b_full = a_empty + HL_MAX_A;
+    uint64_t* b_empty = b_full + HL_MAX_B;
+    uint64_t* acc_full = b_empty + HL_MAX_B;      // [4]: dual -> [issuer][buffer], single -> [buffer]
+    uint64_t* acc_empty = acc_full + 4;
+    uint64_t* r_full = acc_empty + 4;             // [HL_MAX_RES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + HL_MAX_RES);
+    float* bias_s = reinterpret_cast<float*>(bars) + 256;                 // 1024 B after the barrier block
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int issuers = p.dual ? 2 : 1;
+    const int ring_a = p.num_a_stages / issuers;  // each issuer owns a private ring of activation stages
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < p.num_a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < p.num_b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, issuers); }
+        for (int a = 0; a < 4; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, p.dual ? 4 : HL_EPI_WARPS); }
+        if (p.resident) for (int kb = 0; kb < k_blocks; ++kb) mbar_init(r_full + kb, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    {
+        const int r2 = p.shuffle_r > 1 ? p.shuffle_r * p.shuffle_r : 1;
+        const int cq = p.Cout / r2;
+        for (int i = threadIdx.x; i < p.Cout; i += HL_THREADS) {
+            float b = 0.f;
+            if (p.bias) { const int sub = i / cq, ch = i - sub * cq; b = p.bias[r2 > 1 ? ch * r2 + sub : i]; }
+            bias_s[i] = b;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int sa[2] = {0, 0}; uint32_t pa[2] = {0, 0};
+            int sb = 0; uint32_t pb = 0;
+            int t0, t1, nb;
+            for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    for (int w = 0; w < issuers; ++w) {
+                        const int tile = w ? t1 : t0;
+                        if (tile < 0) continue;
+                        int n, y0, x0;
+                        hl_tile_origin(p, tile, n, y0, x0);
+                        const int st = w * ring_a + sa[w];
+                        mbar_wait(a_empty + st, pa[w] ^ 1);
+                        mbar_expect_tx(a_full + st, (uint32_t)p.a_box_bytes);
+                        tma_load_4d(a_base + (size_t)st * p.a_stage_bytes, &map_a, a_full + st, cb * 64, x0 - 1, y0 - 1, n);
+                        if (++sa[w] == ring_a) { sa[w] = 0; pa[w] ^= 1; }
+                    }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kb = cb * 9 + tap;
+                        if (p.resident) {
+                            if (it == 0) {
+                                mbar_expect_tx(r_full + kb, (uint32_t)b_bytes);
+                                tma_load_2d(smem + (size_t)kb * b_bytes, &map_b, r_full + kb, cb * 64, tap * p.Cout + nb * p.block_n);
+                            }
+                        } else {
+                            mbar_wait(b_empty + sb, pb ^ 1);
+                            mbar_expect_tx(b_full + sb, (uint32_t)b_bytes);
+                            tma_load_2d(b_base + (size_t)sb * b_bytes, &map_b, b_full + sb, cb * 64, tap * p.Cout + nb * p.block_n);
+                            if (++sb == p.num_b_stages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp <= 2) {
+        // ===== MMA issuers (warp 1, and warp 2 in dual mode).  One thread issuing short dependent groups of tcgen05.mma
+        // sustains ~100 clk per instruction; two issuers on independent accumulators reach the 64 clk floor of an
+        // M=128 x N=128 instruction (profiles/r01_umma_issue_rate.txt).  The warp walks the schedule converged. =====
+        const int w = warp - 1;
+        if (w < issuers) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t tap_off[9];      // descriptor start-address offsets (16-byte units) of the nine tap views
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap % 3;
+                const int oh = p.flip ? 2 - ky : ky, ow = p.flip ? 2 - kx : kx;
+                tap_off[tap] = (uint32_t)(oh * p.TWp + ow) * 8u;
+            }
+            const uint32_t b_step = (uint32_t)b_bytes >> 4;
+            const int acc_stride = p.dual ? 128 : 256;
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            bool res_ready = false;
+            int t0, t1, nb;
+            for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
+                const bool has = (w ? t1 : t0) >= 0;
+                uint32_t d_tmem = 0;
+                if (has) {
+                    mbar_wait(acc_empty + w * 2 + acc, acc_phase ^ 1);
+                    tc_fence_after();
+                    d_tmem = tmem_base + (uint32_t)((w * 2 + acc) * acc_stride);
+                }
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    uint64_t adesc0 = 0;
+                    const int st = w * ring_a + sa;
+                    if (has) {
+                        mbar_wait(a_full + st, pa);
+                        adesc0 = make_kmajor_sw128_desc(smem_u32(a_base + (size_t)st * p.a_stage_bytes));
+                    }
+                    if (p.resident) {
+                        if (has) {
+                            const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(smem + (size_t)cb * 9 * b_bytes));
+                            if (!res_ready) {
+#pragma unroll
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    mbar_wait(r_full + cb * 9 + tap, 0);
+                                    tc_fence_after();
+                                    if (lane == 0) umma_f16_x4(d_tmem, adesc0 + tap_off[tap], bdesc0 + (uint64_t)(tap * b_step), idesc, (cb | tap) ? 1u : 0u);
+                                    __syncwarp();
+                                }
+                            } else {
+                                tc_fence_after();
+                                if (lane == 0) {
+#pragma unroll
+                                    for (int tap = 0; tap < 9; ++tap)
+                                        umma_f16_x4(d_tmem, adesc0 + tap_off[tap], bdesc0 + (uint64_t)(tap * b_step), idesc, (cb | tap) ? 1u : 0u);
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(b_full + sb, pb);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                if (has) {
+                                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)sb * b_bytes));
+                                    umma_f16_x4(d_tmem, adesc0 + tap_off[tap], bdesc, idesc, (cb | tap) ? 1u : 0u);
+                                }
+                                umma_commit(b_empty + sb);      // both issuers release every weight stage (count = issuers)
+                            }
+                            __syncwarp();
+                            if (++sb == p.num_b_stages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                    if (has) {
+                        if (lane == 0) umma_commit(a_empty + st);
+                        __syncwarp();
+                        if (++sa == ring_a) { sa = 0; pa ^= 1; }
+                    }
+                }
+                if (has) {
+                    if (p.resident) res_ready = true;
+                    if (lane == 0) umma_commit(acc_full + w * 2 + acc);
+                    __syncwarp();
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int e = warp - 3;                    // 0..7
+        const int quarter = warp & 3, grp = e >> 2;
+        switch (p.act) {
+            case SR_ACT_LRELU: hl_epilogue<OutT, SR_ACT_LRELU>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            case SR_ACT_RELU: hl_epilogue<OutT, SR_ACT_RELU>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            case SR_ACT_SIGMOID: hl_epilogue<OutT, SR_ACT_SIGMOID>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            default: hl_epilogue<OutT, SR_ACT_NONE>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int g_hl_sms = 0;
+
+static bool hl_cout_ok(int Cout) { return Cout % 64 == 0; }
+
+bool conv_halo_supported(const sr_conv_desc* d, bool dgrad) {
+    if (d->in_dtype != SR_BF16) return false;
+    if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1) return false;
+    const int Cs = dgrad ? d->Cout : d->Cin, Cd = dgrad ? d->Cin : d->Cout;
+    if (Cs % 64 != 0 || !hl_cout_ok(Cd) || Cd > HL_BIAS_MAX) return false;
+    const int r = d->shuffle_r > 1 ? d->shuffle_r : 1;
+    if (!dgrad && r > 1 && (Cd % (r * r) != 0 || (Cd / (r * r)) % 32 != 0)) return false;
+    if ((long long)d->N * d->H * d->W >= (1ll << 31)) return false;
+    return true;
+}
+
+int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* w, const float* bias,
+                  const void* residual, void* dst, cudaStream_t st) {
+    int rc = load_driver_fns();
+    if (rc != SR_OK) return rc;
+    if (!g_hl_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_hl_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int Cs = dgrad ? d->Cout : d->Cin, Cd = dgrad ? d->Cin : d->Cout;
+    HaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = Cd;
+    // tile = TR rows x TW columns of one image with TR * (TW + 2) <= 129 MMA rows; column strips of <= 62 pixels keep
+    // the halo tile (and its shared-memory stage) small for every map width
+    p.tiles_x = (int)cdiv(d->W, 62);
+    p.TW = (int)cdiv(d->W, p.tiles_x); p.TWp = p.TW + 2; p.TR = 129 / p.TWp;
+    if (p.TR > d->H) p.TR = d->H;
+    p.tiles_y = (int)cdiv(d->H, p.TR);
+    p.p_tiles = d->N * p.tiles_y * p.tiles_x;
+    p.c_blocks = Cs / 64;
+    p.flip = dgrad ? 1 : 0;
+    p.act = dgrad ? SR_ACT_NONE : d->act; p.slope = d->slope;
+    p.shuffle_r = dgrad ? 0 : d->shuffle_r;
+    p.bias = bias; p.residual = residual; p.out = dst;
+    p.a_box_bytes = (p.TR + 2) * p.TWp * 128;
+    // the tap views of junk rows reach up to pixel row 129 + 2*TWp of the stage: keep that inside the stage
+    const int rows_needed = 130 + 2 * p.TWp, rows_loaded = (p.TR + 2) * p.TWp;
+    p.a_stage_bytes = (int)cdiv((rows_needed > rows_loaded ? rows_needed : rows_loaded) * 128, 1024) * 1024;
+    const int k_blocks = 9 * p.c_blocks;
+
+    // Column-block width and issue mode (profiles/r01_umma_issue_rate.txt):
+    //   resident + dual : the [9*Cin] x 128 weight slab stays in smem (Cin = 64), two issuer warps on two pixel tiles
+    //   N = 256 single  : one issuer already sustains the 128 clk floor of an N=256 instruction (weights streamed)
+    //   dual streamed   : Cout = 64 / 128 (one column block): two pixel tiles share every streamed weight stage
+    //   single streamed : everything else (Cout = 192 * k, 128 * odd)
+    int bn;
+    if (Cd % 128 == 0) bn = 128; else if (Cd % 192 == 0) bn = 192; else bn = 64;
+    long long res_bytes = (long long)k_blocks * bn * 128;
+    bool resident = k_blocks <= HL_MAX_RES && bn <= 128 && res_bytes + 2 * p.a_stage_bytes <= HL_TILE_BUDGET;
+    if (!resident && Cd % 256 == 0) bn = 256;
+    p.block_n = bn;
+    p.n_blocks = Cd / bn;
+    const int b_bytes = bn * 128;
+    res_bytes = (long long)k_blocks * b_bytes;
+    int grid = g_hl_sms;
+    if (resident) {
+        grid -= grid % p.n_blocks;
+        if (p.p_tiles * p.n_blocks <= grid) resident = false;       // every CTA would run a single tile: nothing to keep
+    }
+    p.resident = resident ? 1 : 0;
+    p.dual = (bn <= 128 && (resident || p.n_blocks == 1)) ? 1 : 0;
+    const int lane_ctas = resident ? grid / p.n_blocks : grid;
+    if (p.dual) {
+        const int pairs_total = p.p_tiles / 2;
+        const int full = (pairs_total / lane_ctas) * lane_ctas;      // pair items of the complete rounds
+        const int rem_tiles = p.p_tiles - 2 * full;
+        if (rem_tiles <= lane_ctas) { p.n_pair_items = full; p.n_items = full + rem_tiles; }
+        else { p.n_pair_items = (int)cdiv(p.p_tiles, 2); p.n_items = p.n_pair_items; }
+    } else {
+        p.n_pair_items = 0;
+        p.n_items = resident ? p.p_tiles : p.p_tiles * p.n_blocks;
+    }
+    const int total_items = resident ? p.n_items * p.n_blocks : p.n_items;
+    if (total_items < grid) { grid = total_items; if (resident) grid -= grid % p.n_blocks; }
+    if (grid < 1) grid = p.n_blocks;
+
+    size_t tile_bytes;
+    if (resident) {
+        int na = (int)((HL_TILE_BUDGET - res_bytes) / p.a_stage_bytes);
+        if (na > HL_MAX_A) na = HL_MAX_A;
+        if (p.dual) na -= na % 2;
+        p.num_a_stages = na; p.num_b_stages = 0;
+        tile_bytes = (size_t)res_bytes + (size_t)na * p.a_stage_bytes;
+    } else {
+        int na = p.dual ? 4 : 3;
+        while (na > 2 && (HL_TILE_BUDGET - na * p.a_stage_bytes) / b_bytes < 4) na -= p.dual ? 2 : 1;
+        int nbs = (HL_TILE_BUDGET - na * p.a_stage_bytes) / b_bytes;
+        if (nbs > HL_MAX_B) nbs = HL_MAX_B;
+        if (nbs < 2) { set_error("conv_halo: tile does not fit shared memory (TWp=%d TR=%d block_n=%d)", p.TWp, p.TR, bn); return SR_ERR_UNSUPPORTED; }
+        p.num_a_stages = na; p.num_b_stages = nbs;
+        tile_bytes = (size_t)na * p.a_stage_bytes + (size_t)nbs * b_bytes;
+    }
+    alignas(64) CUtensorMap map_a, map_b;
+    rc = make_tiled4d_map(&map_a, src, d->N, d->H, d->W, Cs, p.TWp, p.TR + 2);
+    if (rc != SR_OK) return rc;
+    rc = make_tiled2d_map(&map_b, w, (uint64_t)9 * Cd, (uint64_t)Cs, (uint32_t)bn);
+    if (rc != SR_OK) return rc;
+    const size_t smem = 1024 + tile_bytes + 1024 + HL_BIAS_MAX * 4;
+    const bool out_bf16 = d->out_dtype == SR_BF16;
+    static bool attr_set[2] = {false, false};
+    if (out_bf16) {
+        if (!attr_set[0]) { cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[0] = true; }
+        conv_halo_kernel<__nv_bfloat16><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
+    } else {
+        if (!attr_set[1]) { cudaFuncSetAttribute(conv_halo_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[1] = true; }
+        conv_halo_kernel<float><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
+    }
+    count_launch();
+    return check_launch("conv_halo_kernel");
+}
+
+}  // namespace sr

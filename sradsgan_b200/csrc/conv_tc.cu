@@ -66,90 +66,6 @@ __device__ __forceinline__ bool tc_tile_at(const TcParams& p, int it, int& m_til
     return true;
 }
 
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-// waits for every outstanding tcgen05.ld of this thread; the registers are passed through so that the
-// compiler cannot move their first use above the wait
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
-                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
-                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-                 :
-                 : "memory");
-}
-
-template <int ACT> __device__ __forceinline__ float tc_act(float x, float slope) {
-    if (ACT == SR_ACT_LRELU) return fmaxf(x, x * slope);          // slope in [0, 1]
-    if (ACT == SR_ACT_RELU) return fmaxf(x, 0.f);
-    if (ACT == SR_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
-    return x;
-}
-
-// bias (shared memory, already in packed-column order) -> activation -> (+ residual) -> 16-byte stores of one
-// 32-column accumulator chunk of one output row
-template <typename OutT, int ACT>
-__device__ __forceinline__ void tc_store_chunk(const uint32_t (&v)[32], const float* bias_s, float slope, const OutT* res, OutT* o) {
-    float f[32];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const float4 b = *reinterpret_cast<const float4*>(bias_s + g * 4);
-        f[g * 4 + 0] = tc_act<ACT>(__uint_as_float(v[g * 4 + 0]) + b.x, slope);
-        f[g * 4 + 1] = tc_act<ACT>(__uint_as_float(v[g * 4 + 1]) + b.y, slope);
-        f[g * 4 + 2] = tc_act<ACT>(__uint_as_float(v[g * 4 + 2]) + b.z, slope);
-        f[g * 4 + 3] = tc_act<ACT>(__uint_as_float(v[g * 4 + 3]) + b.w, slope);
-    }
-    if (sizeof(OutT) == 2) {
-        if (res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint4 rv = rp[g];
-                const __nv_bfloat162* r2p = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    f[g * 8 + h * 2] += __low2float(r2p[h]);
-                    f[g * 8 + h * 2 + 1] += __high2float(r2p[h]);
-                }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            uint4 w;
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
-            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
-            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-            w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
-            w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
-            reinterpret_cast<uint4*>(o)[g] = w;
-        }
-    } else {
-        if (res) {
-            const float4* rp = reinterpret_cast<const float4*>(res);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const float4 rv = rp[g];
-                f[g * 4] += rv.x; f[g * 4 + 1] += rv.y; f[g * 4 + 2] += rv.z; f[g * 4 + 3] += rv.w;
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-            reinterpret_cast<float4*>(o)[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-    }
-}
-
 // Epilogue warp: TMEM lane quarter `quarter`, every second 32-column chunk starting at `half`; the tcgen05.ld of
 // the next chunk is in flight while the current one is converted and stored.
 template <typename OutT, int ACT>
@@ -282,34 +198,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            int m_tile, nb;
-            for (int it = 0; tc_tile_at(p, it, m_tile, nb); ++it) {
-                mbar_wait(acc_empty + acc, acc_phase ^ 1);
+        // ===== MMA issuer: the whole warp walks the schedule converged, lane 0 issues =====
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        int m_tile, nb;
+        for (int it = 0; tc_tile_at(p, it, m_tile, nb); ++it) {
+            mbar_wait(acc_empty + acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_STRIDE);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                if (p.resident && it == 0) mbar_wait(b_full + kb, 0);
+                mbar_wait(full + stage, phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_ACC_STRIDE);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    if (p.resident && it == 0) mbar_wait(b_full + kb, 0);
-                    mbar_wait(full + stage, phase);
-                    tc_fence_after();
+                if (lane == 0) {
                     const uint32_t a_addr = smem_u32(stage_base + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = p.resident ? smem_u32(smem + (size_t)kb * b_bytes) : a_addr + TC_A_BYTES;
-                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(b_addr);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)   // 4 x K=16 per 64-channel block: +32 B per step
-                        umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_f16_x4(d_tmem, make_kmajor_sw128_desc(a_addr), make_kmajor_sw128_desc(b_addr), idesc, kb ? 1u : 0u);
                     umma_commit(empty + stage);
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(acc_full + acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
             }
+            if (lane == 0) umma_commit(acc_full + acc);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column-chunk parity = (warp - 2) / 4 =====

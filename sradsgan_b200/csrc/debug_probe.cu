@@ -76,4 +76,66 @@ int debug_umma_shift(const void* a, int rows_a, const void* b, int shift, int sb
     return check_launch("umma_shift_probe_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Issue-rate probe: one thread per CTA issues `iters` rounds of tcgen05.mma (M=128, N=n, K=16, bf16, both operands in
+// shared memory, garbage data) round-robin over `num_acc` independent TMEM accumulators, then commits and waits.
+// cycles[blockIdx.x] = clock64 ticks from the first issue to the completion of the last MMA.
+// Answers: what is the cost of back-to-back MMAs that accumulate into the SAME accumulator vs different ones?
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_rate_probe_kernel(int n, int num_acc, int iters, int k_steps, long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sa = smem;                      // 128 x 128 B
+    uint8_t* sb = smem + 16384;              // 256 x 128 B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 4);
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(bar + i, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // `issuers` = num_acc >> 8 (0 -> 1): that many warps issue concurrently (lane 0 of each), every issuer round-robins
+    // over its own (num_acc & 0xff) accumulators; mode bit 16: four K-steps per asm statement
+    const int issuers = ((num_acc >> 8) & 0xff) ? ((num_acc >> 8) & 0xff) : 1;
+    const int x4 = (num_acc >> 16) & 1;
+    const int nacc = num_acc & 0xff;
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && warp < issuers) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sa));
+        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sb));
+        const int cols = 512 / (issuers * nacc);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            for (int a = 0; a < nacc; ++a) {
+                const uint32_t d = tmem_base + (uint32_t)((warp * nacc + a) * cols);
+                if (x4) { for (int k = 0; k < k_steps; k += 4) umma_f16_x4(d, adesc, bdesc, idesc, 1u); }
+                else { for (int k = 0; k < k_steps; ++k) umma_f16(d, adesc + (uint64_t)((k & 3) * 2), bdesc + (uint64_t)((k & 3) * 2), idesc, 1u); }
+            }
+        }
+        umma_commit(bar + warp);
+        mbar_wait(bar + warp, 0);
+        cycles[blockIdx.x * issuers + warp] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+}
+
+int debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, long long* cycles, cudaStream_t st) {
+    const int issuers = ((num_acc >> 8) & 0xff) ? ((num_acc >> 8) & 0xff) : 1, nacc = num_acc & 0xff;
+    SR_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && issuers <= 4 && n * nacc * issuers <= 512 && iters > 0 && k_steps > 0 && grid > 0,
+               "umma_rate probe: bad arguments");
+    const size_t smem = 1024 + 16384 + 32768 + 64;
+    cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    umma_rate_probe_kernel<<<grid, 128, smem, st>>>(n, num_acc, iters, k_steps, cycles);
+    count_launch();
+    return check_launch("umma_rate_probe_kernel");
+}
+
 }  // namespace sr

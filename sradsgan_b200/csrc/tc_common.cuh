@@ -168,6 +168,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the four K=16 steps of one 64-deep K-major SW128 k-block (descriptor start address +32 B per step) in ONE asm
+// statement: a single operand hand-off to the uniform datapath instead of four
+__device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+        "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+        "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -206,39 +224,96 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-// Epilogue of one 32-column accumulator chunk of one output pixel: bias -> activation -> store (16-byte
-// vectors).  `col` is the packed GEMM column of v[0]; with shuffle_r > 1 the weights were packed
-// subpixel-major, so a chunk is 32 consecutive channels of ONE sub-pixel (PixelShuffle = contiguous store).
-struct TcEpilogue {
-    int Cout, Ho, Wo;          // conv output grid (before the shuffle) and channel count
-    int act; float slope; int shuffle_r;
-    const float* bias; void* out;
-};
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// waits for every outstanding tcgen05.ld of this thread; the registers are passed through so that the
+// compiler cannot move their first use above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
 
-template <typename OutT>
-__device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& e, const uint32_t (&v)[32], int col, int n, int oy, int ox) {
-    const int r = e.shuffle_r > 1 ? e.shuffle_r : 1;
-    long long idx;
-    int sub = 0, ch0 = col, r2 = 1;
-    if (r > 1) {
-        r2 = r * r;
-        const int cq = e.Cout / r2;
-        sub = col / cq; ch0 = col - sub * cq;
-        const int si = sub / r, sj = sub - si * r;
-        idx = ((((long long)n * e.Ho * r + (oy * r + si)) * ((long long)e.Wo * r)) + (ox * r + sj)) * cq + ch0;
-    } else {
-        idx = (((long long)n * e.Ho + oy) * e.Wo + ox) * e.Cout + col;
-    }
+template <int ACT> __device__ __forceinline__ float tc_act(float x, float slope) {
+    if (ACT == SR_ACT_LRELU) return fmaxf(x, x * slope);          // slope in [0, 1]
+    if (ACT == SR_ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == SR_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+    return x;
+}
+
+// bias (shared memory, already in packed-column order) -> activation -> (+ residual) -> 16-byte stores of one
+// 32-column accumulator chunk of one output row
+// 16-byte load from SHARED memory through an explicit shared-space instruction (a generic pointer would compile to
+// a generic LD with global-memory-like scoreboard latency in the epilogue's critical path)
+__device__ __forceinline__ float4 lds128(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
+template <typename OutT, int ACT>
+__device__ __forceinline__ void tc_store_chunk(const uint32_t (&v)[32], const float* bias_s, float slope, const OutT* res, OutT* o) {
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (e.bias) x += e.bias[r > 1 ? (ch0 + j) * r2 + sub : col + j];
-        f[j] = apply_act(x, e.act, e.slope);
+    for (int g = 0; g < 8; ++g) {
+        const float4 b = lds128(bias_s + g * 4);
+        f[g * 4 + 0] = tc_act<ACT>(__uint_as_float(v[g * 4 + 0]) + b.x, slope);
+        f[g * 4 + 1] = tc_act<ACT>(__uint_as_float(v[g * 4 + 1]) + b.y, slope);
+        f[g * 4 + 2] = tc_act<ACT>(__uint_as_float(v[g * 4 + 2]) + b.z, slope);
+        f[g * 4 + 3] = tc_act<ACT>(__uint_as_float(v[g * 4 + 3]) + b.w, slope);
     }
-    OutT* o = reinterpret_cast<OutT*>(e.out) + idx;
+    if (sizeof(OutT) == 2) {
+        if (res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) store4<OutT>(o + g * 4, f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+            for (int g = 0; g < 4; ++g) {
+                const uint4 rv = rp[g];
+                const __nv_bfloat162* r2p = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    f[g * 8 + h * 2] += __low2float(r2p[h]);
+                    f[g * 8 + h * 2 + 1] += __high2float(r2p[h]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+            w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
+            w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
+            reinterpret_cast<uint4*>(o)[g] = w;
+        }
+    } else {
+        if (res) {
+            const float4* rp = reinterpret_cast<const float4*>(res);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 rv = rp[g];
+                f[g * 4] += rv.x; f[g * 4 + 1] += rv.y; f[g * 4 + 2] += rv.z; f[g * 4 + 3] += rv.w;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(o)[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+    }
 }
 
 // MN-major, 128B-swizzled operand tile ([k rows][64 bf16 of M/N], 8-row groups 1024 B apart, further

@@ -35,7 +35,7 @@ def _ref_w(wt, dtype):
     return wt.to(dtype).float()
 
 
-from sradsgan_b200._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, conv_geom)
+from sradsgan_b200._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, IMPL_AUTO, IMPL_HALO, IMPL_SIMT, IMPL_TCGEN05, conv_geom)
 
 SIMT_CASES = [
     # n, cin, h, w, cout, k, stride, pad
@@ -230,3 +230,55 @@ def test_full_size_linearity_and_impl_agreement(be):
         assert rel(ys, ya + yb) < 1e-5
     y_simt = be.conv_fwd(a, wp, None, None, g, out_dtype=torch.float32, impl=IMPL_SIMT)
     assert rel(ya, y_simt) < 1e-5
+
+
+HALO_CASES = [
+    # n, cin, h, w, cout  (3x3, stride 1, pad 1)
+    (2, 64, 54, 54, 256),      # RAB.conv1 (K1): resident weights, 2 rows per tile
+    (2, 256, 54, 54, 64),      # RAB.conv2 (K2): streamed weights, 4 channel blocks
+    (1, 64, 216, 216, 64),     # 216^2 layers: column strips (2 x 108) with real neighbours in the halo
+    (1, 128, 108, 108, 128),   # one padded row per tile
+    (3, 256, 27, 27, 512),     # 4 rows per tile, 4 column blocks
+    (2, 512, 14, 14, 512),     # 8 rows per tile, last tile ragged
+    (1, 64, 5, 7, 64),         # fewer rows than TR
+    (2, 64, 130, 33, 128),     # W + 2 <= 129 with 3 rows per tile, ragged height
+    (1, 64, 40, 300, 64),      # three column strips
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_halo_fwd_dgrad_match_cpu_and_im2col_kernel(be, case):
+    """Halo-tile tcgen05 kernel (one TMA box per channel block, nine shifted UMMA views) == torch CPU == the
+    im2col-TMA tcgen05 kernel, forward (bias + LeakyReLU, bf16 out; fp32 out + residual) and input gradient."""
+    n, cin, h, w, cout = case
+    x, wt, b = _mk(n, cin, h, w, cout, 3, torch.bfloat16, seed=cin * 3 + cout + h)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    wp = be.pack_weights(wt.cuda(), 0, torch.bfloat16)
+    y = be.conv_fwd(xc, wp, b.cuda(), None, g, ACT_LRELU, 0.2, impl=IMPL_HALO)
+    torch.cuda.synchronize()
+    y_ref = F.leaky_relu(F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1), 0.2)
+    assert y.shape == y_ref.shape
+    assert rel(y, y_ref) < 4e-3
+    y_tc = be.conv_fwd(xc, wp, b.cuda(), None, g, ACT_LRELU, 0.2, impl=IMPL_TCGEN05)
+    assert rel(y, y_tc) < 1e-3          # same bf16 products; fp32 accumulation order differs (channel-block major vs tap major)
+    res = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(2))
+    y2 = be.conv_fwd(xc, wp, b.cuda(), res.cuda().contiguous(memory_format=torch.channels_last), g, out_dtype=torch.float32,
+                     impl=IMPL_HALO)
+    assert rel(y2, F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1) + res) < 2e-5
+    gy = torch.randn(n, cout, h, w, generator=torch.Generator().manual_seed(4)).bfloat16()
+    gyc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, torch.bfloat16), g, impl=IMPL_HALO)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, wt.bfloat16().float(), gy.float(), stride=1, padding=1)
+    assert rel(dx, dx_ref) < 4e-3
+
+
+@pytest.mark.parametrize("r,cout", [(2, 256), (3, 576)])
+def test_halo_pixel_shuffle_epilogue(be, r, cout):
+    x, wt, b = _mk(2, 64, 24, 24, cout, 3, torch.bfloat16, seed=r)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = be.conv_fwd(xc, be.pack_weights(wt.cuda(), 0, torch.bfloat16, r), b.cuda(), None, g, ACT_LRELU, 0.01, shuffle_r=r,
+                    impl=IMPL_HALO)
+    y_ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1), r), 0.01)
+    assert y.shape == y_ref.shape and rel(y, y_ref) < 4e-3
