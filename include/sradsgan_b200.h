@@ -81,6 +81,12 @@ int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* w_packed_
 int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float* dw_oihw, float* dbias,
                     int accumulate, void* stream);
 
+/* Registers a caller-owned DEVICE scratch buffer that stays valid until replaced (NULL, 0 removes it).  With it,
+ * sr_conv2d_wgrad combines its split-K partial tiles through plain stores + one reduce kernel instead of fp32
+ * atomics (3x faster, and deterministic); without it (or when it is too small) the atomic path is used.
+ * The library still never allocates.  64 MiB covers every layer of the x4 B=16 training step. */
+int sr_set_workspace(void* ptr, uint64_t bytes);
+
 /* Fused local-attention tail of RAB / ResGroup (C = 64): z = Conv1x1(SLAM(CLAM(x))) + t, i.e.
  * nn modules CLAM (model/sradsgan.py:101-127), SLAM (:129-151), the 1x1 `conv` (:233/:297) and the
  * in-place residual `out += x` (:274/:323) in five kernels.  x: NHWC (x_dtype), t/z32: NHWC fp32,

@@ -19,7 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_HALO = 0, 1, 2, 3
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
-    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate",
+    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate", "sr_set_workspace",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
     lib.sr_bn_act_bwd_bwd.restype = i32
     lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
     lib.sr_debug_umma_shift.restype = i32
+    lib.sr_set_workspace.argtypes = [vp, ctypes.c_uint64]
+    lib.sr_set_workspace.restype = i32
     lib.sr_debug_umma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
     lib.sr_debug_umma_rate.restype = i32
     for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
@@ -137,6 +139,13 @@ class CudaBackend:
     def __init__(self):
         self.lib = load()
         self.prof = None      # bench.py: list of (kernel class, flops, bytes, start event, end event)
+        self._workspace = None
+
+    def ensure_workspace(self, device, nbytes=64 << 20):
+        """persistent scratch for the split-K weight-gradient reduction (owned here, registered with the library)"""
+        if self._workspace is None or self._workspace.device != device:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _check(self.lib.sr_set_workspace(ctypes.c_void_p(self._workspace.data_ptr()), nbytes), "set_workspace")
 
     def _timed(self, kind, d, dgrad, call):
         """optional per-launch CUDA-event timing on the launching stream (bench.py roofline attribution)"""
@@ -217,6 +226,7 @@ class CudaBackend:
         dw = torch.empty((g.Cout, g.Cin, g.kh, g.kw), dtype=torch.float32, device=x.device)
         db = torch.empty((g.Cout,), dtype=torch.float32, device=x.device) if want_bias else None
         d = self._desc(g, _dt(x), SR_F32, impl=impl)
+        self.ensure_workspace(x.device)
         self._timed("wgrad", d, False, lambda: _check(
             self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 0, _stream()), "conv2d_wgrad"))
         return dw, db
@@ -231,6 +241,7 @@ class CudaBackend:
         if dw.dtype != torch.float32 or not dw.is_contiguous() or (db is not None and (db.dtype != torch.float32 or not db.is_contiguous())):
             raise ValueError("conv_wgrad_into: contiguous fp32 gradient buffers required")
         d = self._desc(g, _dt(x), SR_F32, impl=impl)
+        self.ensure_workspace(x.device)
         self._timed("wgrad", d, False, lambda: _check(
             self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 1, _stream()), "conv2d_wgrad"))
 

@@ -40,6 +40,7 @@ int conv_halo_run(const sr_conv_desc*, bool dgrad, const void*, const void*, con
 // conv_tc_wgrad.cu
 bool conv_tc_wgrad_supported(const sr_conv_desc*);
 int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
+void conv_tc_wgrad_set_workspace(void*, size_t);
 // conv_thin.cu
 bool thin_fwd_supported(const sr_conv_desc*, bool dgrad);
 bool thin_wgrad_supported(const sr_conv_desc*);
@@ -188,6 +189,13 @@ int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float*
     if (rc) return rc;
     if (dbias) rc = colsum(dy, d->in_dtype, (long long)d->N * d->Ho * d->Wo, d->Cout, dbias, nullptr, accumulate, st);
     return rc;
+}
+
+int sr_set_workspace(void* ptr, uint64_t bytes) {
+    SR_REQUIRE((ptr == nullptr) == (bytes == 0), "set_workspace: pointer and size must both be given or both be zero");
+    SR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "set_workspace: pointer must be 16-byte aligned");
+    conv_tc_wgrad_set_workspace(ptr, (size_t)bytes);
+    return SR_OK;
 }
 
 size_t sr_la_chain_workspace_bytes(int N, int H, int W) { return la_workspace_bytes(N, H, W); }

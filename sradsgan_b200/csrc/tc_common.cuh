@@ -186,6 +186,23 @@ __device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint64_t adesc, uin
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// four consecutive K=16 steps of MN-major SW128 operands (16 pixel rows = 2048 B = 128 descriptor units per step)
+__device__ __forceinline__ void umma_f16_x4_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "add.s64 a1, %1, 128;\n\tadd.s64 b1, %2, 128;\n\t"
+        "add.s64 a2, %1, 256;\n\tadd.s64 b2, %2, 256;\n\t"
+        "add.s64 a3, %1, 384;\n\tadd.s64 b3, %2, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -107,8 +107,9 @@ def test_bn_leaky_relu_forward_backward(be, shape, dtype):
     u = torch.randn(shape, generator=g).to(dtype)
     r_gy, r_x, r_gamma = emu.bn_act_bwd_bwd(u, gy, x, save_ref, dg_ref, db_ref, 0.2)
     d_gy, d_x, d_gamma = be.bn_act_bwd_bwd(u.cuda(), gy.cuda(), xc, save, dg, db, 0.2)
-    lim = 2e-4 if dtype == torch.float32 else 8e-3
-    assert rel(d_gy, r_gy) < lim and rel(d_x, r_x) < lim, (rel(d_gy, r_gy), rel(d_x, r_x))
+    lim = 3e-4 if dtype == torch.float32 else 8e-3
+    e_gy, e_x = rel(d_gy.cpu().float() * keep, r_gy.float() * keep), rel(d_x.cpu().float() * keep, r_x.float() * keep)
+    assert e_gy < lim and e_x < lim, (e_gy, e_x)
     assert rel(d_gamma, r_gamma) < 1e-3, rel(d_gamma, r_gamma)
 
 
