@@ -75,6 +75,12 @@ int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w_packed, co
  * w_packed from sr_pack_weights(mode 1).  dy has dtype d->in_dtype, dx has d->out_dtype.
  * (autograd of every nn.Conv2d above; reference: torch.autograd, model/sradsgan.py:857,886,621) */
 int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
+/* dx = conv_transpose(dy, w) * act'(y_prev): the input gradient of the conv described by d, multiplied by the
+ * derivative of the LeakyReLU / ReLU that PRODUCED this conv's input (y_prev = that activation's output, shaped like dx,
+ * dtype d->out_dtype) — the mask is applied in the epilogue of the tensor-core kernel.  RAB backward: conv2.dgrad followed
+ * by LeakyReLU(0.2).backward (model/sradsgan.py:251-253) in one kernel. */
+int sr_conv2d_dgrad_act(const sr_conv_desc* d, const void* dy, const void* w_packed_t, const void* y_prev, int act, float slope,
+                        void* dx, void* stream);
 /* dw (OIHW fp32) (+)= sum_pixels dy (x) x ; dbias (fp32, may be NULL) (+)= sum_pixels dy.
  * accumulate=0 overwrites (the library zero-fills first), 1 adds (tied upsampler weights, GP double
  * backward).  x and dy have dtype d->in_dtype. */

@@ -83,6 +83,12 @@ class EmuBackend:
         dx = torch.nn.grad.conv2d_input((g.N, g.Cin, g.H, g.W), w, dy.float(), stride=g.stride, padding=g.pad)
         return dx.to(out_dtype).contiguous(memory_format=torch.channels_last)
 
+    def conv_dgrad_act(self, dy, w_packed_t, g, y_prev, act, slope, impl=0):
+        dx = self.conv_dgrad(dy, w_packed_t, g).float()
+        yp = y_prev.float()
+        dx = torch.where(yp > 0, dx, dx * (slope if act == ACT_LRELU else 0.0))
+        return dx.to(dy.dtype).contiguous(memory_format=torch.channels_last)
+
     def conv_wgrad(self, x, dy, g, want_bias=True, impl=0):
         self.launches += 1
         dw = torch.nn.grad.conv2d_weight(x.float(), (g.Cout, g.Cin, g.kh, g.kw), dy.float(), stride=g.stride, padding=g.pad)

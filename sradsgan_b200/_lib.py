@@ -18,7 +18,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_HALO = 0, 1, 2, 3
 
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
-    "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
+    "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
     "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate", "sr_set_workspace",
 ]
 
@@ -67,6 +67,8 @@ def load():
     lib.sr_pack_weights.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.sr_conv2d_fwd.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]
     lib.sr_conv2d_dgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp]
+    lib.sr_conv2d_dgrad_act.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, i32, f32, vp, vp]
+    lib.sr_conv2d_dgrad_act.restype = i32
     lib.sr_conv2d_wgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, i32, vp]
     lib.sr_colsum.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp]
     lib.sr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, f32, f32, vp]
@@ -87,7 +89,7 @@ def load():
     lib.sr_debug_umma_rate.restype = i32
     for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
         getattr(lib, name).restype = i32
-    for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
+    for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -215,6 +217,20 @@ class CudaBackend:
         d = self._desc(g, _dt(dy), _dt(dx), impl=impl)
         self._timed("dgrad", d, True, lambda: _check(
             self.lib.sr_conv2d_dgrad(ctypes.byref(d), _ptr(dy), _ptr(w_packed_t), _ptr(dx), _stream()), "conv2d_dgrad"))
+        return dx
+
+    def conv_dgrad_act(self, dy, w_packed_t, g, y_prev, act, slope, impl=IMPL_AUTO):
+        """dx = conv_dgrad(dy) * act'(y_prev) (y_prev: the activated tensor that was this conv's input)"""
+        _require_cuda(dy, w_packed_t, y_prev)
+        dy = _nhwc(dy)
+        y_prev = _nhwc(y_prev)
+        if y_prev.dtype != dy.dtype or tuple(y_prev.shape) != (g.N, g.Cin, g.H, g.W):
+            raise ValueError("conv_dgrad_act: y_prev must have the input's shape and the gradient's dtype")
+        dx = torch.empty((g.N, g.Cin, g.H, g.W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        d = self._desc(g, _dt(dy), _dt(dx), impl=impl)
+        self._timed("dgrad", d, True, lambda: _check(
+            self.lib.sr_conv2d_dgrad_act(ctypes.byref(d), _ptr(dy), _ptr(w_packed_t), _ptr(y_prev), int(act), float(slope), _ptr(dx),
+                                         _stream()), "conv2d_dgrad_act"))
         return dx
 
     def conv_wgrad(self, x, dy, g, want_bias=True, impl=IMPL_AUTO):

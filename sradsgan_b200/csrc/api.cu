@@ -36,7 +36,8 @@ bool conv_tc_supported(const sr_conv_desc*, bool dgrad);
 int conv_tc_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 // conv_halo.cu
 bool conv_halo_supported(const sr_conv_desc*, bool dgrad);
-int conv_halo_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+int conv_halo_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t,
+                  const void* mask = nullptr, float mask_slope = 0.f);
 // conv_tc_wgrad.cu
 bool conv_tc_wgrad_supported(const sr_conv_desc*);
 int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
@@ -167,6 +168,23 @@ int sr_conv2d_dgrad(const sr_conv_desc* d, const void* dy, const void* wt, void*
     if (tc_ok && d->impl != SR_IMPL_SIMT) return conv_tc_run(d, true, dy, wt, nullptr, nullptr, dx, (cudaStream_t)stream);
     if (d->impl == SR_IMPL_AUTO && thin_fwd_supported(d, true)) return thin_fwd_run(d, true, dy, wt, nullptr, dx, (cudaStream_t)stream);
     return conv_dgrad_simt(d, dy, wt, dx, (cudaStream_t)stream);
+}
+
+int sr_conv2d_dgrad_act(const sr_conv_desc* d, const void* dy, const void* wt, const void* y_prev, int act, float slope, void* dx,
+                        void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    rc = check_desc(d);
+    if (rc) return rc;
+    SR_REQUIRE(dy && wt && dx && y_prev, "conv2d_dgrad_act: NULL pointer");
+    SR_REQUIRE(act == SR_ACT_LRELU || act == SR_ACT_RELU, "conv2d_dgrad_act: LeakyReLU / ReLU only");
+    const float ms = act == SR_ACT_RELU ? 0.f : slope;
+    if (d->in_dtype == SR_BF16 && d->out_dtype == SR_BF16 && (d->impl == SR_IMPL_AUTO || d->impl == SR_IMPL_HALO) && conv_halo_supported(d, true))
+        return conv_halo_run(d, true, dy, wt, nullptr, nullptr, dx, (cudaStream_t)stream, y_prev, ms);
+    // unfused: input gradient, then the activation mask in place
+    rc = sr_conv2d_dgrad(d, dy, wt, dx, stream);
+    if (rc) return rc;
+    return act_bwd(dx, d->out_dtype, y_prev, d->out_dtype, act, slope, 0, d->N, d->H, d->W, d->Cin, dx, d->out_dtype, (cudaStream_t)stream);
 }
 
 int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, int accumulate,

@@ -34,6 +34,8 @@ struct HaloParams {
     int n_pair_items, n_items;       // per CTA lane: items [0, n_pair_items) are tile pairs, the rest single tiles
     const float* bias;
     const void* residual;
+    const void* mask;                // nullable bf16 tensor shaped like the output: out *= act'(mask)
+    float mask_slope;
     void* out;
 };
 
@@ -85,6 +87,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
     const int bar0 = p.dual ? grp * 2 : 0;       // this warp's pair of accumulator barriers / TMEM buffers
     OutT* out = reinterpret_cast<OutT*>(p.out);
     const OutT* res = reinterpret_cast<const OutT*>(p.residual);
+    const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(p.mask);
     int acc = 0; uint32_t acc_phase = 0;
     int t0, t1, nb;
     for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
@@ -109,7 +112,8 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
             } else {
                 idx = row_idx + col;
             }
-            tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx);
+            tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx,
+                                      mask ? mask + idx : nullptr, p.mask_slope);
         };
         uint32_t va[32], vb[32];
         int c = c_first;
@@ -339,7 +343,7 @@ bool conv_halo_supported(const sr_conv_desc* d, bool dgrad) {
 }
 
 int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* w, const float* bias,
-                  const void* residual, void* dst, cudaStream_t st) {
+                  const void* residual, void* dst, cudaStream_t st, const void* mask, float mask_slope) {
     int rc = load_driver_fns();
     if (rc != SR_OK) return rc;
     if (!g_hl_sms) {
@@ -363,6 +367,7 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.act = dgrad ? SR_ACT_NONE : d->act; p.slope = d->slope;
     p.shuffle_r = dgrad ? 0 : d->shuffle_r;
     p.bias = bias; p.residual = residual; p.out = dst;
+    p.mask = mask; p.mask_slope = mask_slope;
     p.a_box_bytes = (p.TR + 2) * p.TWp * 128;
     // the tap views of junk rows reach up to pixel row 129 + 2*TWp of the stage: keep that inside the stage
     const int rows_needed = 130 + 2 * p.TWp, rows_loaded = (p.TR + 2) * p.TWp;

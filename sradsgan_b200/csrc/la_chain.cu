@@ -352,30 +352,54 @@ la_conv7_dgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m,
     dq[pix * 2] = a; dq[pix * 2 + 1] = b;
 }
 
-// dw7[ch][ky][kx] += sum_p de[p] * q[p + off][ch]   (grid: filter element x pixel slice)
+// dw7[ch][ky][kx] += sum_p de[p] * q[p + off][ch],  de = dm * m * (1 - m).
+// block = one band of LA_WG_ROWS image rows: the band's de values and the q rows it touches (+-3 halo) are staged in
+// shared memory once, thread (f, h) accumulates filter element f over half h of the band, one atomic per element.
+constexpr int LA_WG_ROWS = 8;
+
 __global__ void __launch_bounds__(256)
 la_conv7_wgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m, const float* __restrict__ q, int N, int H, int W,
                       float* __restrict__ dw7) {
-    const int idx = blockIdx.x, ch = idx / 49, ky = (idx % 49) / 7, kx = idx % 7;
-    const long long NP = (long long)N * H * W;
-    float acc = 0.f;
-    for (long long pix = (long long)blockIdx.y * blockDim.x + threadIdx.x; pix < NP; pix += (long long)gridDim.y * blockDim.x) {
-        const int x = (int)(pix % W); const long long r = pix / W;
-        const int y = (int)(r % H); const int n = (int)(r / H);
-        const int yy = y + ky - 3, xx = x + kx - 3;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const float mv = m[pix];
-        acc += dm[pix] * mv * (1.f - mv) * q[(((long long)n * H + yy) * W + xx) * 2 + ch];
+    extern __shared__ __align__(16) float la_wg_smem[];
+    const int Wp = W + 6;
+    float* qs = la_wg_smem;                                  // [(ROWS+6)][Wp][2], zero outside the image
+    float* des = qs + (LA_WG_ROWS + 6) * Wp * 2;             // [ROWS][W]
+    float* red = des + LA_WG_ROWS * W;                       // [2][98]
+    const int bands = (H + LA_WG_ROWS - 1) / LA_WG_ROWS;
+    const int n = blockIdx.x / bands, y0 = (blockIdx.x % bands) * LA_WG_ROWS;
+    const int rows = min(LA_WG_ROWS, H - y0);
+    for (int i = threadIdx.x; i < (LA_WG_ROWS + 6) * Wp; i += 256) {
+        const int r = i / Wp, c = i - r * Wp;
+        const int yy = y0 + r - 3, xx = c - 3;
+        float2 v = make_float2(0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *reinterpret_cast<const float2*>(q + (((long long)n * H + yy) * W + xx) * 2);
+        qs[i * 2] = v.x; qs[i * 2 + 1] = v.y;
     }
-    __shared__ float red[8];
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    for (int i = threadIdx.x; i < LA_WG_ROWS * W; i += 256) {
+        const int r = i / W, c = i - r * W;
+        float v = 0.f;
+        if (r < rows) {
+            const long long pix = ((long long)n * H + y0 + r) * W + c;
+            const float mv = m[pix];
+            v = dm[pix] * mv * (1.f - mv);
+        }
+        des[i] = v;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += red[w];
-        atomicAdd(dw7 + idx, s);
+    const int f = threadIdx.x % 98, h = threadIdx.x / 98;    // threads 196..255 idle in the main loop
+    if (h < 2) {
+        const int ch = f / 49, ky = (f % 49) / 7, kx = f % 7;
+        const int r0 = h * (LA_WG_ROWS / 2), r1 = r0 + LA_WG_ROWS / 2;
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const float* qrow = qs + ((r + ky) * Wp + kx) * 2 + ch;
+            const float* drow = des + r * W;
+            for (int c = 0; c < W; ++c) acc = fmaf(drow[c], qrow[c * 2], acc);
+        }
+        red[h * 98 + f] = acc;
     }
+    __syncthreads();
+    if (threadIdx.x < 98) atomicAdd(dw7 + threadIdx.x, red[threadIdx.x] + red[98 + threadIdx.x]);
 }
 
 // per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x
@@ -508,7 +532,13 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
     if (!attr[ai]) { cudaFuncSetAttribute(la_bwd_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr[ai] = true; }
     la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
     la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
-    la_conv7_wgrad_kernel<<<dim3(98, (unsigned)std::min<long long>(24, cdiv(NP, 1024))), 256, 0, st>>>(dm, m, q, N, H, W, d_w7);
+    {
+        const int bands = (H + LA_WG_ROWS - 1) / LA_WG_ROWS;
+        const size_t wg_smem = sizeof(float) * ((size_t)(LA_WG_ROWS + 6) * (W + 6) * 2 + (size_t)LA_WG_ROWS * W + 2 * 98);
+        static bool wg_attr = false;
+        if (!wg_attr) { cudaFuncSetAttribute(la_conv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); wg_attr = true; }
+        la_conv7_wgrad_kernel<<<N * bands, 256, wg_smem, st>>>(dm, m, q, N, H, W, d_w7);
+    }
     la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds);
     la_gate_bwd_kernel<<<N, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, N, Cr, d_fc1, d_fc2, da, dmx);
     la_fix_kernel<T><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((T*)dx, da, dmx, pstar, P, NP * LA_C);

@@ -282,8 +282,11 @@ __device__ __forceinline__ float4 lds128(const float* p) {
     return v;
 }
 
+// `mask` (nullable, bf16, same indexing as the output): f *= (mask > 0 ? 1 : mask_slope) — the derivative of the
+// LeakyReLU / ReLU that produced `mask`, fused into the epilogue of the input-gradient convolution behind it.
 template <typename OutT, int ACT>
-__device__ __forceinline__ void tc_store_chunk(const uint32_t (&v)[32], const float* bias_s, float slope, const OutT* res, OutT* o) {
+__device__ __forceinline__ void tc_store_chunk(const uint32_t (&v)[32], const float* bias_s, float slope, const OutT* res, OutT* o,
+                                               const __nv_bfloat16* mask = nullptr, float mask_slope = 0.f) {
     float f[32];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -292,6 +295,19 @@ __device__ __forceinline__ void tc_store_chunk(const uint32_t (&v)[32], const fl
         f[g * 4 + 1] = tc_act<ACT>(__uint_as_float(v[g * 4 + 1]) + b.y, slope);
         f[g * 4 + 2] = tc_act<ACT>(__uint_as_float(v[g * 4 + 2]) + b.z, slope);
         f[g * 4 + 3] = tc_act<ACT>(__uint_as_float(v[g * 4 + 3]) + b.w, slope);
+    }
+    if (mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(mask);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 mv = mp[g];
+            const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (!(__low2float(m2[h]) > 0.f)) f[g * 8 + h * 2] *= mask_slope;
+                if (!(__high2float(m2[h]) > 0.f)) f[g * 8 + h * 2 + 1] *= mask_slope;
+            }
+        }
     }
     if (sizeof(OutT) == 2) {
         if (res) {

@@ -236,6 +236,12 @@ class RAB(nn.Module):
 
     def forward(self, x):
         xc = ops.to_compute(x)
+        c1, c2 = self.conv1, self.conv2
+        if (self.act_type in ('lrelu', 'relu') and c1.kernel_size == 3 and c1.stride == 1 and c1.padding == 1 and c1.bias is not None
+                and c2.bias is not None):
+            # the default block: both convolutions in one autograd node (activation derivative fused into conv2's dgrad)
+            out = ops.conv_act_conv(xc, c1, c2, ACT_LRELU if self.act_type == 'lrelu' else ACT_RELU, 0.2)
+            return _la_forward(self, out, x)
         if self.act_type == 'lrelu':
             out = self.conv1.fused(xc, ACT_LRELU, 0.2)
         elif self.act_type == 'relu':

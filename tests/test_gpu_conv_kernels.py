@@ -282,3 +282,25 @@ def test_halo_pixel_shuffle_epilogue(be, r, cout):
                     impl=IMPL_HALO)
     y_ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1), r), 0.01)
     assert y.shape == y_ref.shape and rel(y, y_ref) < 4e-3
+
+
+@pytest.mark.parametrize("case", [(2, 64, 54, 54, 256), (1, 256, 27, 27, 64), (1, 64, 20, 20, 64)])
+@pytest.mark.parametrize("act", [ACT_LRELU, ACT_RELU])
+def test_dgrad_with_fused_activation_derivative(be, case, act):
+    """sr_conv2d_dgrad_act: dx = dgrad(dy) * act'(y_prev) in the halo kernel's epilogue == dgrad followed by the mask."""
+    from oracle import ops_emu
+    n, cin, h, w, cout = case
+    x, wt, _ = _mk(n, cin, h, w, cout, 3, torch.bfloat16, seed=cin + cout)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    gen = torch.Generator().manual_seed(11)
+    gy = torch.randn(n, cout, h, w, generator=gen).bfloat16()
+    y_prev = torch.randn(n, cin, h, w, generator=gen).bfloat16()
+    wt_p = be.pack_weights(wt.cuda(), 1, torch.bfloat16)
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
+    got = be.conv_dgrad_act(cl(gy), wt_p, g, cl(y_prev), act, 0.2)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, wt.bfloat16().float(), gy.float(), stride=1, padding=1)
+    ref = torch.where(y_prev.float() > 0, dx_ref, dx_ref * (0.2 if act == ACT_LRELU else 0.0))
+    assert rel(got, ref) < 4e-3
+    emu = ops_emu.EmuBackend()
+    ref2 = emu.conv_dgrad_act(gy, emu.pack_weights(wt, 1, torch.bfloat16), g, y_prev, act, 0.2)
+    assert rel(got, ref2) < 4e-3
