@@ -11,6 +11,8 @@
 // for the residual trunk and once in the compute dtype for the next 3x3 conv) and 6 backward.
 // All reductions are warp-shuffle / shared-memory based with fp32 accumulation; every kernel is HBM/L2
 // bound.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -492,7 +494,7 @@ static int la_slices(int P) { int s = (P + 255) / 256; return s < 1 ? 1 : (s > 3
 size_t la_workspace_bytes(int N, int H, int W) {
     const int P = H * W, S = la_slices(P);
     // fwd: psum, pmax, pidx ; bwd: g, dm, dq, ds, da, dmx
-    size_t fwd = (size_t)N * S * LA_C * 12;
+    size_t fwd = (size_t)N * (S > 32 ? S : 32) * LA_C * 12 + (size_t)N * 16 + 64;   // + the fused kernel's partials / barrier counters
     size_t bwd = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + ((size_t)N * P + 4) * 8 + (size_t)N * LA_C * 12;
     return (fwd > bwd ? fwd : bwd) + 256;
 }
@@ -546,9 +548,22 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
     return check_launch("la_chain_bwd");
 }
 
+int la_fused_fwd(const void*, int, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
+                 float*, void*, float*, float*, float*, float*, int*, float*, unsigned char*, float*, cudaStream_t);
+
 int la_chain_fwd(const void* x, int dtype, const float* t_res, const float* fc1, const float* fc2, const float* w7, const float* Wm,
                  const float* bias, int N, int H, int W, int Cr, float* z32, void* z16, float* s_out, float* m_out, float* avg_out,
                  float* max_out, int* pstar, float* q, unsigned char* cstar, float* ws, cudaStream_t st) {
+    // Experimental (SR_LA_FUSED=1): one co-resident wave with per-image barriers (la_fused.cu).  Measured 36.9 us vs
+    // 39.1 us for the five kernels at the x4 B=16 shape — the chain is latency-, not bandwidth-bound at 54^2 — so the
+    // default stays the multi-kernel path, which needs no co-residency guarantee.
+    static int fused_on = -1;
+    if (fused_on < 0) { const char* e = getenv("SR_LA_FUSED"); fused_on = (e && atoi(e)) ? 1 : 0; }
+    if (fused_on) {
+        const int r = la_fused_fwd(x, dtype, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q,
+                                   cstar, ws, st);
+        if (r != 0) return r < 0 ? r : SR_OK;
+    }
     if (dtype == SR_F32) return la_fwd_t<float>(x, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q, cstar, ws, st);
     return la_fwd_t<__nv_bfloat16>(x, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q, cstar, ws, st);
 }
