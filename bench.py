@@ -110,6 +110,37 @@ def cpu_reference_step(batch, steps, warmup):
                       "%.2f s/step" % (steps, batch, BATCH, cores, mean)}, mean
 
 
+def inference_bench(size, scale=9, tile=128, overlap=16, tile_batch=8):
+    """Second half of BASELINE.json's metric: x9 generator inference on a synthetic size^2 LR tile (configs[3]) through
+    overlapped tiling (the reference cannot run this: SGAM materialises an (HW)^2 attention).  Input resident on
+    the device; output Mpix/s = (size*scale)^2 / time of one full pass (one warm-up pass over 2 tile batches)."""
+    import torch
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup
+    from sradsgan_b200.model.trainer import tiled_forward
+    from sradsgan_b200.utils import weights_init_normal
+    torch.manual_seed(0)
+    G = GeneratorResNet(ResGroup, n_residual_blocks=12, n_basic_blocks=3, upscale_factor=scale)
+    G.apply(weights_init_normal)
+    G.cuda().eval()
+    lr = torch.rand(1, 3, size, size, device="cuda")
+    tiled_forward(G, lr[:, :, :2 * tile, :4 * tile].contiguous(), scale, tile, overlap, tile_batch)      # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = tiled_forward(G, lr, scale, tile, overlap, tile_batch)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    mpix = (size * scale) ** 2 / 1e6
+    ok = bool(torch.isfinite(out[:, :, ::97, ::89]).all().item())
+    del out
+    torch.cuda.empty_cache()
+    return {"metric": "x%d inference output Mpix/s" % scale, "value": mpix / sec, "unit": "Mpix/s", "seconds": sec,
+            "config": {"workload": "SRADSGAN x%d generator, synthetic %dx%d LR -> %dx%d, overlapped tiles %d^2 (overlap %d LR px, "
+                                   "feathered), %d tiles per forward, bf16" % (scale, size, size, size * scale, size * scale, tile, overlap, tile_batch)},
+            "output_finite": ok}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,6 +165,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (BASELINE config: 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-inference", action="store_true", help="skip the x9 tiled-inference measurement (second half of the metric)")
+    ap.add_argument("--infer-size", type=int, default=2048, help="side of the synthetic LR image of the inference measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -247,6 +280,10 @@ def main():
                 "measured": "CUDA events around each launch of this kernel class on the launching stream, one eagerly launched step",
                 "step_frac_of_tensor_roofline": (FLOP_PER_IMG * B * K / (ms * 1e-3) / 1e12) / peak_tf}
 
+    infer = None
+    if not args.no_inference:
+        infer = inference_bench(args.infer_size)
+
     cb = None
     if not args.no_cpu_baseline:
         cb, _ = cpu_reference_step(batch=2, steps=1, warmup=0)
@@ -263,7 +300,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": imgs / e2e_s, "unit": "HR images/s", "h2d_bytes_per_step": int(lr_host.numel() * 4 + hr_host.numel() * 4),
                     "d2h_bytes_per_step": 8},
-            "roofline": roof, "kernels": kernels, "cpu_baseline": cb}
+            "roofline": roof, "kernels": kernels, "inference": infer, "cpu_baseline": cb}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

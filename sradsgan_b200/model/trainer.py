@@ -477,22 +477,26 @@ def tile_starts(size, tile, overlap):
 
 
 @torch.no_grad()
-def tiled_forward(generator, lr, scale, tile, overlap=16):
+def tiled_forward(generator, lr, scale, tile, overlap=16, tile_batch=8):
     """Overlapped-tile inference (new): LR tiles of `tile`^2 with `overlap` LR pixels of
     overlap, feathered (linear ramp) blending of the SR tiles.  Parity is defined per tile: each tile's
-    output equals the generator run on that tile alone."""
+    output equals the generator run on that tile alone.  Tiles (all the same shape) go through the generator
+    `tile_batch` at a time."""
     n, c, h, w = lr.shape
     out = torch.zeros(n, c, h * scale, w * scale, device=lr.device, dtype=torch.float32)
     wsum = torch.zeros(1, 1, h * scale, w * scale, device=lr.device, dtype=torch.float32)
-    for y0 in tile_starts(h, tile, overlap):
-        for x0 in tile_starts(w, tile, overlap):
-            th, tw = min(tile, h), min(tile, w)
-            sr = generator(lr[:, :, y0:y0 + th, x0:x0 + tw].contiguous()).float()
+    th, tw = min(tile, h), min(tile, w)
+    origins = [(y0, x0) for y0 in tile_starts(h, tile, overlap) for x0 in tile_starts(w, tile, overlap)]
+    for i in range(0, len(origins), max(1, tile_batch // max(n, 1))):
+        group = origins[i:i + max(1, tile_batch // max(n, 1))]
+        batch = torch.cat([lr[:, :, y0:y0 + th, x0:x0 + tw] for y0, x0 in group], dim=0).contiguous()
+        sr = generator(batch).float()
+        for k, (y0, x0) in enumerate(group):
             wy = _feather(th * scale, overlap * scale, y0 > 0, y0 + th < h, lr.device)
             wx = _feather(tw * scale, overlap * scale, x0 > 0, x0 + tw < w, lr.device)
             wgt = wy.view(1, 1, -1, 1) * wx.view(1, 1, 1, -1)
             ys, xs = y0 * scale, x0 * scale
-            out[:, :, ys:ys + th * scale, xs:xs + tw * scale] += sr * wgt
+            out[:, :, ys:ys + th * scale, xs:xs + tw * scale] += sr[k * n:(k + 1) * n] * wgt
             wsum[:, :, ys:ys + th * scale, xs:xs + tw * scale] += wgt
     return out / wsum
 
