@@ -139,6 +139,27 @@ int sr_bn_act_bwd_bwd(const void* u, const void* gy, const void* x, int dtype, i
                       const float* dgamma, const float* dbeta, float slope, void* d_gy, void* d_x, float* d_gamma,
                       void* workspace, void* stream);
 
+/* Position attention SGAM (model/sradsgan.py:153-176) without the N x N energy / softmax tensors (N = P tokens per image,
+ * q, k: [N][P][8] in qk_dtype, v / o / dO: [N][P][64] bf16, statistics fp32 [N][P]).
+ *   sr_sgam_stats : m = row max of q.k^T, linv = 1 / sum exp(q.k^T - m)                      (softmax(dim=-1), :169)
+ *   sr_sgam_pv    : acc[r] = sum_c exp(a_r.b_c - row_m[r] - col_m[c]) row_s[r] col_s[c] vals[c]   (tcgen05)
+ *                   forward  (a=q, b=k, row_m=m, row_s=linv, vals=v): o16 = acc, y32 = gamma*acc + resid32   (:170-172)
+ *                   backward (a=k, b=q, col_m=m, col_s=linv, vals=dO): o16 = dV
+ *   sr_sgam_ds    : out8[r] = sum_c P(r,c) (rowvals[r].colvals[c] - row_d[r] - col_d[c]) b_c       (tcgen05 + SIMT)
+ *                   dQ: a=q, b=k, rowvals=dO, colvals=v, row_m=m, row_s=linv, row_d=D;  dK: a=k, b=q, rowvals=v, colvals=dO,
+ *                   col_m=m, col_s=linv, col_d=D
+ *   sr_sgam_bwd_prep : dO = gamma*dy (bf16), D[r] = sum_ch dO o, dgamma += sum dy o.
+ * Statistic pointers may be NULL (0 for m / d, 1 for s). */
+int sr_sgam_stats(const void* q, const void* k, int qk_dtype, int N, int P, float* m, float* linv, void* stream);
+int sr_sgam_pv(const void* a, const void* b, int ab_dtype, const void* vals16, const float* row_m, const float* row_s,
+               const float* col_m, const float* col_s, int N, int P, void* o16, float* y32, const float* resid32,
+               const float* gamma, void* stream);
+int sr_sgam_ds(const void* a, const void* b, int ab_dtype, const void* rowvals16, const void* colvals16, const float* row_m,
+               const float* row_s, const float* row_d, const float* col_m, const float* col_s, const float* col_d, int N, int P,
+               float* out8, void* stream);
+int sr_sgam_bwd_prep(const float* dy, const void* o16, const float* gamma, int64_t rows, void* do16, float* d_out, float* dgamma,
+                     void* stream);
+
 /* out[c] = sum over rows of x[rows][C] (fp32 accumulate); sq (may be NULL) = sum of squares.
  * BatchNorm2d batch statistics (model/sradsgan.py:478) and bias gradients. */
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate,

@@ -20,6 +20,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
     "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate", "sr_set_workspace",
+    "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep",
 ]
 
 
@@ -83,6 +84,12 @@ def load():
     lib.sr_bn_act_bwd_bwd.restype = i32
     lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
     lib.sr_debug_umma_shift.restype = i32
+    lib.sr_sgam_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.sr_sgam_pv.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.sr_sgam_ds.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.sr_sgam_bwd_prep.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+    for name in ("sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep"):
+        getattr(lib, name).restype = i32
     lib.sr_set_workspace.argtypes = [vp, ctypes.c_uint64]
     lib.sr_set_workspace.restype = i32
     lib.sr_debug_umma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
@@ -363,6 +370,50 @@ class CudaBackend:
         _check(self.lib.sr_bn_act_bwd_bwd(_ptr(u), _ptr(gy), _ptr(x), _dt(x), n * h * w, c, _ptr(save), _ptr(dgamma), _ptr(dbeta),
                                           float(slope), _ptr(d_gy), _ptr(d_x), _ptr(d_gamma), _ptr(ws), _stream()), "bn_act_bwd_bwd")
         return d_gy, d_x, d_gamma
+
+    # -- SGAM flash attention (tokens-major views of NHWC tensors) ---------------------------------------
+    def sgam_stats(self, q, k):
+        """q, k: (N, 8, H, W) NHWC -> (m, linv): fp32 [N, H*W]"""
+        q, k = _nhwc(q), _nhwc(k)
+        n, d, h, w = q.shape
+        m = torch.empty((n, h * w), dtype=torch.float32, device=q.device)
+        linv = torch.empty_like(m)
+        _check(self.lib.sr_sgam_stats(_ptr(q), _ptr(k), _dt(q), n, h * w, _ptr(m), _ptr(linv), _stream()), "sgam_stats")
+        return m, linv
+
+    def sgam_pv(self, a, b, vals, row_m=None, row_s=None, col_m=None, col_s=None, resid=None, gamma=None, want_o16=True):
+        """-> (o16 | None, y32 | None); a, b: (N,8,H,W); vals: (N,64,H,W) bf16; resid: (N,64,H,W) fp32"""
+        a, b, vals = _nhwc(a), _nhwc(b), _nhwc(vals)
+        n, c, h, w = vals.shape
+        o16 = torch.empty_like(vals) if want_o16 else None
+        y32 = None
+        if resid is not None:
+            resid = _nhwc(resid.float())
+            y32 = torch.empty_like(resid)
+        _check(self.lib.sr_sgam_pv(_ptr(a), _ptr(b), _dt(a), _ptr(vals), _ptr(row_m), _ptr(row_s), _ptr(col_m), _ptr(col_s), n, h * w,
+                                   _ptr(o16), _ptr(y32), _ptr(resid), _ptr(gamma), _stream()), "sgam_pv")
+        return o16, y32
+
+    def sgam_ds(self, a, b, rowvals, colvals, row_m=None, row_s=None, row_d=None, col_m=None, col_s=None, col_d=None):
+        """-> out8 fp32 shaped (N, 8, H, W) NHWC"""
+        a, b, rowvals, colvals = _nhwc(a), _nhwc(b), _nhwc(rowvals), _nhwc(colvals)
+        n, c, h, w = rowvals.shape
+        out = torch.empty((n, 8, h, w), dtype=torch.float32, device=a.device, memory_format=torch.channels_last)
+        _check(self.lib.sr_sgam_ds(_ptr(a), _ptr(b), _dt(a), _ptr(rowvals), _ptr(colvals), _ptr(row_m), _ptr(row_s), _ptr(row_d),
+                                   _ptr(col_m), _ptr(col_s), _ptr(col_d), n, h * w, _ptr(out), _stream()), "sgam_ds")
+        return out
+
+    def sgam_bwd_prep(self, dy, o16, gamma):
+        """-> (dO bf16, D fp32 [N, H*W], dgamma fp32 [1])"""
+        dy = _nhwc(dy.float())
+        o16 = _nhwc(o16)
+        n, c, h, w = dy.shape
+        do16 = torch.empty_like(o16)
+        d = torch.empty((n, h * w), dtype=torch.float32, device=dy.device)
+        dgamma = torch.zeros((1,), dtype=torch.float32, device=dy.device)
+        _check(self.lib.sr_sgam_bwd_prep(_ptr(dy), _ptr(o16), _ptr(gamma), n * h * w, _ptr(do16), _ptr(d), _ptr(dgamma), _stream()),
+               "sgam_bwd_prep")
+        return do16, d, dgamma
 
     # -- reductions / optimiser ----------------------------------------------------------------
     def colsum(self, x2d, want_sq=False):

@@ -65,6 +65,16 @@ int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStr
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
 int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, const int*, float, float, float, cudaStream_t);
 
+// sgam.cu
+struct SgCommon {
+    const void* a; const void* b; int ab_f32;
+    const float* row_m; const float* row_s; const float* row_d; const float* col_m; const float* col_s; const float* col_d;
+    int N, P;
+};
+int sgam_stats(const void*, const void*, int, int, int, float*, float*, cudaStream_t);
+int sgam_pv(const SgCommon&, const void*, __nv_bfloat16*, float*, const float*, const float*, cudaStream_t);
+int sgam_ds(const SgCommon&, const void*, const void*, float*, cudaStream_t);
+int sgam_bwd_prep(const float*, const void*, const float*, long long, void*, float*, float*, cudaStream_t);
 // debug_probe.cu
 int debug_umma_shift(const void*, int, const void*, int, int, int, float*, cudaStream_t);
 int debug_umma_rate(int, int, int, int, int, long long*, cudaStream_t);
@@ -278,6 +288,44 @@ int sr_bn_act_bwd_bwd(const void* u, const void* gy, const void* x, int dtype, i
     SR_REQUIRE(u && gy && x && save && dgamma && dbeta && d_gy && d_x && d_gamma && workspace && rows > 0 && C > 0 && C % 4 == 0,
                "bn_act_bwd_bwd: bad arguments");
     return bn_act_bwd_bwd(u, gy, x, dtype, rows, C, save, dgamma, dbeta, slope, d_gy, d_x, d_gamma, (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_sgam_stats(const void* q, const void* k, int qk_dtype, int N, int P, float* m, float* linv, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(q && k && m && linv && N > 0 && P > 0, "sgam_stats: bad arguments");
+    SR_REQUIRE(qk_dtype == SR_F32 || qk_dtype == SR_BF16, "sgam_stats: bad dtype");
+    return sgam_stats(q, k, qk_dtype, N, P, m, linv, (cudaStream_t)stream);
+}
+
+int sr_sgam_pv(const void* a, const void* b, int ab_dtype, const void* vals16, const float* row_m, const float* row_s, const float* col_m,
+               const float* col_s, int N, int P, void* o16, float* y32, const float* resid32, const float* gamma, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && b && vals16 && N > 0 && P > 0 && (o16 || y32), "sgam_pv: bad arguments");
+    SR_REQUIRE(!y32 || resid32, "sgam_pv: y32 needs resid32");
+    SR_REQUIRE((long long)N * P < (1ll << 31), "sgam_pv: too many tokens");
+    SgCommon c{a, b, ab_dtype == SR_F32 ? 1 : 0, row_m, row_s, nullptr, col_m, col_s, nullptr, N, P};
+    return sgam_pv(c, vals16, (__nv_bfloat16*)o16, y32, resid32, gamma, (cudaStream_t)stream);
+}
+
+int sr_sgam_ds(const void* a, const void* b, int ab_dtype, const void* rowvals16, const void* colvals16, const float* row_m,
+               const float* row_s, const float* row_d, const float* col_m, const float* col_s, const float* col_d, int N, int P,
+               float* out8, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && b && rowvals16 && colvals16 && out8 && N > 0 && P > 0, "sgam_ds: bad arguments");
+    SR_REQUIRE((long long)N * P < (1ll << 31), "sgam_ds: too many tokens");
+    SgCommon c{a, b, ab_dtype == SR_F32 ? 1 : 0, row_m, row_s, row_d, col_m, col_s, col_d, N, P};
+    return sgam_ds(c, rowvals16, colvals16, out8, (cudaStream_t)stream);
+}
+
+int sr_sgam_bwd_prep(const float* dy, const void* o16, const float* gamma, int64_t rows, void* do16, float* d_out, float* dgamma,
+                     void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(dy && o16 && gamma && do16 && d_out && dgamma && rows > 0, "sgam_bwd_prep: bad arguments");
+    return sgam_bwd_prep(dy, o16, gamma, rows, do16, d_out, dgamma, (cudaStream_t)stream);
 }
 
 int sr_colsum(const void* x, int dtype, int64_t rows, int C, float* sum, float* sq, int accumulate, void* stream) {

@@ -143,6 +143,10 @@ class SGAM(nn.Module):
 
     def forward(self, x):
         b, c, h, w = x.shape
+        if (ops.config.compute_dtype == torch.bfloat16 and x.is_cuda and c == 64 and self.query_conv.out_channels == 8
+                and h * w >= 64):
+            # flash-style kernels (csrc/sgam.cu): no (HW) x (HW) energy / softmax tensors
+            return ops.sgam_attention(self.query_conv(x), self.key_conv(x), self.value_conv(x), x, self.gamma)
         xf = x.float()
         q = self.query_conv(x).float().flatten(2).permute(0, 2, 1)
         k = self.key_conv(x).float().flatten(2)

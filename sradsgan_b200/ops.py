@@ -322,6 +322,38 @@ def local_attn_chain(x, t, ca, sa, conv):
 
 
 # ----------------------------------------------------------------------------------------------
+# SGAM position attention without the N x N tensors (bf16 mode; fp32 mode keeps the explicit softmax path)
+# ----------------------------------------------------------------------------------------------
+class SGAMAttention(Function):
+    """y = gamma * (V softmax(Q^T K)^T) + x  (reference model/sradsgan.py:164-176) through the flash-style kernels of
+    csrc/sgam.cu.  q, k: (N, 8, H, W), v: (N, 64, H, W) in the compute dtype (bf16); x, y: fp32 trunk tensors."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, x, gamma):
+        be = _lib.backend()
+        m, linv = be.sgam_stats(q, k)
+        g32 = gamma.detach().float().contiguous()
+        o16, y = be.sgam_pv(q, k, v, row_m=m, row_s=linv, resid=x, gamma=g32)
+        ctx.save_for_backward(q, k, v, g32, m, linv, o16)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        q, k, v, g32, m, linv, o16 = ctx.saved_tensors
+        be = _lib.backend()
+        do16, d, dgamma = be.sgam_bwd_prep(dy, o16, g32)
+        dv, _ = be.sgam_pv(k, q, do16, col_m=m, col_s=linv)
+        dq = be.sgam_ds(q, k, do16, v, row_m=m, row_s=linv, row_d=d)
+        dk = be.sgam_ds(k, q, v, do16, col_m=m, col_s=linv, col_d=d)
+        return dq.to(q.dtype), dk.to(k.dtype), dv, dy, dgamma
+
+
+def sgam_attention(q, k, v, x, gamma):
+    return SGAMAttention.apply(to_compute(q), to_compute(k), to_compute(v), x.float().contiguous(memory_format=torch.channels_last), gamma)
+
+
+# ----------------------------------------------------------------------------------------------
 # any-order differentiable fused blocks of the discriminator (first-order passes AND the WGAN-GP double backward
 # run on the same kernels): conv+bias+LeakyReLU, and train-mode BatchNorm2d+LeakyReLU
 # ----------------------------------------------------------------------------------------------

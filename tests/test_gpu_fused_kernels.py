@@ -152,3 +152,43 @@ def test_discriminator_fused_double_backward_matches_unfused():
     finally:
         ops.config.double_backward = False
         ops.config.compute_dtype = prev
+
+
+@pytest.mark.parametrize("shape", [(2, 54, 54), (1, 13, 11), (3, 24, 24), (1, 40, 33)])
+def test_sgam_flash_attention_forward_backward(be, shape):
+    """csrc/sgam.cu (statistics pass, tcgen05 weight x value kernel, tcgen05 + SIMT dS kernel) vs the explicit
+    softmax(Q^T K) formulation of the reference (model/sradsgan.py:164-176) in fp32 torch, forward and all gradients."""
+    from sradsgan_b200 import ops
+    n, h, w = shape
+    g = torch.Generator().manual_seed(h * w)
+    q = (torch.randn(n, 8, h, w, generator=g) * 1.2).bfloat16()
+    k = (torch.randn(n, 8, h, w, generator=g) * 1.2).bfloat16()
+    v = torch.randn(n, 64, h, w, generator=g).bfloat16()
+    x = torch.randn(n, 64, h, w, generator=g)
+    gamma = torch.tensor([0.7])
+    dy = torch.randn(n, 64, h, w, generator=g)
+
+    def ref(q, k, v, x, gamma):
+        qf = q.flatten(2).permute(0, 2, 1)
+        att = torch.softmax(torch.bmm(qf, k.flatten(2)), dim=-1)
+        out = torch.bmm(v.flatten(2), att.permute(0, 2, 1)).view(n, 64, h, w)
+        return gamma * out + x, out
+
+    leaves = [t.float().clone().requires_grad_(True) for t in (q, k, v, x, gamma)]
+    y_ref, out_ref = ref(*leaves)
+    y_ref.backward(dy)
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
+    cu = [cl(q).requires_grad_(True), cl(k).requires_grad_(True), cl(v).requires_grad_(True), cl(x).requires_grad_(True),
+          gamma.cuda().requires_grad_(True)]
+    y = ops.SGAMAttention.apply(*cu)
+    y.backward(cl(dy))
+    torch.cuda.synchronize()
+    assert rel(y - cu[3], (y_ref - leaves[3])) < 6e-3          # the attention term itself (bf16 weights and values)
+    assert rel(y, y_ref) < 3e-3
+    names = ["dq", "dk", "dv", "dx", "dgamma"]
+    tols = [2e-2, 2e-2, 8e-3, 1e-6, 3e-2]      # dgamma = sum dy*o is a cancelling sum of bf16-rounded o: looser
+    for nm, a, b, tol in zip(names[:4], cu, leaves, tols):
+        assert rel(a.grad.float(), b.grad) < tol, (nm, rel(a.grad.float(), b.grad))
+    # dgamma = sum dy * o is a cancelling sum over bf16-rounded o: judge it against the sum of magnitudes
+    mag = (dy.abs() * out_ref.detach().abs()).sum().item()
+    assert abs(cu[4].grad.item() - leaves[4].grad.item()) < 2e-3 * mag
