@@ -148,7 +148,8 @@ int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w, const flo
         set_error("conv2d_fwd: the halo-tile tcgen05 path needs 3x3 / stride 1 / pad 1, bf16, Cin %% 64 == 0 (Cin=%d Cout=%d k=%d s=%d)", d->Cin, d->Cout, d->kh, d->stride);
         return SR_ERR_UNSUPPORTED;
     }
-    if (halo_ok && (d->impl == SR_IMPL_AUTO || d->impl == SR_IMPL_HALO)) return conv_halo_run(d, false, x, w, bias, residual, y, (cudaStream_t)stream);
+    if (halo_ok && !(d->Cout <= 4 && residual) && (d->impl == SR_IMPL_AUTO || d->impl == SR_IMPL_HALO))
+        return conv_halo_run(d, false, x, w, bias, residual, y, (cudaStream_t)stream);
     if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
         set_error("conv2d_fwd: tcgen05 path does not support this shape (Cin=%d Cout=%d k=%d s=%d dtype=%d)", d->Cin, d->Cout, d->kh, d->stride, d->in_dtype);
         return SR_ERR_UNSUPPORTED;

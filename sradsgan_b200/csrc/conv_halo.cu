@@ -23,7 +23,8 @@
 namespace sr {
 
 struct HaloParams {
-    int N, H, W, Cout;
+    int N, H, W, Cout;               // Cout = channels actually stored (bias length); narrow: Cout <= 4 computed as a 64-wide block
+    int narrow;
     int TWp, TW, TR;                 // padded tile width, valid columns (TWp - 2), output rows per tile
     int tiles_x, tiles_y, p_tiles;   // pixel tiles = N * tiles_y * tiles_x
     int block_n, n_blocks, c_blocks;
@@ -103,6 +104,15 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
         const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((bar0 + acc) * acc_stride);
         auto emit = [&](const uint32_t (&v)[32], int c) {
             if (!valid) return;
+            if (p.narrow) {              // thin output (RGB / 1-channel critic map): only the first Cout accumulator columns are real
+                if (c == 0) {
+                    OutT* o = out + ((((long long)n * p.H + oy) * p.W) + ox) * p.Cout;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < p.Cout) o[j] = from_f32<OutT>(tc_act<ACT>(__uint_as_float(v[j]) + bias_s[j], p.slope));
+                }
+                return;
+            }
             const int col = nb * p.block_n + c * 32;
             long long idx;
             if (r > 1) {
@@ -329,7 +339,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 static int g_hl_sms = 0;
 
-static bool hl_cout_ok(int Cout) { return Cout % 64 == 0; }
+static bool hl_cout_ok(int Cout) { return Cout % 64 == 0 || Cout <= 4; }
 
 bool conv_halo_supported(const sr_conv_desc* d, bool dgrad) {
     if (d->in_dtype != SR_BF16) return false;
@@ -337,7 +347,7 @@ bool conv_halo_supported(const sr_conv_desc* d, bool dgrad) {
     const int Cs = dgrad ? d->Cout : d->Cin, Cd = dgrad ? d->Cin : d->Cout;
     if (Cs % 64 != 0 || !hl_cout_ok(Cd) || Cd > HL_BIAS_MAX) return false;
     const int r = d->shuffle_r > 1 ? d->shuffle_r : 1;
-    if (!dgrad && r > 1 && (Cd % (r * r) != 0 || (Cd / (r * r)) % 32 != 0)) return false;
+    if (!dgrad && r > 1 && (Cd % (r * r) != 0 || (Cd / (r * r)) % 32 != 0 || Cd <= 4)) return false;
     if ((long long)d->N * d->H * d->W >= (1ll << 31)) return false;
     return true;
 }
@@ -379,13 +389,18 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     //   N = 256 single  : one issuer already sustains the 128 clk floor of an N=256 instruction (weights streamed)
     //   dual streamed   : Cout = 64 / 128 (one column block): two pixel tiles share every streamed weight stage
     //   single streamed : everything else (Cout = 192 * k, 128 * odd)
+    // Thin outputs (Cd <= 4: conv3 64->3, the critic's 512->1 map, the input gradients of the RGB-side convolutions) run as
+    // ONE 64-wide column block: the weight box of a tap then also covers rows of the following taps (or zero fill past
+    // the end) — junk accumulator columns that are simply never stored.
+    p.narrow = Cd <= 4 ? 1 : 0;
+    if (p.narrow && (residual || mask || p.shuffle_r > 1)) { set_error("conv_halo: thin outputs support bias / activation only"); return SR_ERR_UNSUPPORTED; }
     int bn;
-    if (Cd % 128 == 0) bn = 128; else if (Cd % 192 == 0) bn = 192; else bn = 64;
+    if (p.narrow) bn = 64; else if (Cd % 128 == 0) bn = 128; else if (Cd % 192 == 0) bn = 192; else bn = 64;
     long long res_bytes = (long long)k_blocks * bn * 128;
     bool resident = k_blocks <= HL_MAX_RES && bn <= 128 && res_bytes + 2 * p.a_stage_bytes <= HL_TILE_BUDGET;
     if (!resident && Cd % 256 == 0) bn = 256;
     p.block_n = bn;
-    p.n_blocks = Cd / bn;
+    p.n_blocks = p.narrow ? 1 : Cd / bn;
     const int b_bytes = bn * 128;
     res_bytes = (long long)k_blocks * b_bytes;
     int grid = g_hl_sms;

@@ -304,3 +304,30 @@ def test_dgrad_with_fused_activation_derivative(be, case, act):
     emu = ops_emu.EmuBackend()
     ref2 = emu.conv_dgrad_act(gy, emu.pack_weights(wt, 1, torch.bfloat16), g, y_prev, act, 0.2)
     assert rel(got, ref2) < 4e-3
+
+
+@pytest.mark.parametrize("case", [(2, 64, 40, 40, 3), (2, 512, 14, 14, 1), (1, 64, 216, 216, 3), (3, 128, 27, 27, 2)])
+def test_halo_thin_output_forward(be, case):
+    """Cout <= 4 (conv3 64->3, critic map 512->1) on the halo kernel: one 64-wide column block, only Cout columns stored."""
+    n, cin, h, w, cout = case
+    x, wt, b = _mk(n, cin, h, w, cout, 3, torch.bfloat16, seed=cin + cout)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    wp = be.pack_weights(wt.cuda(), 0, torch.bfloat16)
+    for od, tol in ((torch.bfloat16, 4e-3), (torch.float32, 2e-5)):
+        y = be.conv_fwd(xc, wp, b.cuda(), None, g, ACT_LRELU, 0.2, out_dtype=od, impl=IMPL_HALO)
+        y_ref = F.leaky_relu(F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1), 0.2)
+        assert y.shape == y_ref.shape and rel(y, y_ref) < tol, (od, rel(y, y_ref))
+
+
+@pytest.mark.parametrize("case", [(2, 3, 40, 40, 64), (1, 3, 216, 216, 64), (2, 1, 14, 14, 512)])
+def test_halo_thin_input_gradient(be, case):
+    """dgrad of a conv with Cin <= 4 (RGB-side layers): thin OUTPUT of the transposed convolution."""
+    n, cin, h, w, cout = case
+    x, wt, _ = _mk(n, cin, h, w, cout, 3, torch.bfloat16, seed=cin + cout)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    gy = torch.randn(n, cout, h, w, generator=torch.Generator().manual_seed(4)).bfloat16()
+    gyc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, torch.bfloat16), g, impl=IMPL_HALO)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, wt.bfloat16().float(), gy.float(), stride=1, padding=1)
+    assert dx.shape == dx_ref.shape and rel(dx, dx_ref) < 4e-3
