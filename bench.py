@@ -275,8 +275,16 @@ def main():
     roof = None
     if dom:
         ach = agg[dom][0] / agg[dom][1] / 1e12
+        traffic, traffic_note = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+            if dom in tr:
+                traffic = tr[dom]["traffic"]
+                traffic_note = "%s: %s; algorithmic %d B" % (tr[dom]["layer"], tr["unit"], tr[dom]["algorithmic_bytes"])
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "peak_source": peak_src, "launches": agg[dom][2],
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "launches": agg[dom][2],
                 "measured": "CUDA events around each launch of this kernel class on the launching stream, one eagerly launched step",
                 "step_frac_of_tensor_roofline": (FLOP_PER_IMG * B * K / (ms * 1e-3) / 1e12) / peak_tf}
 

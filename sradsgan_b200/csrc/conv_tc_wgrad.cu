@@ -197,9 +197,16 @@ wgrad_reduce_kernel(const float* __restrict__ partial, WgParams p, int tiles, lo
     const int tap = g * p.tg + t_local;
     const int co = cob * p.mt + row;
     if (tap >= taps || co >= p.Cout) return;
-    float acc = 0.f;
-    for (int s = 0; s < p.splits; ++s) acc += partial[(((long long)s * tiles + tile) * p.mt + row) * ncols + col];
-    p.dw[((long long)co * p.Cin + cib * p.nt + ci) * taps + tap] += acc;
+    const long long stride = (long long)tiles * p.mt * ncols;
+    const float* src = partial + ((long long)tile * p.mt + row) * ncols + col;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // independent chains: the loads of four splits are in flight together
+    int s = 0;
+    for (; s + 4 <= p.splits; s += 4) {
+        a0 += src[(long long)s * stride]; a1 += src[(long long)(s + 1) * stride];
+        a2 += src[(long long)(s + 2) * stride]; a3 += src[(long long)(s + 3) * stride];
+    }
+    for (; s < p.splits; ++s) a0 += src[(long long)s * stride];
+    p.dw[((long long)co * p.Cin + cib * p.nt + ci) * taps + tap] += (a0 + a1) + (a2 + a3);
 }
 
 static int g_wg_sms = 0;

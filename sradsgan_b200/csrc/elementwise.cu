@@ -54,6 +54,37 @@ colsum_kernel(const T* __restrict__ x, long long rows, int C, float* __restrict_
     }
 }
 
+// Vectorised variant for C in {64, 128, 256, 512}: a thread owns 4 consecutive channels (one 8- or 16-byte load per row),
+// C/4 threads span a row and the block's 256 threads cover 1024/C rows per iteration, so the per-thread channel is fixed
+// and the accumulators stay in registers; rows of the same channel meet in shared memory, then one atomic per channel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ x, long long rows, int C, float* __restrict__ sum, float* __restrict__ sq) {
+    __shared__ float red[2][256][4];
+    const int tpr = C >> 2;                       // threads per row
+    const int rpb = 256 / tpr;                    // rows per block iteration
+    const int tr = threadIdx.x / tpr, tc = (threadIdx.x - tr * tpr) * 4;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long r = (long long)blockIdx.x * rpb + tr; r < rows; r += (long long)gridDim.x * rpb) {
+        float v[4];
+        load4<T>(x + r * C + tc, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[k] += v[k]; b[k] += v[k] * v[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { red[0][threadIdx.x][k] = a[k]; red[1][threadIdx.x][k] = b[k]; }
+    __syncthreads();
+    if (threadIdx.x < tpr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float s = 0.f, q = 0.f;
+            for (int i = 0; i < rpb; ++i) { s += red[0][i * tpr + threadIdx.x][k]; q += red[1][i * tpr + threadIdx.x][k]; }
+            atomicAdd(sum + tc + k, s);
+            if (sq) atomicAdd(sq + tc + k, q);
+        }
+    }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                             const int* __restrict__ step_dev, float grad_scale, float lo, float hi) {
@@ -135,6 +166,14 @@ int colsum(const void* x, int dtype, long long rows, int C, float* sum, float* s
     long long bx = cdiv(148 * 8, cy);
     if (bx > cdiv(rows, 8)) bx = cdiv(rows, 8);
     dim3 grid((unsigned)bx, (unsigned)cy);
+    if (C == 64 || C == 128 || C == 256 || C == 512) {
+        const int rpb = 1024 / C;
+        const unsigned blocks = (unsigned)std::min<long long>(148 * 4, cdiv(rows, (long long)rpb * 4));
+        if (dtype == SR_F32) colsum_vec_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, rows, C, sum, sq);
+        else colsum_vec_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, C, sum, sq);
+        count_launch();
+        return check_launch("colsum_vec_kernel");
+    }
     if (dtype == SR_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, C, sum, sq);
     else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, rows, C, sum, sq);
     count_launch();
