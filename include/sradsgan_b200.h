@@ -67,6 +67,12 @@ int sr_conv_uses_tcgen05(const sr_conv_desc* d, int kind);
 int sr_pack_weights(const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,
                     int mode, int dtype, int shuffle_r, void* stream);
 
+/* The same re-packing for MANY weights in one launch (all convolutions of a network after its optimiser step,
+ * model/sradsgan.py:857-858,887).  table_dev: DEVICE array of n_entries records of 8 int64:
+ * {w_oihw pointer, packed pointer, Cout, Cin, kh*kw, mode, shuffle_r, first block}, where entry e owns blocks
+ * [first_block[e], first_block[e+1]) and needs ceil(Cout*Cin*kh*kw / 1024) of them; total_blocks = their sum. */
+int sr_pack_weights_batched(const void* table_dev, int n_entries, int total_blocks, int dtype, void* stream);
+
 /* y = act(conv(x,w)+bias) (+residual) ; w_packed from sr_pack_weights(mode 0); bias/residual may be NULL.
  * residual has y's layout and dtype. */
 int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w_packed, const float* bias,

@@ -20,7 +20,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
     "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate", "sr_set_workspace",
-    "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep",
+    "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep", "sr_pack_weights_batched",
 ]
 
 
@@ -66,6 +66,7 @@ def load():
     lib.sr_conv_uses_tcgen05.argtypes = [ctypes.POINTER(ConvDesc), i32]
     lib.sr_conv_uses_tcgen05.restype = i32
     lib.sr_pack_weights.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.sr_pack_weights_batched.argtypes = [vp, i32, i32, i32, vp]
     lib.sr_conv2d_fwd.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]
     lib.sr_conv2d_dgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp]
     lib.sr_conv2d_dgrad_act.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, i32, f32, vp, vp]
@@ -96,7 +97,7 @@ def load():
     lib.sr_debug_umma_rate.restype = i32
     for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
         getattr(lib, name).restype = i32
-    for name in ("sr_pack_weights", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
+    for name in ("sr_pack_weights", "sr_pack_weights_batched", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -187,6 +188,12 @@ class CudaBackend:
         _check(self.lib.sr_pack_weights(_ptr(w), _ptr(out), cout, cin, kh, kw, mode, _dt(out), int(shuffle_r), _stream()),
                "pack_weights")
         return out
+
+    def pack_weights_batched(self, table, n_entries, total_blocks, dtype):
+        """table: device int64 [n_entries, 8] (see include/sradsgan_b200.h); one launch re-packs every entry"""
+        _require_cuda(table)
+        _check(self.lib.sr_pack_weights_batched(_ptr(table), int(n_entries), int(total_blocks), (SR_F32 if dtype == torch.float32 else SR_BF16), _stream()),
+               "pack_weights_batched")
 
     # -- convolution ---------------------------------------------------------------------------
     def _desc(self, g, in_dtype, out_dtype, act=ACT_NONE, slope=0.0, shuffle_r=0, impl=IMPL_AUTO):

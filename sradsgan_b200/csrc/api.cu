@@ -42,6 +42,8 @@ int conv_halo_run(const sr_conv_desc*, bool dgrad, const void*, const void*, con
 bool conv_tc_wgrad_supported(const sr_conv_desc*);
 int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
 void conv_tc_wgrad_set_workspace(void*, size_t);
+bool conv_wgrad_halo_supported(const sr_conv_desc*);
+int conv_wgrad_halo_run(const sr_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
 // conv_thin.cu
 bool thin_fwd_supported(const sr_conv_desc*, bool dgrad);
 bool thin_wgrad_supported(const sr_conv_desc*);
@@ -62,6 +64,7 @@ int bn_act_bwd_bwd(const void*, const void*, const void*, int, long long, int, c
                    float*, float*, cudaStream_t);
 // elementwise.cu
 int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int pack_weights_batched(const long long*, int, int, int, cudaStream_t);
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
 int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, const int*, float, float, float, cudaStream_t);
 
@@ -133,6 +136,14 @@ int sr_pack_weights(const float* w, void* packed, int Cout, int Cin, int kh, int
     SR_REQUIRE(dtype == SR_F32 || dtype == SR_BF16, "pack_weights: bad dtype");
     SR_REQUIRE(shuffle_r <= 1 || (mode == 0 && Cout % (shuffle_r * shuffle_r) == 0), "pack_weights: bad shuffle_r");
     return pack_weights(w, packed, Cout, Cin, kh, kw, mode, dtype, shuffle_r, (cudaStream_t)stream);
+}
+
+int sr_pack_weights_batched(const void* table_dev, int n_entries, int total_blocks, int dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(table_dev && n_entries > 0 && total_blocks > 0, "pack_weights_batched: bad arguments");
+    SR_REQUIRE(dtype == SR_F32 || dtype == SR_BF16, "pack_weights_batched: bad dtype");
+    return pack_weights_batched((const long long*)table_dev, n_entries, total_blocks, dtype, (cudaStream_t)stream);
 }
 
 int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
@@ -211,6 +222,11 @@ int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float*
     if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
         set_error("conv2d_wgrad: tcgen05 path does not support this shape");
         return SR_ERR_UNSUPPORTED;
+    }
+    if (tc_ok && d->impl != SR_IMPL_SIMT && conv_wgrad_halo_supported(d)) {
+        // 3x3 / stride 1: shifted-view kernel, bias gradient accumulated inside it
+        if (dbias && !accumulate) cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)d->Cout, st);
+        return conv_wgrad_halo_run(d, x, dy, dw, dbias, st);
     }
     if (tc_ok && d->impl != SR_IMPL_SIMT) rc = conv_tc_wgrad_run(d, x, dy, dw, st);
     else if (d->impl == SR_IMPL_AUTO && thin_wgrad_supported(d)) rc = thin_wgrad_run(d, x, dy, dw, st);

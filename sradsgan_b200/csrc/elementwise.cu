@@ -29,6 +29,47 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, T* __restrict__
     }
 }
 
+// Batched variant: ONE launch re-packs every convolution weight of a network after its optimiser step.
+// table[e] = {w (fp32 OIHW), out, Cout, Cin, taps, mode, shuffle_r, first block}; a block handles 1024 consecutive
+// OUTPUT elements of one entry (found by binary search over the first-block column).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const long long* __restrict__ table, int n_entries) {
+    __shared__ int e_s;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_entries - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid * 8 + 7] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        e_s = lo;
+    }
+    __syncthreads();
+    const long long* t = table + (long long)e_s * 8;
+    const float* __restrict__ w = reinterpret_cast<const float*>(t[0]);
+    T* __restrict__ out = reinterpret_cast<T*>(t[1]);
+    const int Cout = (int)t[2], Cin = (int)t[3], taps = (int)t[4], mode = (int)t[5], shuffle_r = (int)t[6];
+    const long long total = (long long)Cout * Cin * taps;
+    const long long base = ((long long)blockIdx.x - t[7]) * 1024;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long i = base + k * 256 + threadIdx.x;
+        if (i >= total) break;
+        int tap, co, ci;
+        if (mode == 0) {
+            ci = (int)(i % Cin); long long q = i / Cin; co = (int)(q % Cout); tap = (int)(q / Cout);
+        } else {
+            co = (int)(i % Cout); long long q = i / Cout; ci = (int)(q % Cin); tap = (int)(q / Cin);
+        }
+        if (shuffle_r > 1) {
+            const int r2 = shuffle_r * shuffle_r, cq = Cout / r2;
+            const int sub = co / cq, c = co - sub * cq;
+            co = c * r2 + sub;
+        }
+        out[i] = from_f32<T>(w[((long long)co * Cin + ci) * taps + tap]);
+    }
+}
+
 // sum (and sum of squares) over rows of x[rows][C]; block = 32 channels x 8 row-lanes
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -154,6 +195,14 @@ int pack_weights(const float* w, void* out, int Cout, int Cin, int kh, int kw, i
     else pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)out, Cout, Cin, kh * kw, mode, shuffle_r);
     count_launch();
     return check_launch("pack_weights_kernel");
+}
+
+int pack_weights_batched(const long long* table, int n_entries, int total_blocks, int dtype, cudaStream_t st) {
+    if (n_entries <= 0 || total_blocks <= 0) return SR_OK;
+    if (dtype == SR_F32) pack_weights_batched_kernel<float><<<total_blocks, 256, 0, st>>>(table, n_entries);
+    else pack_weights_batched_kernel<__nv_bfloat16><<<total_blocks, 256, 0, st>>>(table, n_entries);
+    count_launch();
+    return check_launch("pack_weights_batched_kernel");
 }
 
 int colsum(const void* x, int dtype, long long rows, int C, float* sum, float* sq, int accumulate, cudaStream_t st) {

@@ -63,6 +63,7 @@ class FeatureExtractor(nn.Module):
             self.load_state_dict(state_dict, strict=True)
         for p in self.parameters():
             p.requires_grad_(False)
+            p._sr_frozen = True        # ops.packed: packed operands of frozen weights may be reused inside CUDA graphs
 
     def forward(self, img):
         out = img

@@ -134,6 +134,7 @@ class SRADSGAN(object):
         G, D, Fx = self.generator, self.discriminator, self.feature_extractor
         mark = getattr(self, "_phase_mark", None) or (lambda name: None)
         mark("start")
+        self._repack()
         self.optimizer_G.zero_grad()
         for p in self.optimizer_D.params:
             p.requires_grad_(False)          # skip D's weight gradients in the G step (discarded by the reference, :865)
@@ -155,6 +156,18 @@ class SRADSGAN(object):
             p.requires_grad_(True)
         return {"loss_G": loss_G.detach(), "pixel": pixel_loss_G.detach(), "content": loss_content.detach(),
                 "adv": loss_gan.detach(), "gen_hr": gen_hr.detach()}
+
+    def _repack(self):
+        """packed bf16 operands of every G and D convolution weight, refreshed from the fp32 masters by one launch per
+        network at the start of the step (ops.PackPlan; built by _capture after its eager warm-up steps)"""
+        plans = getattr(self, "_pack_plans", None)
+        if not plans:
+            return
+        if not all(pl.valid() for pl in plans):
+            self._pack_plans = None
+            return
+        for pl in plans:
+            pl.repack()
 
     def _d_phase(self, imgs_hr, gen_det, fuse_gp_backward=True):
         """discriminator losses + WGAN-GP + backward (reference :865-886): gradients in optimizer_D.flat_grad"""
@@ -243,6 +256,8 @@ class SRADSGAN(object):
                 for _ in range(2):
                     self.train_step(st["lr"], st["hr"])
             torch.cuda.current_stream().wait_stream(s)
+            if os.environ.get("SR_PACK_PLAN", "1") == "1":
+                self._pack_plans = [ops.PackPlan(self.optimizer_G.params), ops.PackPlan(self.optimizer_D.params)]
             n0 = _lib.backend().launch_count()
             if world == 1:
                 graph = torch.cuda.CUDAGraph()
@@ -272,6 +287,7 @@ class SRADSGAN(object):
         self._alpha_override = prev_override if prev_override is not st["alpha"] else None
         self._alpha_static = st["alpha"]
         st["graphs"] = graphs
+        st["pack_plans"] = getattr(self, "_pack_plans", None)     # the captured launches read the plans' device tables
         self._graph = st
 
     def _mutable_state(self):

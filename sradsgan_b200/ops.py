@@ -80,25 +80,82 @@ def bump_weight_generation():
     _generation += 1
 
 
+def next_generation():
+    """fresh, never repeated stamp for a network's parameters (FlatAdam.step)"""
+    global _generation_counter
+    _generation_counter += 1
+    return _generation_counter
+
+
+_generation_counter = 0
+
+
 def _capturing(t):
     return t.is_cuda and torch.cuda.is_current_stream_capturing()
+
+
+def _ver(w):
+    return (_generation, getattr(w, "_sr_gen", 0), w._version, w.data_ptr())
 
 
 def packed(w, mode, dtype, shuffle_r=0):
     """Packed operand for weight `w`. Cached ON the nn.Parameter object (never for temporaries such as the
     double-backward cotangents, whose storage may be recycled), keyed by layout and validated by
-    (optimiser generation, tensor version, storage address)."""
-    if not isinstance(w, torch.nn.Parameter) or _capturing(w):
+    (global generation, owning optimiser's generation, tensor version, storage address).
+    While a CUDA graph is being captured a cached operand is only trusted when something inside the SAME graph
+    keeps it fresh on replay (a PackPlan entry, re-packed at the start of every step) or the weight is frozen
+    (VGG19); otherwise the pack kernel is captured with the use."""
+    if not isinstance(w, torch.nn.Parameter):
         return _lib.backend().pack_weights(w, mode, dtype, shuffle_r)
     cache = w.__dict__.setdefault("_sr_pack", {})
     key = (mode, dtype, shuffle_r)
-    ver = (_generation, w._version, w.data_ptr())
     hit = cache.get(key)
-    if hit is not None and hit[0] == ver:
+    capturing = _capturing(w)
+    if hit is not None and hit[0] == _ver(w) and (not capturing or hit[2] or getattr(w, "_sr_frozen", False)):
         return hit[1]
     p = _lib.backend().pack_weights(w, mode, dtype, shuffle_r)
-    cache[key] = (ver, p)
+    if not capturing:
+        cache[key] = (_ver(w), p, False)
     return p
+
+
+class PackPlan:
+    """Every packed operand the parameters `params` have been used with so far (their `_sr_pack` caches), re-packed
+    by ONE kernel launch (`sr_pack_weights_batched`) into the same persistent tensors.  The trainer calls `repack()`
+    at the start of each step, inside the captured graph, so the ~200 per-use pack launches of a step collapse
+    into one per network and the operands always follow the master weights."""
+
+    def __init__(self, params):
+        self.entries = []          # (param, key, packed tensor)
+        rows, blocks = [], 0
+        self.dtype = None
+        for w in params:
+            if w.dim() != 4 or w.dtype != torch.float32 or not w.is_contiguous():
+                continue
+            for key, hit in w.__dict__.get("_sr_pack", {}).items():
+                mode, dtype, shuffle_r = key
+                if self.dtype is None:
+                    self.dtype = dtype
+                if dtype != self.dtype:
+                    continue
+                cout, cin, kh, kw = w.shape
+                rows.append([w.data_ptr(), hit[1].data_ptr(), cout, cin, kh * kw, mode, int(shuffle_r), blocks])
+                blocks += (w.numel() + 1023) // 1024
+                self.entries.append((w, key, hit[1]))
+        self.blocks = blocks
+        self.ptrs = [r[0] for r in rows]
+        self.table = torch.tensor(rows, dtype=torch.int64, device=self.entries[0][0].device) if rows else None
+
+    def valid(self):
+        """master weights still where the table points (FlatAdam views are stable; load_state_dict copies in place)"""
+        return all(w.data_ptr() == ptr for (w, _, _), ptr in zip(self.entries, self.ptrs))
+
+    def repack(self):
+        if self.table is None:
+            return
+        _lib.backend().pack_weights_batched(self.table, len(self.entries), self.blocks, self.dtype)
+        for w, key, t in self.entries:
+            w.__dict__["_sr_pack"][key] = (_ver(w), t, True)
 
 
 def to_compute(x):

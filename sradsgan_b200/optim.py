@@ -81,7 +81,10 @@ class FlatAdam:
         g = self.param_groups[0]
         _lib.backend().adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
                                  g["betas"][1], g["eps"], self.step_count, grad_scale, self.clamp, step_tensor=self.step_t)
-        ops.bump_weight_generation()
+        # the parameters changed through raw pointers: invalidate THIS network's packed operands only
+        gen = ops.next_generation()
+        for p in self.params:
+            p._sr_gen = gen
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),

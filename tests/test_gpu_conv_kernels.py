@@ -331,3 +331,28 @@ def test_halo_thin_input_gradient(be, case):
     dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, torch.bfloat16), g, impl=IMPL_HALO)
     dx_ref = torch.nn.grad.conv2d_input(x.shape, wt.bfloat16().float(), gy.float(), stride=1, padding=1)
     assert dx.shape == dx_ref.shape and rel(dx, dx_ref) < 4e-3
+
+
+def test_batched_weight_packing_matches_single_packs(be):
+    """ops.PackPlan: ONE sr_pack_weights_batched launch rewrites every cached packed operand of a set of parameters
+    (both layouts, PixelShuffle row permutation, ragged sizes) exactly as the per-weight kernel does."""
+    from sradsgan_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    shapes = [(256, 64, 3, 3, 2), (64, 256, 3, 3, 0), (64, 3, 3, 3, 0), (3, 64, 3, 3, 0), (64, 64, 1, 1, 0), (1, 2, 7, 7, 0), (576, 64, 3, 3, 3)]
+    params = [torch.nn.Parameter(torch.randn(co, ci, k, k2, generator=g).cuda()) for co, ci, k, k2, _ in shapes]
+    for w, sh in zip(params, shapes):
+        ops.packed(w, 0, torch.bfloat16, sh[4])
+        ops.packed(w, 1, torch.bfloat16, 0)
+    plan = ops.PackPlan(params)
+    assert len(plan.entries) == 2 * len(shapes) and plan.valid()
+    with torch.no_grad():
+        for w in params:
+            w.data.mul_(-1.7).add_(0.3)          # in-place change of the masters (what the fused Adam kernel does)
+    plan.repack()
+    torch.cuda.synchronize()
+    for w, sh in zip(params, shapes):
+        for mode, r in ((0, sh[4]), (1, 0)):
+            got = ops.packed(w, mode, torch.bfloat16, r)            # cache hit: the plan's persistent tensor
+            want = be.pack_weights(w, mode, torch.bfloat16, r)
+            assert got.data_ptr() in [e[2].data_ptr() for e in plan.entries]
+            assert torch.equal(got, want), (sh, mode)

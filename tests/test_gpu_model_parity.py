@@ -6,6 +6,8 @@ mode; generator-output PSNR within 0.01 dB."""
 import types
 
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -208,6 +210,53 @@ def test_two_training_iterations_vs_reference_golden(golden, prec):
                         # fp32 bits changes the vector norm by ~1e-2; everything else is held to 3e-3.
                         dtol = 3e-2 if (k.endswith(".bias") and it > 0) else 3e-3
                         assert abs(summarize(dsd[k].float().cpu(), 8)["norm"] - w["norm"]) <= dtol * max(1e-6, w["norm"]), (it, k)
+    finally:
+        ops.config.compute_dtype = prev
+
+
+def test_graphed_step_matches_eager_steps(golden):
+    """The CUDA-graph replay of the iteration (what bench.py times: batched weight re-packing at the start of the step,
+    device-side Adam step counter, static input buffers) == the same iterations launched eagerly, bf16 mode."""
+    from sradsgan_b200 import ops
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup, SRADSGAN
+    gcfg = golden["train_steps"]["cfg"]
+    ng, nb, scale = gcfg["n_groups"], gcfg["n_blocks"], gcfg["scale"]
+    Gsd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=gcfg["gseed"], init="fan"))
+    Dsd = O.make_state(O.discriminator_spec(), seed=gcfg["dseed"], init="ref")
+    Vsd = O.make_state(O.vgg_spec(), seed=gcfg["vseed"], init="fan")
+    prev = ops.config.compute_dtype
+    try:
+        nets = []
+        for _ in range(2):
+            net = SRADSGAN(_args(vgg_state=Vsd, precision="bf16"))
+            net.new_generator = lambda: GeneratorResNet(ResGroup, n_residual_blocks=ng, n_basic_blocks=nb, upscale_factor=scale)
+            net.build(init=False)
+            net.generator.load_state_dict(Gsd, strict=True)
+            net.discriminator.load_state_dict(Dsd, strict=True)
+            ops.bump_weight_generation()
+            nets.append(net)
+        eager, graphed = nets
+        batches = [O.synthetic_batch(gcfg["batch"], scale, gcfg["lr_size"] * scale, seed=gcfg["data_seed"] + it) for it in range(3)]
+        outs_e, outs_g = [], []
+        for it, (lr, hr) in enumerate(batches):
+            np.random.seed(77 + it)
+            eager._alpha_override = torch.Tensor(np.random.random((gcfg["batch"], 1, 1, 1)))
+            o = eager.train_step(lr.cuda(), hr.cuda())
+            outs_e.append({k: o[k].item() for k in ("loss_G", "loss_D")})
+        for it, (lr, hr) in enumerate(batches):
+            np.random.seed(77 + it)          # graphed_step draws the GP interpolation factors from numpy (reference :609)
+            o = graphed.graphed_step(lr.cuda(), hr.cuda())
+            outs_g.append({k: o[k].item() for k in ("loss_G", "loss_D")})
+        assert graphed._graph is not None and graphed._graph["launches"] > 0
+        if os.environ.get("SR_PACK_PLAN", "1") == "1":
+            assert graphed._pack_plans and all(pl.table is not None for pl in graphed._pack_plans)
+        for a, b in zip(outs_e, outs_g):
+            for k in a:
+                assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, outs_e, outs_g)
+        assert rel(graphed.optimizer_G.flat_param, eager.optimizer_G.flat_param) < 2e-3
+        assert rel(graphed.optimizer_D.flat_param, eager.optimizer_D.flat_param) < 2e-2
+        assert graphed.optimizer_G.step_count == eager.optimizer_G.step_count == 3
+        assert int(graphed.optimizer_G.step_t.item()) == 3 and int(graphed.optimizer_D.step_t.item()) == 3
     finally:
         ops.config.compute_dtype = prev
 
