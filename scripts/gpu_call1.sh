@@ -8,7 +8,7 @@ export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv > $OUT/gpu.txt 2>&1
 
 echo "== wgrad parity, halo kernel ==" | tee $OUT/summary.txt
-SR_WG_HALO=1 timeout 600 python -m pytest tests/test_gpu_conv_kernels.py -q -k "wgrad or batched" > $OUT/wgrad_halo.log 2>&1
+SR_WG_HALO=1 timeout -s KILL 240 python -m pytest tests/test_gpu_conv_kernels.py -q --timeout 60 -k "wgrad or batched" > $OUT/wgrad_halo.log 2>&1
 H=$?
 tail -3 $OUT/wgrad_halo.log | tee -a $OUT/summary.txt
 if [ $H -ne 0 ]; then
@@ -31,7 +31,7 @@ if [ $H -eq 0 ]; then
 fi
 
 echo "== full gpu test suite (SR_WG_HALO=$SR_WG_HALO) ==" | tee -a $OUT/summary.txt
-timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1
+timeout -s KILL 1200 python -m pytest tests -m gpu -x -q --timeout 300 > $OUT/pytest_gpu.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/summary.txt
 tail -5 $OUT/pytest_gpu.log | tee -a $OUT/summary.txt
 
