@@ -141,6 +141,39 @@ def inference_bench(size, scale=9, tile=128, overlap=16, tile_batch=8):
             "output_finite": ok}
 
 
+def edsr_bench(batch, steps, warmup, peak_tf):
+    """BASELINE.json configs[4]: EDSR(256 filters, 32 residual blocks) x4 L1 training on the same convolution kernels,
+    batch 16, HR 216^2 / LR 54^2, bf16, CUDA-graph replay; inputs resident.  293.1 GFLOP per image forward,
+    x3 for forward + input gradients + weight gradients."""
+    import torch
+    from sradsgan_b200.model.edsr import EDSR
+    net = EDSR(trainer_args(model_name="EDSR", batch_size=batch, lr=1e-4, seed=0))
+    net.build(init=True)
+    g = torch.Generator().manual_seed(4321)
+    hr = torch.rand(batch, 3, HR, HR, generator=g).cuda()
+    lr = torch.nn.functional.interpolate(hr, size=HR // SCALE, mode="bicubic", align_corners=False).clamp(0, 1)
+    for _ in range(max(warmup, 3)):
+        out = net.graphed_step(lr, hr)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = net.graphed_step(lr, hr)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flop_img = 3 * 293.1e9
+    tf = flop_img * batch / (ms * 1e-3) / 1e12
+    res = {"metric": "EDSR x4 train HR images/sec (216^2)", "value": batch / (ms * 1e-3), "unit": "HR images/s", "ms_per_step": ms,
+           "tflops": tf, "frac_of_tensor_peak": tf / peak_tf, "loss_finite": bool(torch.isfinite(out["loss_G"]).item()),
+           "gpu_launches_per_step": net._graph["launches"],
+           "config": {"workload": "EDSR(256,32) x4 L1 training step, batch %d, HR 216^2 / LR 54^2, bf16, random init" % batch,
+                      "flop_per_image": flop_img}}
+    del net
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,6 +199,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-inference", action="store_true", help="skip the x9 tiled-inference measurement (second half of the metric)")
+    ap.add_argument("--no-edsr", action="store_true", help="skip the EDSR(256,32) x4 training measurement (BASELINE configs[4])")
     ap.add_argument("--infer-size", type=int, default=2048, help="side of the synthetic LR image of the inference measurement")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -292,6 +326,13 @@ def main():
     if not args.no_inference:
         infer = inference_bench(args.infer_size)
 
+    edsr = None
+    if not args.no_edsr:
+        try:
+            edsr = edsr_bench(B, 5, 3, peak_tf)
+        except Exception as e:      # the second workload must never take the headline number down with it
+            edsr = {"error": "%s: %s" % (type(e).__name__, e)}
+
     cb = None
     if not args.no_cpu_baseline:
         cb, _ = cpu_reference_step(batch=2, steps=1, warmup=0)
@@ -308,7 +349,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": imgs / e2e_s, "unit": "HR images/s", "h2d_bytes_per_step": int(lr_host.numel() * 4 + hr_host.numel() * 4),
                     "d2h_bytes_per_step": 8},
-            "roofline": roof, "kernels": kernels, "inference": infer, "cpu_baseline": cb}
+            "roofline": roof, "kernels": kernels, "inference": infer, "edsr": edsr, "cpu_baseline": cb}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

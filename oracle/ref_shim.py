@@ -41,14 +41,14 @@ def available():
     return os.path.isdir(os.path.join(REF_ROOT, "model"))
 
 
-_cached = None
+_cached = {}
 
 
-def load_reference():
-    """Returns the reference's `model.sradsgan` module (and `utils.utils` as attribute .srutils)."""
-    global _cached
-    if _cached is not None:
-        return _cached
+def load_reference(module="model.sradsgan"):
+    """Returns the reference's `model.sradsgan` module (or another `model.*` module, e.g. `model.edsr`), with
+    `utils.utils` as attribute .srutils_mod."""
+    if module in _cached:
+        return _cached[module]
     if not available():
         raise RuntimeError("reference tree not found at %s" % REF_ROOT)
     import torchvision  # noqa: F401  (must be imported before cv2/skimage stubs are registered)
@@ -71,7 +71,7 @@ def load_reference():
             del sys.modules[k]
     sys.path.insert(0, REF_ROOT)
     try:
-        mod = importlib.import_module("model.sradsgan")
+        mod = importlib.import_module(module)
         mod.srutils_mod = importlib.import_module("utils.utils")
     finally:
         sys.path.remove(REF_ROOT)
@@ -83,5 +83,5 @@ def load_reference():
     for k, v in saved.items():
         if v is not None:
             sys.modules[k] = v
-    _cached = mod
+    _cached[module] = mod
     return mod

@@ -296,39 +296,45 @@ def conv2d_fused(x, w, b=None, residual=None, stride=1, pad=0, act=ACT_NONE, slo
 
 
 class ConvActConv(Function):
-    """y2 = conv2(act(conv1(x) + b1)) + b2 — the two 3x3 convolutions of a RAB (reference model/sradsgan.py:251-253) as ONE
-    autograd node, so that the backward can multiply conv2's input gradient by act'(y1) inside the epilogue of the
-    tensor-core dgrad kernel (sr_conv2d_dgrad_act) instead of a separate pass over the 256-channel tensor."""
+    """y2 = conv2(act(conv1(x) + b1)) + b2 [+ residual] — the two 3x3 convolutions of a RAB (reference model/sradsgan.py:251-253)
+    or of an EDSR ResnetBlock (model/base_networks.py:283-297, with its `torch.add(out, residual)` as the epilogue of conv2) as
+    ONE autograd node, so that the backward can multiply conv2's input gradient by act'(y1) inside the epilogue of the
+    tensor-core dgrad kernel (sr_conv2d_dgrad_act) instead of a separate pass over the wide tensor."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, act, slope):
+    def forward(ctx, x, w1, b1, w2, b2, act, slope, residual=None, out_dtype=None):
         g1 = conv_geom(x.shape, w1.shape, 1, 1)
         be = _lib.backend()
         y1 = be.conv_fwd(x, packed(w1, 0, x.dtype), b1, None, g1, act, slope, impl=config.conv_impl)
         g2 = conv_geom(y1.shape, w2.shape, 1, 1)
-        y2 = be.conv_fwd(y1, packed(w2, 0, x.dtype), b2, None, g2, impl=config.conv_impl)
+        y2 = be.conv_fwd(y1, packed(w2, 0, x.dtype), b2, residual, g2, out_dtype=out_dtype, impl=config.conv_impl)
         ctx.g1, ctx.g2, ctx.act, ctx.slope = g1, g2, act, slope
         ctx.params = (w1, b1, w2, b2)
+        ctx.has_res = residual is not None
         ctx.save_for_backward(x, y1, w1, w2)
         return y2
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gy2):
+    def backward(ctx, gy2_in):
         x, y1, w1, w2 = ctx.saved_tensors
         _, b1, _, b2 = ctx.params
         be = _lib.backend()
-        gy2 = gy2.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        g_res = gy2_in if (ctx.has_res and ctx.needs_input_grad[7]) else None
+        gy2 = gy2_in.to(x.dtype).contiguous(memory_format=torch.channels_last)
         g1 = be.conv_dgrad_act(gy2, packed(w2, 1, x.dtype), ctx.g2, y1, ctx.act, ctx.slope, impl=config.conv_impl)
         gw2, gb2 = _wgrad(y1, gy2, ctx.g2, w2, b2, True, ctx.needs_input_grad[3], ctx.needs_input_grad[4])
         gx = be.conv_dgrad(g1, packed(w1, 1, x.dtype), ctx.g1, impl=config.conv_impl) if ctx.needs_input_grad[0] else None
         gw1, gb1 = _wgrad(x, g1, ctx.g1, w1, b1, True, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        return gx, gw1, gb1, gw2, gb2, None, None
+        return gx, gw1, gb1, gw2, gb2, None, None, g_res, None
 
 
-def conv_act_conv(x, conv1, conv2, act, slope):
-    """conv1 -> activation -> conv2 for two 3x3 / stride 1 / pad 1 Conv2d modules with biases"""
-    return ConvActConv.apply(to_compute(x), conv1.weight, conv1.bias, conv2.weight, conv2.bias, act, slope)
+def conv_act_conv(x, conv1, conv2, act, slope, residual=None, out_dtype=None):
+    """conv1 -> activation -> conv2 (+ residual) for two 3x3 / stride 1 / pad 1 Conv2d modules with biases"""
+    if residual is not None:
+        od = out_dtype or config.compute_dtype
+        residual = residual.to(od).contiguous(memory_format=torch.channels_last)
+    return ConvActConv.apply(to_compute(x), conv1.weight, conv1.bias, conv2.weight, conv2.bias, act, slope, residual, out_dtype)
 
 
 # ----------------------------------------------------------------------------------------------
