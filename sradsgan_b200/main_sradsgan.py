@@ -11,7 +11,7 @@ import torch
 
 def parse_args(argv=None):
     parser = argparse.ArgumentParser(description="B200-native SRADSGAN")
-    parser.add_argument('--model_name', type=str, default='SRADSGAN', choices=['SRADSGAN'], help='The type of model')
+    parser.add_argument('--model_name', type=str, default='SRADSGAN', choices=['SRADSGAN', 'EDSR'], help='The type of model')
     parser.add_argument('--root_dir', type=str, default='./')
     parser.add_argument('--data_dir', type=str, default='./dataset/sradsgan/')
     parser.add_argument('--train_dataset', type=list, default=["AID", "DOTA", "LoveDA", "RSSCN7_2800", "SECOND"])
@@ -56,6 +56,9 @@ def parse_args(argv=None):
     parser.add_argument('--img', type=str, default=None)
     parser.add_argument('--modelpath', type=str, default=None)
     parser.add_argument('--tile', type=int, default=0)
+    parser.add_argument('--pretrained_G', type=str, default=None, help='generator state_dict to warm-start from (chain training)')
+    parser.add_argument('--pretrained_D', type=str, default=None, help='discriminator state_dict to warm-start from')
+    parser.add_argument('--chain_scales', type=str, default='', help="e.g. '2,3,4': train these scales one after the other, each warm-started from the previous")
     return check_args(parser.parse_args(argv))
 
 
@@ -81,8 +84,14 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
     from .model.sradsgan import SRADSGAN
-    net = SRADSGAN(args)
-    if args.mode == 'train':
+    if args.model_name == 'EDSR':
+        from .model.edsr import EDSR
+        net = EDSR(args)
+    else:
+        net = SRADSGAN(args)
+    if args.mode == 'train' and args.chain_scales:
+        net.chain_train([int(v) for v in args.chain_scales.split(',')])
+    elif args.mode == 'train':
         net.train()
     elif args.mode == 'validate':
         print(net.mfeNew_validateByClass(100, save_img=True, modelpath=args.modelpath))

@@ -41,6 +41,9 @@ class SRADSGAN(object):
         self.log_interval = getattr(args, "log_interval", 50)
         self.vgg_state = getattr(args, "vgg_state", None)
         self.seed = getattr(args, "seed", 0)
+        # chain training (the paper's x2 -> x3 -> x4 ... warm starts; reference :716-721 does it by hand-editing two paths)
+        self.pretrained_G = getattr(args, "pretrained_G", None)
+        self.pretrained_D = getattr(args, "pretrained_D", None)
         ops.set_precision(self.precision)
         if self.relative:
             raise NotImplementedError("relativistic GAN branch (reference :840-844) is unreachable from the CLI and not built")
@@ -322,6 +325,8 @@ class SRADSGAN(object):
         if self.epoch != 0:                                                         # :705-710
             self.load_epoch_network(model_dir + '/generator_param_epoch_%d.pkl' % self.epoch, self.generator, strict=True)
             self.load_epoch_network(model_dir + '/discriminator_param_epoch_%d.pkl' % self.epoch, self.discriminator, strict=True)
+        elif self.pretrained_G or self.pretrained_D:                                # :716-721 (chain training warm start)
+            self.load_pretrained(self.pretrained_G, self.pretrained_D)
         self.logger = CsvLogger(os.path.join(self.save_dir, 'logs')) if _rank() == 0 else None
         lr_sz = self.crop_size // self.scale_factor
         input_lr = torch.empty(self.batch_size, self.num_channels, lr_sz, lr_sz, device=self.device)      # :739-741
@@ -448,6 +453,49 @@ class SRADSGAN(object):
         network.load_state_dict(torch.load(load_path, map_location=self.device), strict=strict)
         ops.bump_weight_generation()
         print('Trained model is loaded.')
+
+    # ------------------------------------------------------------------------------------------
+    # chain training (paper title; reference :716-721): the generator of scale s is warm-started from the trained
+    # generator of the previous scale of the chain, the critic (whose input is always the 216^2 HR image) is carried over
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def warm_start(network, state_dict):
+        """`load_state_dict(strict=False)` as the reference does (:720-721), with the one extension a chain across the two
+        up-sampler families needs: entries whose SHAPE differs (x2/x4/x8 heads are 64->256, x3/x9 heads 64->576, SURVEY.md
+        App. A) are skipped instead of raising, so they keep their fresh initialisation.  Returns (loaded, skipped) keys."""
+        own = network.state_dict()
+        ok = {k: v for k, v in state_dict.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
+        skipped = [k for k in state_dict if k not in ok]
+        network.load_state_dict(ok, strict=False)
+        ops.bump_weight_generation()
+        return sorted(ok), skipped
+
+    def load_pretrained(self, G_path=None, D_path=None):
+        for path, net in ((G_path, self.generator), (D_path, self.discriminator)):
+            if path:
+                sd = torch.load(path, map_location=self.device) if isinstance(path, str) else path
+                _, skipped = self.warm_start(net, sd)
+                print('Pretrained model is loaded (%d entries re-initialised: %s)' % (len(skipped), ", ".join(skipped[:4])))
+
+    def chain_train(self, scales=(2, 3, 4), on_stage_end=None):
+        """BASELINE.json configs[2]: train the scales of the chain one after the other in ONE process; every stage is a
+        complete `train()` of the reference (fresh Adam state, `num_epochs` epochs, own save_dir/x<scale>) whose generator
+        and critic start from the previous stage's final weights.  Returns {scale: (avg_loss_G, avg_loss_D)}."""
+        base_dir, results, prev = self.save_dir, {}, None
+        for s in scales:
+            self.scale_factor = int(s)
+            self.save_dir = os.path.join(base_dir, "x%d" % s)
+            self.epoch = 0
+            self._graph = None
+            self._pack_plans = None
+            self.pretrained_G, self.pretrained_D = (prev if prev is not None else (self.pretrained_G, self.pretrained_D))
+            results[s] = self.train()
+            prev = ({k: v.detach().clone() for k, v in self.generator.state_dict().items()},
+                    {k: v.detach().clone() for k, v in self.discriminator.state_dict().items()})
+            if on_stage_end is not None:
+                on_stage_end(s, self)
+        self.save_dir = base_dir
+        return results
 
     def save_model(self, epoch=None):
         model_dir = os.path.join(self.save_dir, 'model')
