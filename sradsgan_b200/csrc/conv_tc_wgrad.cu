@@ -386,6 +386,35 @@ wgrad_reduce_kernel(const float* __restrict__ partial, WgParams p, int tiles, lo
     p.dw[((long long)co * p.Cin + cib * p.nt + ci) * taps + tap] += (a0 + a1) + (a2 + a3);
 }
 
+// Split-K reduction of the halo variant (3x3: tg = 3, nt = 64): one block per (output channel, 64-wide ci block) gathers the
+// row's 3 x 192 partial columns (one thread per column, the splits summed in registers), transposes them through shared
+// memory into OIHW order ([ci][ky][kx]) and adds the 576 contiguous floats of dW with coalesced accesses — the one-thread-
+// per-element kernel above scatters its read-modify-writes 36 bytes apart.
+__global__ void __launch_bounds__(576)
+wgrad_reduce_rows_kernel(const float* __restrict__ partial, WgParams p, int tiles) {
+    __shared__ float row_s[576];
+    const int co = blockIdx.x / p.ci_blocks, cib = blockIdx.x - co * p.ci_blocks;
+    const int cob = co / p.mt, row = co - cob * p.mt;
+    const int e = threadIdx.x;
+    const int g = e / 192, col = e - g * 192;
+    const int t_local = col >> 6, ci = col & 63;
+    const int tile = (g * p.ci_blocks + cib) * p.co_blocks + cob;
+    const long long stride = (long long)tiles * p.mt * 192;
+    const float* src = partial + ((long long)tile * p.mt + row) * 192 + col;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int sp = 0;
+    for (; sp + 8 <= p.splits; sp += 8) {
+        const float v0 = src[(long long)sp * stride], v1 = src[(long long)(sp + 1) * stride], v2 = src[(long long)(sp + 2) * stride],
+                    v3 = src[(long long)(sp + 3) * stride], v4 = src[(long long)(sp + 4) * stride], v5 = src[(long long)(sp + 5) * stride],
+                    v6 = src[(long long)(sp + 6) * stride], v7 = src[(long long)(sp + 7) * stride];
+        a0 += v0 + v4; a1 += v1 + v5; a2 += v2 + v6; a3 += v3 + v7;
+    }
+    for (; sp < p.splits; ++sp) a0 += src[(long long)sp * stride];
+    row_s[ci * 9 + g * 3 + t_local] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    p.dw[((long long)co * p.Cin + cib * 64) * 9 + e] += row_s[e];
+}
+
 static int g_wg_sms = 0;
 static float* g_wg_workspace = nullptr;
 static size_t g_wg_workspace_bytes = 0;
@@ -551,8 +580,7 @@ int conv_wgrad_halo_run(const sr_conv_desc* d, const void* x, const void* dy, fl
     conv_wgrad_halo_kernel<<<grid, WH_THREADS, smem, st>>>(map_dy, map_x, p);
     count_launch();
     if (p.partial) {
-        const long long total = (long long)tiles * p.mt * (p.tg * p.nt);
-        wgrad_reduce_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, p, tiles, total);
+        wgrad_reduce_rows_kernel<<<(unsigned)(d->Cout * p.ci_blocks), 576, 0, st>>>(p.partial, p, tiles);
         count_launch();
     }
     return check_launch("conv_wgrad_halo_kernel");

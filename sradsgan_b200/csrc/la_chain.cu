@@ -326,6 +326,244 @@ la_bwd_apply_kernel(const float* __restrict__ gz32, const T* __restrict__ gz16, 
     if (t < LA_C) atomicAdd(db + t, bacc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16 mode: the two 64x64x64 products of the chain on the tensor cores (warp-level mma.sync m16n8k16, fp32
+// accumulation).  The fp32 SIMT kernels above spend about half of their time in the register-tiled GEMM; with
+// the products on the tensor pipe both kernels are bound by their tensor traffic.  Operands are staged in shared
+// memory as bf16 rows of 72 elements (144 B pitch: ldmatrix rows and fragment loads hit 32 distinct banks).
+// fp32 mode keeps the SIMT kernels (<=1e-4 parity).
+// ------------------------------------------------------------------------------------------------
+constexpr int LA_LD = LA_C + 8;
+
+__device__ __forceinline__ uint32_t la_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(la_smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(la_smem_u32(p)));
+}
+// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&lo); v.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = v;
+}
+
+// z = W.(m*s*x) + b + t, persistent over 64-pixel tiles.  warp = (16-pixel row tile mt, 32-channel half nh).
+__global__ void __launch_bounds__(256)
+la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s, const float* __restrict__ m,
+                    const float* __restrict__ t_res, const float* __restrict__ Wm, const float* __restrict__ bias, int P, long long NP,
+                    int tiles, float* __restrict__ z32, __nv_bfloat16* __restrict__ z16) {
+    __shared__ __align__(16) __nv_bfloat16 Ws[LA_C * LA_LD];     // [co][ci]
+    __shared__ __align__(16) __nv_bfloat16 Vs[LA_C * LA_LD];     // [pixel][ci] = m*s*x
+    __shared__ float bias_s[LA_C];
+    const int t = threadIdx.x;
+    for (int i = t; i < LA_C * LA_C; i += 256) Ws[(i >> 6) * LA_LD + (i & 63)] = __float2bfloat16_rn(Wm[i]);
+    if (t < LA_C) bias_s[t] = bias[t];
+    const int warp = t >> 5, lane = t & 31, mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
+    const int a_row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_col = ((lane >> 4) & 1) * 8;
+    const int b_row = (lane & 7) + ((lane >> 4) & 1) * 8, b_col = ((lane >> 3) & 1) * 8;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long p0 = (long long)tile * 64;
+        __syncthreads();
+        {
+            const int pl = t >> 2, cb = (t & 3) * 4;
+            const long long pix = p0 + pl;
+            if (pix < NP) {
+                const int n = (int)(pix / P);
+                const float mp = m[pix];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c = cb + 16 * jj;
+                    float v[4];
+                    load4<__nv_bfloat16>(x + pix * LA_C + c, v);
+                    const float4 sv = *reinterpret_cast<const float4*>(s + n * LA_C + c);
+                    st_bf16x4(Vs + pl * LA_LD + c, v[0] * mp * sv.x, v[1] * mp * sv.y, v[2] * mp * sv.z, v[3] * mp * sv.w);
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) st_bf16x4(Vs + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[4];
+            ldsm_x4(a, Vs + a_row * LA_LD + ks * 16 + a_col);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                uint32_t b[4];          // B[k = ci][n = co] = W[co][ci]: rows of Ws are already the "col" fragments
+                ldsm_x4(b, Ws + (nh * 32 + np * 16 + b_row) * LA_LD + ks * 16 + b_col);
+                mma_bf16(acc[np * 2], a, b[0], b[1]);
+                mma_bf16(acc[np * 2 + 1], a, b[2], b[3]);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const long long pix = p0 + mt * 16 + g + rr * 8;
+            if (pix >= NP) continue;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int co = nh * 32 + nt * 8 + 2 * tq;
+                const float2 r = *reinterpret_cast<const float2*>(t_res + pix * LA_C + co);
+                const float o0 = acc[nt][rr * 2] + bias_s[co] + r.x, o1 = acc[nt][rr * 2 + 1] + bias_s[co + 1] + r.y;
+                *reinterpret_cast<float2*>(z32 + pix * LA_C + co) = make_float2(o0, o1);
+                if (z16) *reinterpret_cast<__nv_bfloat162*>(z16 + pix * LA_C + co) = __floats2bfloat162_rn(o0, o1);
+            }
+        }
+    }
+}
+
+// Backward of the same tile: with e = m*dz staged once as bf16,
+//   g = m*dv = W^T e (GEMM 1, stored fp32),  dm = (sum_ci g*u) / m,  dW += e^T u (GEMM 2, K = pixels, both operands
+//   read transposed through ldmatrix.trans),  db += sum dz (fp32, from the loaded values),  dz_out = dz.
+__global__ void __launch_bounds__(256)
+la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __restrict__ gz16, const __nv_bfloat16* __restrict__ x,
+                        const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ Wm, int P, long long NP,
+                        int tiles, float* __restrict__ g_out, float* __restrict__ dm, float* __restrict__ dW, float* __restrict__ db,
+                        float* __restrict__ dz_out) {
+    __shared__ __align__(16) __nv_bfloat16 Ws[LA_C * LA_LD];     // [co][ci]
+    __shared__ __align__(16) __nv_bfloat16 Es[LA_C * LA_LD];     // [pixel][co] = m*dz
+    __shared__ __align__(16) __nv_bfloat16 Us[LA_C * LA_LD];     // [pixel][ci] = s*x
+    __shared__ float ms[LA_C], dm_part[2][LA_C], bsum[LA_C];
+    const int t = threadIdx.x;
+    for (int i = t; i < LA_C * LA_C; i += 256) Ws[(i >> 6) * LA_LD + (i & 63)] = __float2bfloat16_rn(Wm[i]);
+    if (t < LA_C) bsum[t] = 0.f;
+    const int warp = t >> 5, lane = t & 31, mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
+    const int r8a = (lane & 7) + ((lane >> 3) & 1) * 8, c8a = ((lane >> 4) & 1) * 8;     // matrices 1/2 = rows+8 / cols+8
+    const int r8b = (lane & 7) + ((lane >> 4) & 1) * 8, c8b = ((lane >> 3) & 1) * 8;     // matrices 1/2 = cols+8 / rows+8
+    float wacc[4][4];      // dW[co = mt*16 + g (+8)][ci = nh*32 + nt*8 + 2*tq (+1)]
+    float bacc[16];        // db partial of channels cb + 16*jj + k over this thread's pixels
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { wacc[i][j] = 0.f; bacc[i * 4 + j] = 0.f; }
+
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long p0 = (long long)tile * 64;
+        __syncthreads();
+        {
+            const int pl = t >> 2, cb = (t & 3) * 4;
+            const long long pix = p0 + pl;
+            if (pix < NP) {
+                const int n = (int)(pix / P);
+                const float mp = m[pix];
+                if ((t & 3) == 0) ms[pl] = mp;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c = cb + 16 * jj;
+                    float xv[4], d[4] = {0.f, 0.f, 0.f, 0.f};
+                    load4<__nv_bfloat16>(x + pix * LA_C + c, xv);
+                    if (gz32) { const float4 a = *reinterpret_cast<const float4*>(gz32 + pix * LA_C + c); d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; }
+                    if (gz16) { float b[4]; load4<__nv_bfloat16>(gz16 + pix * LA_C + c, b); d[0] += b[0]; d[1] += b[1]; d[2] += b[2]; d[3] += b[3]; }
+                    if (dz_out) *reinterpret_cast<float4*>(dz_out + pix * LA_C + c) = make_float4(d[0], d[1], d[2], d[3]);
+                    const float4 sv = *reinterpret_cast<const float4*>(s + n * LA_C + c);
+                    st_bf16x4(Es + pl * LA_LD + c, mp * d[0], mp * d[1], mp * d[2], mp * d[3]);
+                    st_bf16x4(Us + pl * LA_LD + c, xv[0] * sv.x, xv[1] * sv.y, xv[2] * sv.z, xv[3] * sv.w);
+                    bacc[jj * 4] += d[0]; bacc[jj * 4 + 1] += d[1]; bacc[jj * 4 + 2] += d[2]; bacc[jj * 4 + 3] += d[3];
+                }
+            } else {
+                if ((t & 3) == 0) ms[pl] = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    st_bf16x4(Es + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
+                    st_bf16x4(Us + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        __syncthreads();
+        // GEMM 1: g[pixel][ci] = sum_co e[pixel][co] * W[co][ci]      (M = pixels, N = ci, K = co)
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[4];
+            ldsm_x4(a, Es + (mt * 16 + r8a) * LA_LD + ks * 16 + c8a);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                uint32_t b[4];          // B[k = co][n = ci] = Ws[co][ci] read transposed
+                ldsm_x4_t(b, Ws + (ks * 16 + r8a) * LA_LD + nh * 32 + np * 16 + c8a);
+                mma_bf16(acc[np * 2], a, b[0], b[1]);
+                mma_bf16(acc[np * 2 + 1], a, b[2], b[3]);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int px = mt * 16 + g + rr * 8;
+            const long long pix = p0 + px;
+            float part = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int ci = nh * 32 + nt * 8 + 2 * tq;
+                const __nv_bfloat162 u2 = *reinterpret_cast<const __nv_bfloat162*>(Us + px * LA_LD + ci);
+                part += acc[nt][rr * 2] * __low2float(u2) + acc[nt][rr * 2 + 1] * __high2float(u2);
+                if (pix < NP) *reinterpret_cast<float2*>(g_out + pix * LA_C + ci) = make_float2(acc[nt][rr * 2], acc[nt][rr * 2 + 1]);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (tq == 0) dm_part[nh][px] = part;
+        }
+        // GEMM 2: dW[co][ci] += sum_pixel e[pixel][co] * u[pixel][ci]      (M = co, N = ci, K = pixels)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[4];              // A[m = co][k = pixel] = Es[pixel][co] read transposed
+            ldsm_x4_t(a, Es + (ks * 16 + r8b) * LA_LD + mt * 16 + c8b);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                uint32_t b[4];          // B[k = pixel][n = ci] = Us[pixel][ci] read transposed
+                ldsm_x4_t(b, Us + (ks * 16 + r8a) * LA_LD + nh * 32 + np * 16 + c8a);
+                mma_bf16(wacc[np * 2], a, b[0], b[1]);
+                mma_bf16(wacc[np * 2 + 1], a, b[2], b[3]);
+            }
+        }
+        __syncthreads();
+        if (t < LA_C) {
+            const long long pix = p0 + t;
+            const float mp = ms[t];
+            if (pix < NP) dm[pix] = mp > 0.f ? (dm_part[0][t] + dm_part[1][t]) / mp : 0.f;     // m = 0: de = dm*m*(1-m) = 0 anyway
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            float* o = dW + (mt * 16 + g + rr * 8) * LA_C + nh * 32 + nt * 8 + 2 * tq;
+            atomicAdd(o, wacc[nt][rr * 2]);
+            atomicAdd(o + 1, wacc[nt][rr * 2 + 1]);
+        }
+    {
+        const int cb = (t & 3) * 4;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(&bsum[cb + 16 * jj + k], bacc[jj * 4 + k]);
+    }
+    __syncthreads();
+    if (t < LA_C) atomicAdd(db + t, bsum[t]);
+}
+
+static int la_mma_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SR_LA_MMA"); on = e ? atoi(e) : 1; }
+    return on;
+}
+
 // dq[p][ch] = sum_taps w7[ch][tap] * de[p - off],  de = dm * m * (1 - m)
 __global__ void __launch_bounds__(256)
 la_conv7_dgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m, const float* __restrict__ w7, int N, int H, int W,
@@ -510,7 +748,13 @@ static int la_fwd_t(const void* x, const float* t_res, const float* fc1, const f
     la_gate_fwd_kernel<<<N, LA_C, 0, st>>>(psum, pmax, pidx, P, S, fc1, fc2, Cr, s_out, avg_out, max_out, pstar);
     la_stats_kernel<T><<<(unsigned)cdiv(NP, 8), 256, 0, st>>>((const T*)x, s_out, P, NP, q, cstar);
     la_conv7_fwd_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(q, w7, N, H, W, m_out);
-    la_apply_kernel<T><<<(unsigned)cdiv(NP, 64), 256, 0, st>>>((const T*)x, s_out, m_out, t_res, Wm, bias, P, NP, z32, (T*)z16);
+    if (sizeof(T) == 2 && la_mma_enabled()) {
+        const int tiles = (int)cdiv(NP, 64);
+        la_apply_mma_kernel<<<tiles < 296 ? tiles : 296, 256, 0, st>>>((const __nv_bfloat16*)x, s_out, m_out, t_res, Wm, bias, P, NP, tiles, z32,
+                                                                    (__nv_bfloat16*)z16);
+    } else {
+        la_apply_kernel<T><<<(unsigned)cdiv(NP, 64), 256, 0, st>>>((const T*)x, s_out, m_out, t_res, Wm, bias, P, NP, z32, (T*)z16);
+    }
     count_launch(5);
     return check_launch("la_chain_fwd");
 }
@@ -532,7 +776,11 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
     static bool attr[2] = {false, false};
     const int ai = sizeof(T) == 2 ? 1 : 0;
     if (!attr[ai]) { cudaFuncSetAttribute(la_bwd_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr[ai] = true; }
-    la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
+    if (sizeof(T) == 2 && la_mma_enabled())
+        la_bwd_apply_mma_kernel<<<grid, 256, 0, st>>>(gz32, (const __nv_bfloat16*)gz16, (const __nv_bfloat16*)x, s, m, Wm, P, NP, tiles, g, dm, dW,
+                                                     db, dz_out);
+    else
+        la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
     la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
     {
         const int bands = (H + LA_WG_ROWS - 1) / LA_WG_ROWS;
