@@ -357,16 +357,31 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float a, float b, fl
     *reinterpret_cast<uint2*>(p) = v;
 }
 
+// v -> (hi, lo) bf16 pair with hi + lo = v to 16 mantissa bits: operands that are fp32 in the reference chain (the trunk
+// gradient, the gate products, the 1x1 weights) enter the tensor-core products as hi*hi + lo*hi + hi*lo, so the chain keeps
+// fp32-class accuracy (the dropped lo*lo term is 2^-18 relative) at three MMAs per product.
+__device__ __forceinline__ void st_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float a, float b, float c, float d) {
+    const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+    const float ch = __bfloat162float(__float2bfloat16_rn(c)), dh = __bfloat162float(__float2bfloat16_rn(d));
+    st_bf16x4(hi, ah, bh, ch, dh);
+    st_bf16x4(lo, a - ah, b - bh, c - ch, d - dh);
+}
+__device__ __forceinline__ void st_split1(__nv_bfloat16* hi, __nv_bfloat16* lo, float a) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(a);
+    *hi = h;
+    *lo = __float2bfloat16_rn(a - __bfloat162float(h));
+}
+
 // z = W.(m*s*x) + b + t, persistent over 64-pixel tiles.  warp = (16-pixel row tile mt, 32-channel half nh).
 __global__ void __launch_bounds__(256)
 la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s, const float* __restrict__ m,
                     const float* __restrict__ t_res, const float* __restrict__ Wm, const float* __restrict__ bias, int P, long long NP,
                     int tiles, float* __restrict__ z32, __nv_bfloat16* __restrict__ z16) {
-    __shared__ __align__(16) __nv_bfloat16 Ws[LA_C * LA_LD];     // [co][ci]
-    __shared__ __align__(16) __nv_bfloat16 Vs[LA_C * LA_LD];     // [pixel][ci] = m*s*x
+    __shared__ __align__(16) __nv_bfloat16 Ws[LA_C * LA_LD], Wl[LA_C * LA_LD];     // [co][ci], hi / lo
+    __shared__ __align__(16) __nv_bfloat16 Vs[LA_C * LA_LD], Vl[LA_C * LA_LD];     // [pixel][ci] = m*s*x, hi / lo
     __shared__ float bias_s[LA_C];
     const int t = threadIdx.x;
-    for (int i = t; i < LA_C * LA_C; i += 256) Ws[(i >> 6) * LA_LD + (i & 63)] = __float2bfloat16_rn(Wm[i]);
+    for (int i = t; i < LA_C * LA_C; i += 256) st_split1(Ws + (i >> 6) * LA_LD + (i & 63), Wl + (i >> 6) * LA_LD + (i & 63), Wm[i]);
     if (t < LA_C) bias_s[t] = bias[t];
     const int warp = t >> 5, lane = t & 31, mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
     const int a_row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_col = ((lane >> 4) & 1) * 8;
@@ -386,11 +401,11 @@ la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
                     float v[4];
                     load4<__nv_bfloat16>(x + pix * LA_C + c, v);
                     const float4 sv = *reinterpret_cast<const float4*>(s + n * LA_C + c);
-                    st_bf16x4(Vs + pl * LA_LD + c, v[0] * mp * sv.x, v[1] * mp * sv.y, v[2] * mp * sv.z, v[3] * mp * sv.w);
+                    st_split4(Vs + pl * LA_LD + c, Vl + pl * LA_LD + c, v[0] * mp * sv.x, v[1] * mp * sv.y, v[2] * mp * sv.z, v[3] * mp * sv.w);
                 }
             } else {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) st_bf16x4(Vs + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
+                for (int jj = 0; jj < 4; ++jj) st_split4(Vs + pl * LA_LD + cb + 16 * jj, Vl + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
             }
         }
         __syncthreads();
@@ -401,14 +416,20 @@ la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            uint32_t a[4];
+            uint32_t a[4], al[4];
             ldsm_x4(a, Vs + a_row * LA_LD + ks * 16 + a_col);
+            ldsm_x4(al, Vl + a_row * LA_LD + ks * 16 + a_col);
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
-                uint32_t b[4];          // B[k = ci][n = co] = W[co][ci]: rows of Ws are already the "col" fragments
+                uint32_t b[4], bl[4];   // B[k = ci][n = co] = W[co][ci]: rows of Ws are already the "col" fragments
                 ldsm_x4(b, Ws + (nh * 32 + np * 16 + b_row) * LA_LD + ks * 16 + b_col);
+                ldsm_x4(bl, Wl + (nh * 32 + np * 16 + b_row) * LA_LD + ks * 16 + b_col);
                 mma_bf16(acc[np * 2], a, b[0], b[1]);
                 mma_bf16(acc[np * 2 + 1], a, b[2], b[3]);
+                mma_bf16(acc[np * 2], al, b[0], b[1]);
+                mma_bf16(acc[np * 2 + 1], al, b[2], b[3]);
+                mma_bf16(acc[np * 2], a, bl[0], bl[1]);
+                mma_bf16(acc[np * 2 + 1], a, bl[2], bl[3]);
             }
         }
 #pragma unroll
@@ -435,12 +456,16 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
                         const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ Wm, int P, long long NP,
                         int tiles, float* __restrict__ g_out, float* __restrict__ dm, float* __restrict__ dW, float* __restrict__ db,
                         float* __restrict__ dz_out) {
-    __shared__ __align__(16) __nv_bfloat16 Ws[LA_C * LA_LD];     // [co][ci]
-    __shared__ __align__(16) __nv_bfloat16 Es[LA_C * LA_LD];     // [pixel][co] = m*dz
-    __shared__ __align__(16) __nv_bfloat16 Us[LA_C * LA_LD];     // [pixel][ci] = s*x
+    extern __shared__ __align__(16) unsigned char la_mma_smem[];
+    __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(la_mma_smem);      // [co][ci] hi
+    __nv_bfloat16* Wl = Ws + LA_C * LA_LD;                                   //          lo
+    __nv_bfloat16* Es = Wl + LA_C * LA_LD;                                   // [pixel][co] = m*dz hi (dz lives on the fp32 trunk)
+    __nv_bfloat16* El = Es + LA_C * LA_LD;                                   //                     lo
+    __nv_bfloat16* Us = El + LA_C * LA_LD;                                   // [pixel][ci] = s*x hi
+    __nv_bfloat16* Ul = Us + LA_C * LA_LD;                                   //                   lo
     __shared__ float ms[LA_C], dm_part[2][LA_C], bsum[LA_C];
     const int t = threadIdx.x;
-    for (int i = t; i < LA_C * LA_C; i += 256) Ws[(i >> 6) * LA_LD + (i & 63)] = __float2bfloat16_rn(Wm[i]);
+    for (int i = t; i < LA_C * LA_C; i += 256) st_split1(Ws + (i >> 6) * LA_LD + (i & 63), Wl + (i >> 6) * LA_LD + (i & 63), Wm[i]);
     if (t < LA_C) bsum[t] = 0.f;
     const int warp = t >> 5, lane = t & 31, mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
     const int r8a = (lane & 7) + ((lane >> 3) & 1) * 8, c8a = ((lane >> 4) & 1) * 8;     // matrices 1/2 = rows+8 / cols+8
@@ -471,16 +496,16 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
                     if (gz16) { float b[4]; load4<__nv_bfloat16>(gz16 + pix * LA_C + c, b); d[0] += b[0]; d[1] += b[1]; d[2] += b[2]; d[3] += b[3]; }
                     if (dz_out) *reinterpret_cast<float4*>(dz_out + pix * LA_C + c) = make_float4(d[0], d[1], d[2], d[3]);
                     const float4 sv = *reinterpret_cast<const float4*>(s + n * LA_C + c);
-                    st_bf16x4(Es + pl * LA_LD + c, mp * d[0], mp * d[1], mp * d[2], mp * d[3]);
-                    st_bf16x4(Us + pl * LA_LD + c, xv[0] * sv.x, xv[1] * sv.y, xv[2] * sv.z, xv[3] * sv.w);
+                    st_split4(Es + pl * LA_LD + c, El + pl * LA_LD + c, mp * d[0], mp * d[1], mp * d[2], mp * d[3]);
+                    st_split4(Us + pl * LA_LD + c, Ul + pl * LA_LD + c, xv[0] * sv.x, xv[1] * sv.y, xv[2] * sv.z, xv[3] * sv.w);
                     bacc[jj * 4] += d[0]; bacc[jj * 4 + 1] += d[1]; bacc[jj * 4 + 2] += d[2]; bacc[jj * 4 + 3] += d[3];
                 }
             } else {
                 if ((t & 3) == 0) ms[pl] = 0.f;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    st_bf16x4(Es + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
-                    st_bf16x4(Us + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
+                    st_split4(Es + pl * LA_LD + cb + 16 * jj, El + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
+                    st_split4(Us + pl * LA_LD + cb + 16 * jj, Ul + pl * LA_LD + cb + 16 * jj, 0.f, 0.f, 0.f, 0.f);
                 }
             }
         }
@@ -493,14 +518,20 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            uint32_t a[4];
+            uint32_t a[4], al[4];
             ldsm_x4(a, Es + (mt * 16 + r8a) * LA_LD + ks * 16 + c8a);
+            ldsm_x4(al, El + (mt * 16 + r8a) * LA_LD + ks * 16 + c8a);
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
-                uint32_t b[4];          // B[k = co][n = ci] = Ws[co][ci] read transposed
+                uint32_t b[4], bl[4];   // B[k = co][n = ci] = Ws[co][ci] read transposed
                 ldsm_x4_t(b, Ws + (ks * 16 + r8a) * LA_LD + nh * 32 + np * 16 + c8a);
+                ldsm_x4_t(bl, Wl + (ks * 16 + r8a) * LA_LD + nh * 32 + np * 16 + c8a);
                 mma_bf16(acc[np * 2], a, b[0], b[1]);
                 mma_bf16(acc[np * 2 + 1], a, b[2], b[3]);
+                mma_bf16(acc[np * 2], al, b[0], b[1]);
+                mma_bf16(acc[np * 2 + 1], al, b[2], b[3]);
+                mma_bf16(acc[np * 2], a, bl[0], bl[1]);
+                mma_bf16(acc[np * 2 + 1], a, bl[2], bl[3]);
             }
         }
 #pragma unroll
@@ -512,7 +543,8 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
             for (int nt = 0; nt < 4; ++nt) {
                 const int ci = nh * 32 + nt * 8 + 2 * tq;
                 const __nv_bfloat162 u2 = *reinterpret_cast<const __nv_bfloat162*>(Us + px * LA_LD + ci);
-                part += acc[nt][rr * 2] * __low2float(u2) + acc[nt][rr * 2 + 1] * __high2float(u2);
+                const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(Ul + px * LA_LD + ci);
+                part += acc[nt][rr * 2] * (__low2float(u2) + __low2float(v2)) + acc[nt][rr * 2 + 1] * (__high2float(u2) + __high2float(v2));
                 if (pix < NP) *reinterpret_cast<float2*>(g_out + pix * LA_C + ci) = make_float2(acc[nt][rr * 2], acc[nt][rr * 2 + 1]);
             }
             part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -522,14 +554,20 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
         // GEMM 2: dW[co][ci] += sum_pixel e[pixel][co] * u[pixel][ci]      (M = co, N = ci, K = pixels)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            uint32_t a[4];              // A[m = co][k = pixel] = Es[pixel][co] read transposed
+            uint32_t a[4], al[4];       // A[m = co][k = pixel] = Es[pixel][co] read transposed
             ldsm_x4_t(a, Es + (ks * 16 + r8b) * LA_LD + mt * 16 + c8b);
+            ldsm_x4_t(al, El + (ks * 16 + r8b) * LA_LD + mt * 16 + c8b);
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
-                uint32_t b[4];          // B[k = pixel][n = ci] = Us[pixel][ci] read transposed
+                uint32_t b[4], bl[4];   // B[k = pixel][n = ci] = Us[pixel][ci] read transposed
                 ldsm_x4_t(b, Us + (ks * 16 + r8a) * LA_LD + nh * 32 + np * 16 + c8a);
+                ldsm_x4_t(bl, Ul + (ks * 16 + r8a) * LA_LD + nh * 32 + np * 16 + c8a);
                 mma_bf16(wacc[np * 2], a, b[0], b[1]);
                 mma_bf16(wacc[np * 2 + 1], a, b[2], b[3]);
+                mma_bf16(wacc[np * 2], al, b[0], b[1]);
+                mma_bf16(wacc[np * 2 + 1], al, b[2], b[3]);
+                mma_bf16(wacc[np * 2], a, bl[0], bl[1]);
+                mma_bf16(wacc[np * 2 + 1], a, bl[2], bl[3]);
             }
         }
         __syncthreads();
@@ -776,10 +814,13 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
     static bool attr[2] = {false, false};
     const int ai = sizeof(T) == 2 ? 1 : 0;
     if (!attr[ai]) { cudaFuncSetAttribute(la_bwd_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr[ai] = true; }
-    if (sizeof(T) == 2 && la_mma_enabled())
-        la_bwd_apply_mma_kernel<<<grid, 256, 0, st>>>(gz32, (const __nv_bfloat16*)gz16, (const __nv_bfloat16*)x, s, m, Wm, P, NP, tiles, g, dm, dW,
+    if (sizeof(T) == 2 && la_mma_enabled()) {
+        const size_t mma_smem = (size_t)6 * LA_C * LA_LD * sizeof(__nv_bfloat16);
+        static bool mma_attr = false;
+        if (!mma_attr) { cudaFuncSetAttribute(la_bwd_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem); mma_attr = true; }
+        la_bwd_apply_mma_kernel<<<grid, 256, mma_smem, st>>>(gz32, (const __nv_bfloat16*)gz16, (const __nv_bfloat16*)x, s, m, Wm, P, NP, tiles, g, dm, dW,
                                                      db, dz_out);
-    else
+    } else
         la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
     la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
     {

@@ -23,6 +23,8 @@ def world_size():
 
 
 def all_reduce_flat(buf, group=None):
+    from . import ops
+    ops.wgrad_join()
     """sum all-reduce of a flat gradient buffer on the current stream (no-op for one process)"""
     if is_dist():
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
@@ -78,6 +80,8 @@ class BucketReducer:
         return hook
 
     def _launch(self, ci):
+        from . import ops
+        ops.wgrad_join()               # side-stream weight gradients must have landed in the bucket
         _, s, e, _ = self.opt.chunks[ci]
         buf = self.opt.flat_grad[s:e]
         if self.comm_stream is not None:
@@ -97,6 +101,8 @@ class BucketReducer:
     def finish(self):
         """Call after backward: reduces whatever was not overlapped, then makes the compute stream wait.
         Returns the factor FlatAdam.step must apply (1/world)."""
+        from . import ops
+        ops.wgrad_join()
         if self.world > 1:
             if self.overlap:
                 for ci in range(len(self.opt.chunks)):

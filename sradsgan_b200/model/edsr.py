@@ -135,6 +135,7 @@ class EDSR(SRADSGAN):
         loss_G = self.criterion_content(gen_hr, imgs_hr)                                # :257-260
         self.reducer_G.arm()
         loss_G.backward()                                                               # :264
+        ops.wgrad_join()
         return {"loss_G": loss_G.detach(), "gen_hr": gen_hr.detach()}
 
     def train_step(self, imgs_lr, imgs_hr, fuse_gp_backward=True):

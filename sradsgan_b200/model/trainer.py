@@ -154,6 +154,7 @@ class SRADSGAN(object):
         mark("D_adv_fwd")
         self.reducer_G.arm()
         loss_G.backward()
+        ops.wgrad_join()
         mark("G_step_backward")
         for p in self.optimizer_D.params:
             p.requires_grad_(True)
@@ -195,6 +196,7 @@ class SRADSGAN(object):
         else:
             gp = torch.zeros((), device=imgs_hr.device)
             loss_D.backward()
+        ops.wgrad_join()
         return {"loss_D": loss_D.detach(), "gp": gp.detach()}
 
     def train_step(self, imgs_lr, imgs_hr, fuse_gp_backward=True):

@@ -4,6 +4,8 @@ The convolution trio (fwd / dgrad / wgrad) is closed under differentiation — e
 written with the other two — so `torch.autograd.grad(..., create_graph=True)` through the discriminator
 (the WGAN-GP penalty, reference model/sradsgan.py:621,639) works unchanged at the call site.
 """
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -45,6 +47,41 @@ def _grad_target(p):
     return getattr(p, "_sr_flat_grad", None)
 
 
+# ----------------------------------------------------------------------------------------------
+# weight gradients off the critical path
+# ----------------------------------------------------------------------------------------------
+class _WgradStream:
+    """First-order weight gradients that accumulate straight into FlatAdam's flat buffer are needed by nothing before the
+    optimiser step, while the input-gradient chain next to them is a sequence of short latency-bound kernels.  With
+    SR_WGRAD_ASYNC=1 (default) they are launched on ONE side stream (one at a time: they share the split-K workspace) that
+    waits for the producing kernels; `wgrad_join()` — called at the end of each phase and by FlatAdam.step / the gradient
+    all-reduce — makes the main stream wait for them.  Works the same under CUDA-graph capture (a forked branch of the graph).
+    The operands are kept referenced until the join, so the caching allocator cannot hand their memory to main-stream work."""
+    enabled = os.environ.get("SR_WGRAD_ASYNC", "1") == "1"
+    stream = None
+    keep = []
+
+
+def wgrad_join():
+    if _WgradStream.keep:
+        torch.cuda.current_stream().wait_stream(_WgradStream.stream)
+        _WgradStream.keep.clear()
+
+
+def _wgrad_into(x, gy, g, tw, tb):
+    be = _lib.backend()
+    if not (_WgradStream.enabled and x.is_cuda):
+        be.conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
+        return
+    ws = _WgradStream
+    if ws.stream is None or ws.stream.device != x.device:
+        ws.stream = torch.cuda.Stream(device=x.device)
+    ws.stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(ws.stream):
+        be.conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
+    ws.keep.append((x, gy))
+
+
 def _wgrad(x, gy, g, w, b, has_bias, need_w, need_b):
     """weight / bias gradient of one convolution inside a backward pass -> (gw, gb) to RETURN to autograd.
     First-order passes over FlatAdam-owned parameters accumulate in place (no temporary, no memset, no add
@@ -54,8 +91,9 @@ def _wgrad(x, gy, g, w, b, has_bias, need_w, need_b):
     tw = _grad_target(w)
     tb = _grad_target(b) if has_bias else None
     if tw is not None and (not has_bias or tb is not None):
-        _lib.backend().conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
+        _wgrad_into(x, gy, g, tw, tb)
         return None, None              # autograd still runs the parameter's post-accumulate hooks (dp.BucketReducer)
+    wgrad_join()                       # the synchronous weight-gradient kernels below use the same split-K workspace
     if torch.is_grad_enabled():
         gw, gb = ConvWgrad.apply(x, gy, g)
     else:
@@ -225,6 +263,7 @@ class ConvWgrad(Function):
         ctx.g = g
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, gy)
+        wgrad_join()
         dw, db = _lib.backend().conv_wgrad(x, gy, g, want_bias=True, impl=config.conv_impl)
         return dw, db
 

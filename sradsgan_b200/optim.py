@@ -71,10 +71,12 @@ class FlatAdam:
                 p.grad = self.flat_grad[off:off + k].view(p.shape)
 
     def zero_grad(self, set_to_none=False):
+        ops.wgrad_join()
         self.flat_grad.zero_()
         self._rebind(copy=False)
 
     def step(self, grad_scale=1.0):
+        ops.wgrad_join()               # weight gradients launched on the side stream (ops._WgradStream)
         self._rebind(copy=True)
         self.step_count += 1
         self.step_t += 1

@@ -44,9 +44,9 @@ def test_la_chain_forward_backward(be, shape, dtype):
     cu = [v.cuda() for v in (x, t, fc1, fc2, w7, W, b)]
     cu[0] = cu[0].contiguous(memory_format=torch.channels_last)
     z32, z16, sv = be.la_chain_fwd(*cu, want_lowp=True)
-    # fp32 mode: all chain math in fp32.  bf16 mode: the 64x64 products run on the tensor cores with bf16 operands
-    # (one 2^-9 rounding per operand, fp32 accumulation) like every other convolution of that mode.
-    tol = 2e-5 if dtype == torch.float32 else 2e-3
+    # fp32 mode: all chain math in fp32.  bf16 mode: the 64x64 products run on the tensor cores with every fp32 operand split
+    # into a hi + lo bf16 pair (three MMAs per product, ~2^-16 relative), fp32 accumulation.
+    tol = 2e-5 if dtype == torch.float32 else 1e-4
     assert rel(z32, z_ref) < tol
     assert rel(z16, z_ref) < (1e-6 if dtype == torch.float32 else 4e-3)
     g = torch.Generator().manual_seed(3)
@@ -56,13 +56,13 @@ def test_la_chain_forward_backward(be, shape, dtype):
     got = be.la_chain_bwd(gz32.cuda(), gz16.cuda(), cu[0], sv, cu[2], cu[3], cu[4], cu[5])
     names = ["dx", "d_fc1", "d_fc2", "d_w7", "dW", "db", "dz"]
     for nm, a, r in zip(names, got, ref):
-        lim = 2e-4 if (dtype == torch.float32 or nm == "dz") else 1e-2
+        lim = 2e-4 if (dtype == torch.float32 or nm == "dz") else (4e-3 if nm == "dx" else 1e-3)
         assert rel(a, r) < lim, (nm, rel(a, r))
     # only the fp32 gradient present: dz is the incoming gradient itself
     got2 = be.la_chain_bwd(gz32.cuda(), None, cu[0], sv, cu[2], cu[3], cu[4], cu[5])
     ref2 = emu.la_chain_bwd(gz32, None, x, sv_ref, fc1, fc2, w7, W)
-    lim2 = 1e-2 if dtype == torch.bfloat16 else 2e-4
-    assert rel(got2[4], ref2[4]) < lim2 and rel(got2[0], ref2[0]) < lim2
+    assert rel(got2[4], ref2[4]) < (1e-3 if dtype == torch.bfloat16 else 2e-4)
+    assert rel(got2[0], ref2[0]) < (4e-3 if dtype == torch.bfloat16 else 2e-4)
 
 
 @pytest.mark.parametrize("r,act", [(1, ACT_LRELU), (2, ACT_LRELU), (3, ACT_LRELU), (1, ACT_RELU)])
