@@ -141,12 +141,24 @@ class SRADSGAN(object):
         self.optimizer_G.zero_grad()
         for p in self.optimizer_D.params:
             p.requires_grad_(False)          # skip D's weight gradients in the G step (discarded by the reference, :865)
+        # VGG features of the HR batch (:837, detached): independent of the generator, so they are computed on the side
+        # stream while the generator's forward pass (a chain of short kernels) owns the main stream
+        overlap_vgg = imgs_hr.is_cuda and os.environ.get("SR_VGG_ASYNC", "1") == "1"
+        if overlap_vgg:
+            side = ops.side_stream(imgs_hr.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                real_features = Fx(imgs_hr)
         gen_hr = G(imgs_lr)                                                         # :832
         mark("G_fwd")
         pixel_loss_G = self.criterion_content(gen_hr, imgs_hr)                      # :834
         gen_features = Fx(gen_hr)                                                   # :836
-        with torch.no_grad():
-            real_features = Fx(imgs_hr)                                             # :837
+        if overlap_vgg:
+            torch.cuda.current_stream().wait_stream(side)
+            real_features.record_stream(torch.cuda.current_stream())
+        else:
+            with torch.no_grad():
+                real_features = Fx(imgs_hr)                                         # :837
         loss_content = self.criterion_content(gen_features, real_features)         # :838
         mark("VGG_fwd_x2")
         loss_gan = self.criterion_raGAN(D(gen_hr), True)                            # :847-848

@@ -62,6 +62,13 @@ class _WgradStream:
     keep = []
 
 
+def side_stream(device):
+    ws = _WgradStream
+    if ws.stream is None or ws.stream.device != device:
+        ws.stream = torch.cuda.Stream(device=device)
+    return ws.stream
+
+
 def wgrad_join():
     if _WgradStream.keep:
         torch.cuda.current_stream().wait_stream(_WgradStream.stream)
@@ -74,8 +81,7 @@ def _wgrad_into(x, gy, g, tw, tb):
         be.conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
         return
     ws = _WgradStream
-    if ws.stream is None or ws.stream.device != x.device:
-        ws.stream = torch.cuda.Stream(device=x.device)
+    side_stream(x.device)
     ws.stream.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(ws.stream):
         be.conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
