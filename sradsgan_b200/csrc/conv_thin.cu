@@ -22,9 +22,13 @@ struct ThinParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Cs <= 4 -> Cd (multiple of 64).  Register tile: one thread = 4 consecutive pixels of a row x 16 channels, so
+// Cs <= 4 -> Cd (multiple of 64).  Register tile: one thread = 4 consecutive pixels of a row x 8 channels per pass, so
 // every 16-byte weight read from shared memory feeds 16 FMAs (a 1-pixel tile is shared-memory-bandwidth bound).
-// block = 64 pixel groups x 4 channel groups.
+// block = 64 pixel groups x 4 channel groups; a pass covers 32 channels (channel = pass*32 + cg*8 + j*4 + k).
+// The weights of a pass are laid out [j][cg][k] in shared memory, so the four channel groups of a warp read four
+// ADJACENT 16-byte chunks (conflict-free + broadcast; the natural [channel] order put cg 0/2 and 1/3 on the same banks:
+// 50 % of the shared wavefronts were replays), and the 32-accumulator tile keeps the kernel under 128 registers =
+// two resident blocks per SM (the former 4 x 16 tile: 173 registers, one block, 12 % of the warp slots, FMA pipe 28 %).
 // ---------------------------------------------------------------------------------------------
 constexpr int TCI_PX = 4;
 
@@ -36,16 +40,18 @@ template <int ACT> __device__ __forceinline__ float thin_act(float x, float slop
 }
 
 template <typename TIn, typename TOut, int K, int CS, int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 thin_cin_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restrict__ wpk, const float* __restrict__ bias,
                 TOut* __restrict__ dst) {
-    extern __shared__ __align__(16) float thin_smem[];     // ws[tap][cs][Cd], then bias[Cd]
+    extern __shared__ __align__(16) float thin_smem[];     // ws[tap][cs][pass][j][cg][k], then bias[Cd]
     constexpr int TAPS = K * K, NIN = TAPS * CS, WIN = TCI_PX + K - 1;
     for (int i = threadIdx.x; i < NIN * p.Cd; i += 256) {
         const int cd = i % p.Cd; const int r = i / p.Cd; const int cs = r % CS; const int tap = r / CS;
         const int ky = tap / K, kx = tap - ky * K;
         const int wt = p.flip ? (K - 1 - ky) * K + (K - 1 - kx) : tap;      // window offset (ky,kx) reads weight tap wt
-        thin_smem[i] = to_f32<TIn>(wpk[((long long)wt * p.Cd + cd) * CS + cs]);
+        const int ps = cd >> 5, q = cd & 31;                                // channel cd = ps*32 + cgi*8 + j*4 + k
+        const int cgi = q >> 3, j = (q >> 2) & 1, k = q & 3;
+        thin_smem[r * p.Cd + ps * 32 + (j * 4 + cgi) * 4 + k] = to_f32<TIn>(wpk[((long long)wt * p.Cd + cd) * CS + cs]);
     }
     float* bias_s = thin_smem + NIN * p.Cd;
     for (int i = threadIdx.x; i < p.Cd; i += 256) bias_s[i] = bias ? bias[i] : 0.f;
@@ -72,10 +78,11 @@ thin_cin_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restrict
             for (int cs = 0; cs < CS; ++cs) in[r][c][cs] = ok ? to_f32<TIn>(sp[cs]) : 0.f;
         }
     }
-    for (int c0 = cg * 16; c0 < p.Cd; c0 += 64) {
-        float acc[TCI_PX][16];
+    for (int ps = 0; ps * 32 < p.Cd; ++ps) {
+        const int c0 = ps * 32 + cg * 8;
+        float acc[TCI_PX][8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const float b = bias_s[c0 + j];
 #pragma unroll
             for (int px = 0; px < TCI_PX; ++px) acc[px][j] = b;
@@ -86,10 +93,10 @@ thin_cin_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restrict
             for (int kx = 0; kx < K; ++kx)
 #pragma unroll
                 for (int cs = 0; cs < CS; ++cs) {
-                    const float4* wr = reinterpret_cast<const float4*>(thin_smem + (size_t)((ky * K + kx) * CS + cs) * p.Cd + c0);
+                    const float4* wr = reinterpret_cast<const float4*>(thin_smem + (size_t)((ky * K + kx) * CS + cs) * p.Cd + ps * 32) + cg;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 w = wr[j];
+                    for (int j = 0; j < 2; ++j) {
+                        const float4 w = wr[j * 4];
 #pragma unroll
                         for (int px = 0; px < TCI_PX; ++px) {
                             const float v = in[ky][px + kx][cs];
@@ -103,7 +110,7 @@ thin_cin_kernel(ThinParams p, const TIn* __restrict__ src, const TIn* __restrict
             if (ox0 + px < p.Wo) {
                 TOut* o = dst + ((((long long)n * p.Ho + oy) * p.Wo) + ox0 + px) * p.Cd + c0;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
+                for (int j = 0; j < 8; j += 4)
                     store4<TOut>(o + j, thin_act<ACT>(acc[px][j], p.slope), thin_act<ACT>(acc[px][j + 1], p.slope),
                                  thin_act<ACT>(acc[px][j + 2], p.slope), thin_act<ACT>(acc[px][j + 3], p.slope));
             }
