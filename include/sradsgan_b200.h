@@ -125,6 +125,12 @@ int sr_la_chain_bwd(const float* gz32, const void* gz16, const void* x, int x_dt
 int sr_act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act, float slope, int shuffle_r,
                int N, int Ho, int Wo, int C, void* out, int out_dtype, void* stream);
 
+/* nn.MaxPool2d(2, 2) of torchvision's VGG19 features[4] / [9] inside FeatureExtractor (model/sradsgan.py:92-94), NHWC,
+ * C % 8 == 0.  x: (N, H, W, C) -> y: (N, H/2, W/2, C) (floor).  The backward takes the saved INPUT x and routes dy to the
+ * first maximum of each window (row-major order, as torch's max_pool2d_with_indices does); dx: (N, H, W, C), fully written. */
+int sr_maxpool2x2_fwd(const void* x, int dtype, int N, int H, int W, int C, void* y, void* stream);
+int sr_maxpool2x2_bwd(const void* dy, const void* x, int dtype, int N, int H, int W, int C, void* dx, void* stream);
+
 /* Train-mode BatchNorm2d + LeakyReLU(slope) over x viewed as [rows = N*H*W][C] (C % 4 == 0), first-order only
  * (nn.BatchNorm2d + nn.LeakyReLU(0.2) of the discriminator blocks, model/sradsgan.py:476-479).
  * Normalises with the batch mean / biased variance; running_mean / running_var (nullable) are updated in place

@@ -147,6 +147,18 @@ class EmuBackend:
             gp = F.pixel_unshuffle(gp, shuffle_r)
         return gp.to(out_dtype).contiguous(memory_format=torch.channels_last)
 
+    def maxpool2x2_fwd(self, x):
+        self.launches += 1
+        return F.max_pool2d(x, 2, 2).contiguous(memory_format=torch.channels_last)
+
+    def maxpool2x2_bwd(self, dy, x):
+        self.launches += 1
+        xr = x.detach().float().requires_grad_(True)
+        with torch.enable_grad():
+            y = F.max_pool2d(xr, 2, 2)
+        (dx,) = torch.autograd.grad(y, xr, dy.float())
+        return dx.to(x.dtype).contiguous(memory_format=torch.channels_last)
+
     def bn_act_fwd(self, x, gamma, beta, running_mean, running_var, eps, momentum, slope):
         self.launches += 3
         xf = x.float()

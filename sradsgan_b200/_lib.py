@@ -20,7 +20,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
     "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate", "sr_set_workspace",
-    "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep", "sr_pack_weights_batched",
+    "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep", "sr_pack_weights_batched", "sr_maxpool2x2_fwd", "sr_maxpool2x2_bwd",
 ]
 
 
@@ -67,6 +67,10 @@ def load():
     lib.sr_conv_uses_tcgen05.restype = i32
     lib.sr_pack_weights.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.sr_pack_weights_batched.argtypes = [vp, i32, i32, i32, vp]
+    lib.sr_maxpool2x2_fwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.sr_maxpool2x2_bwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.sr_maxpool2x2_fwd.restype = i32
+    lib.sr_maxpool2x2_bwd.restype = i32
     lib.sr_conv2d_fwd.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]
     lib.sr_conv2d_dgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp]
     lib.sr_conv2d_dgrad_act.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, i32, f32, vp, vp]
@@ -339,6 +343,24 @@ class CudaBackend:
         _check(self.lib.sr_act_bwd(_ptr(gy), _dt(gy), _ptr(y), _dt(y), int(act), float(slope), int(shuffle_r or 0), g.N, g.Ho, g.Wo,
                                    g.Cout, _ptr(out), _dt(out), _stream()), "act_bwd")
         return out
+
+    # -- MaxPool2d(2, 2) (VGG19) ---------------------------------------------------------------------
+    def maxpool2x2_fwd(self, x):
+        _require_cuda(x)
+        x = _nhwc(x)
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, h // 2, w // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        _check(self.lib.sr_maxpool2x2_fwd(_ptr(x), _dt(x), n, h, w, c, _ptr(y), _stream()), "maxpool2x2_fwd")
+        return y
+
+    def maxpool2x2_bwd(self, dy, x):
+        _require_cuda(dy, x)
+        x = _nhwc(x)
+        dy = _nhwc(dy.to(x.dtype))
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x)
+        _check(self.lib.sr_maxpool2x2_bwd(_ptr(dy), _ptr(x), _dt(x), n, h, w, c, _ptr(dx), _stream()), "maxpool2x2_bwd")
+        return dx
 
     # -- train-mode BatchNorm + LeakyReLU (first-order) ---------------------------------------------
     def bn_act_fwd(self, x, gamma, beta, running_mean, running_var, eps, momentum, slope):

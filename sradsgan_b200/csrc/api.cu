@@ -65,6 +65,8 @@ int bn_act_bwd_bwd(const void*, const void*, const void*, int, long long, int, c
 // elementwise.cu
 int pack_weights(const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int pack_weights_batched(const long long*, int, int, int, cudaStream_t);
+int maxpool2_fwd(const void*, int, int, int, int, int, void*, cudaStream_t);
+int maxpool2_bwd(const void*, const void*, int, int, int, int, int, void*, cudaStream_t);
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
 int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, const int*, float, float, float, cudaStream_t);
 
@@ -277,6 +279,22 @@ int sr_act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act
     SR_REQUIRE(gy && y && out && N > 0 && Ho > 0 && Wo > 0 && C > 0, "act_bwd: bad arguments");
     SR_REQUIRE(shuffle_r <= 1 || C % (shuffle_r * shuffle_r) == 0, "act_bwd: C %% r^2 != 0");
     return act_bwd(gy, gy_dtype, y, y_dtype, act, slope, shuffle_r, N, Ho, Wo, C, out, out_dtype, (cudaStream_t)stream);
+}
+
+int sr_maxpool2x2_fwd(const void* x, int dtype, int N, int H, int W, int C, void* y, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && y && N > 0 && H > 1 && W > 1 && C > 0 && C % 8 == 0, "maxpool2x2_fwd: bad arguments (C must be a multiple of 8)");
+    SR_REQUIRE(dtype == SR_F32 || dtype == SR_BF16, "maxpool2x2_fwd: bad dtype");
+    return maxpool2_fwd(x, dtype, N, H, W, C, y, (cudaStream_t)stream);
+}
+
+int sr_maxpool2x2_bwd(const void* dy, const void* x, int dtype, int N, int H, int W, int C, void* dx, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(dy && x && dx && N > 0 && H > 1 && W > 1 && C > 0 && C % 8 == 0, "maxpool2x2_bwd: bad arguments (C must be a multiple of 8)");
+    SR_REQUIRE(dtype == SR_F32 || dtype == SR_BF16, "maxpool2x2_bwd: bad dtype");
+    return maxpool2_bwd(dy, x, dtype, N, H, W, C, dx, (cudaStream_t)stream);
 }
 
 int sr_bn_act_fwd(const void* x, int dtype, int64_t rows, int C, const float* gamma, const float* beta, float eps, float momentum,

@@ -236,6 +236,92 @@ int act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act, f
     return check_launch("act_bwd_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// MaxPool2d(2, 2) of VGG19 features[4] / [9] (reference model/sradsgan.py:92-94), NHWC.  thread = (output pixel, 8 channels):
+// four vector loads, one vector store; the backward recomputes the arg-max from the saved input (first maximum in
+// row-major window order, like torch's max_pool2d_with_indices) instead of storing an index tensor.  HBM bound.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, T* __restrict__ y) {
+    const int Ho = H >> 1, Wo = W >> 1, cv = C >> 3;
+    const long long total = (long long)N * Ho * Wo * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8; const long long pix = i / cv;
+        const int ox = (int)(pix % Wo); const long long q = pix / Wo;
+        const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+        const T* base = x + ((((long long)n * H + oy * 2) * W) + ox * 2) * C + c0;
+        float m[8], v[8];
+        load4<T>(base, *reinterpret_cast<float (*)[4]>(m)); load4<T>(base + 4, *reinterpret_cast<float (*)[4]>(m + 4));
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const T* pk = base + ((long long)(k >> 1) * W + (k & 1)) * C;
+            load4<T>(pk, *reinterpret_cast<float (*)[4]>(v)); load4<T>(pk + 4, *reinterpret_cast<float (*)[4]>(v + 4));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = v[j] > m[j] ? v[j] : m[j];
+        }
+        T* o = y + pix * C + c0;
+        store4<T>(o, m[0], m[1], m[2], m[3]);
+        store4<T>(o + 4, m[4], m[5], m[6], m[7]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int N, int H, int W, int C, T* __restrict__ dx) {
+    const int Ho = H >> 1, Wo = W >> 1, cv = C >> 3;
+    const long long total = (long long)N * Ho * Wo * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8; const long long pix = i / cv;
+        const int ox = (int)(pix % Wo); const long long q = pix / Wo;
+        const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+        const long long off = ((((long long)n * H + oy * 2) * W) + ox * 2) * C + c0;
+        float v[4][8], g[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const T* pk = x + off + ((long long)(k >> 1) * W + (k & 1)) * C;
+            load4<T>(pk, *reinterpret_cast<float (*)[4]>(v[k])); load4<T>(pk + 4, *reinterpret_cast<float (*)[4]>(v[k] + 4));
+        }
+        load4<T>(dy + pix * C + c0, *reinterpret_cast<float (*)[4]>(g)); load4<T>(dy + pix * C + c0 + 4, *reinterpret_cast<float (*)[4]>(g + 4));
+        int arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float m = v[0][j]; int a = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (v[k][j] > m) { m = v[k][j]; a = k; }
+            arg[j] = a;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            T* o = dx + off + ((long long)(k >> 1) * W + (k & 1)) * C;
+            store4<T>(o, arg[0] == k ? g[0] : 0.f, arg[1] == k ? g[1] : 0.f, arg[2] == k ? g[2] : 0.f, arg[3] == k ? g[3] : 0.f);
+            store4<T>(o + 4, arg[4] == k ? g[4] : 0.f, arg[5] == k ? g[5] : 0.f, arg[6] == k ? g[6] : 0.f, arg[7] == k ? g[7] : 0.f);
+        }
+    }
+}
+
+int maxpool2_fwd(const void* x, int dtype, int N, int H, int W, int C, void* y, cudaStream_t st) {
+    const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    if (total <= 0) return SR_OK;
+    const int blocks = (int)std::min<long long>(148 * 16, (long long)cdiv(total, 256));
+    if (dtype == SR_F32) maxpool2_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, N, H, W, C, (float*)y);
+    else maxpool2_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, N, H, W, C, (__nv_bfloat16*)y);
+    count_launch();
+    return check_launch("maxpool2_fwd_kernel");
+}
+
+int maxpool2_bwd(const void* dy, const void* x, int dtype, int N, int H, int W, int C, void* dx, cudaStream_t st) {
+    const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    const size_t esz = dtype == SR_F32 ? 4 : 2;
+    if ((H & 1) || (W & 1)) cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * esz, st);      // the odd last row / column is in no window
+    if (total <= 0) return SR_OK;
+    const int blocks = (int)std::min<long long>(148 * 16, (long long)cdiv(total, 256));
+    if (dtype == SR_F32) maxpool2_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, (const float*)x, N, H, W, C, (float*)dx);
+    else maxpool2_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, N, H, W, C, (__nv_bfloat16*)dx);
+    count_launch();
+    return check_launch("maxpool2_bwd_kernel");
+}
+
 int pack_weights(const float* w, void* out, int Cout, int Cin, int kh, int kw, int mode, int dtype, int shuffle_r, cudaStream_t st) {
     const long long total = (long long)Cout * Cin * kh * kw;
     const int blocks = (int)std::min<long long>(148 * 8, (long long)cdiv(total, 256));

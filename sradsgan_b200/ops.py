@@ -374,6 +374,25 @@ class ConvActConv(Function):
         return gx, gw1, gb1, gw2, gb2, None, None, g_res, None
 
 
+class MaxPool2x2(Function):
+    """nn.MaxPool2d(2, 2) of VGG19 (first-order): one vectorised kernel each way instead of ATen's indices kernels."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return _lib.backend().maxpool2x2_fwd(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return _lib.backend().maxpool2x2_bwd(gy, x)
+
+
+def maxpool2x2(x):
+    return MaxPool2x2.apply(to_compute(x))
+
+
 def conv_act_conv(x, conv1, conv2, act, slope, residual=None, out_dtype=None):
     """conv1 -> activation -> conv2 (+ residual) for two 3x3 / stride 1 / pad 1 Conv2d modules with biases"""
     if residual is not None:

@@ -195,3 +195,22 @@ def test_sgam_flash_attention_forward_backward(be, shape):
     # dgamma = sum dy * o is a cancelling sum over bf16-rounded o: judge it against the sum of magnitudes
     mag = (dy.abs() * out_ref.detach().abs()).sum().item()
     assert abs(cu[4].grad.item() - leaves[4].grad.item()) < 2e-3 * mag
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 20), (1, 128, 7, 9), (3, 8, 54, 54)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool2x2_forward_backward(be, shape, dtype):
+    """sr_maxpool2x2_fwd / _bwd == torch's max_pool2d and its autograd, bit for bit — including windows with tied maxima
+    (values quantised to a few levels: the gradient must go to the FIRST maximum in row-major order) and odd sizes
+    (the last row / column belongs to no window: zero gradient)."""
+    g = torch.Generator().manual_seed(shape[1] + shape[2])
+    x = (torch.randint(0, 5, shape, generator=g).float() * 0.25).to(dtype)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = be.maxpool2x2_fwd(xc)
+    xr = x.float().requires_grad_(True)
+    y_ref = F.max_pool2d(xr, 2, 2)
+    assert y.shape == y_ref.shape and torch.equal(y.float().cpu(), y_ref.detach())
+    gy = torch.randn(y_ref.shape, generator=g).to(dtype)
+    (dx_ref,) = torch.autograd.grad(y_ref, xr, gy.float())
+    dx = be.maxpool2x2_bwd(gy.cuda(), xc)
+    assert dx.shape == x.shape and torch.equal(dx.float().cpu(), dx_ref)
