@@ -140,23 +140,49 @@ la_conv7_fwd_kernel(const float* __restrict__ q, const float* __restrict__ w7, i
     m[pix] = 1.f / (1.f + __expf(-e));
 }
 
+// m = sigmoid(conv7x7(q)) at one pixel, computed by the FOUR threads (sub = 0..3, consecutive lanes) that stage this pixel in
+// the apply kernels: 12-13 taps each, two shuffles.  q is the [mean, max] map written by la_stats_kernel (L2 resident);
+// w7s = the 98 filter values in shared memory.  Replaces the separate la_conv7_fwd_kernel launch of the forward chain.
+__device__ __forceinline__ float la_conv7_quad(const float* __restrict__ q, const float* w7s, int n, int y, int x, int H, int W, int sub, bool valid) {
+    float e = 0.f;
+    if (valid) {
+        for (int tap = sub; tap < 49; tap += 4) {
+            const int ky = tap / 7, kx = tap - ky * 7;
+            const int yy = y + ky - 3, xx = x + kx - 3;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float2 v = *reinterpret_cast<const float2*>(q + (((long long)n * H + yy) * W + xx) * 2);
+            e += w7s[tap] * v.x + w7s[49 + tap] * v.y;
+        }
+    }
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    return 1.f / (1.f + __expf(-e));
+}
+
 // z = W.(m*s*x) + b + t   (64 pixels x 64 channels per block; 4x4 register tile per thread)
 template <typename T>
 __global__ void __launch_bounds__(256)
-la_apply_kernel(const T* __restrict__ x, const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ t_res,
-                const float* __restrict__ Wm, const float* __restrict__ bias, int P, long long NP,
+la_apply_kernel(const T* __restrict__ x, const float* __restrict__ s, const float* __restrict__ q, const float* __restrict__ w7,
+                float* __restrict__ m_out, const float* __restrict__ t_res,
+                const float* __restrict__ Wm, const float* __restrict__ bias, int P, int H, int Wd, long long NP,
                 float* __restrict__ z32, T* __restrict__ z16) {
     __shared__ __align__(16) float ws[LA_C][LA_C + 4];   // ws[ci][co] = W[co][ci]
     __shared__ __align__(16) float vs[LA_C][LA_C + 4];   // vs[ci][pixel]
+    __shared__ float w7s[98];
     const int t = threadIdx.x;
     for (int i = t; i < LA_C * LA_C; i += 256) ws[i % LA_C][i / LA_C] = Wm[i];
+    if (t < 98) w7s[t] = w7[t];
+    __syncthreads();
     const long long p0 = (long long)blockIdx.x * 64;
     {
         const int pl = t >> 2, cb = (t & 3) * 4;
         const long long pix = p0 + pl;
+        const bool okp = pix < NP;
+        const int n_ = okp ? (int)(pix / P) : 0, pp = okp ? (int)(pix - (long long)n_ * P) : 0;
+        const float mp = la_conv7_quad(q, w7s, n_, pp / Wd, pp % Wd, H, Wd, t & 3, okp);      // SLAM gate of this pixel
+        if (okp && (t & 3) == 0) m_out[pix] = mp;
         if (pix < NP) {
             const int n = (int)(pix / P);
-            const float mp = m[pix];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int c = cb + 16 * jj;
@@ -374,15 +400,17 @@ __device__ __forceinline__ void st_split1(__nv_bfloat16* hi, __nv_bfloat16* lo, 
 
 // z = W.(m*s*x) + b + t, persistent over 64-pixel tiles.  warp = (16-pixel row tile mt, 32-channel half nh).
 __global__ void __launch_bounds__(256)
-la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s, const float* __restrict__ m,
-                    const float* __restrict__ t_res, const float* __restrict__ Wm, const float* __restrict__ bias, int P, long long NP,
-                    int tiles, float* __restrict__ z32, __nv_bfloat16* __restrict__ z16) {
+la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s, const float* __restrict__ q,
+                    const float* __restrict__ w7, float* __restrict__ m_out,
+                    const float* __restrict__ t_res, const float* __restrict__ Wm, const float* __restrict__ bias, int P, int H, int Wd,
+                    long long NP, int tiles, float* __restrict__ z32, __nv_bfloat16* __restrict__ z16) {
     __shared__ __align__(16) __nv_bfloat16 Ws[LA_C * LA_LD], Wl[LA_C * LA_LD];     // [co][ci], hi / lo
     __shared__ __align__(16) __nv_bfloat16 Vs[LA_C * LA_LD], Vl[LA_C * LA_LD];     // [pixel][ci] = m*s*x, hi / lo
-    __shared__ float bias_s[LA_C];
+    __shared__ float bias_s[LA_C], w7s[98];
     const int t = threadIdx.x;
     for (int i = t; i < LA_C * LA_C; i += 256) st_split1(Ws + (i >> 6) * LA_LD + (i & 63), Wl + (i >> 6) * LA_LD + (i & 63), Wm[i]);
     if (t < LA_C) bias_s[t] = bias[t];
+    if (t < 98) w7s[t] = w7[t];
     const int warp = t >> 5, lane = t & 31, mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
     const int a_row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_col = ((lane >> 4) & 1) * 8;
     const int b_row = (lane & 7) + ((lane >> 4) & 1) * 8, b_col = ((lane >> 3) & 1) * 8;
@@ -392,9 +420,12 @@ la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
         {
             const int pl = t >> 2, cb = (t & 3) * 4;
             const long long pix = p0 + pl;
+            const bool okp = pix < NP;
+            const int n_ = okp ? (int)(pix / P) : 0, pp = okp ? (int)(pix - (long long)n_ * P) : 0;
+            const float mp = la_conv7_quad(q, w7s, n_, pp / Wd, pp % Wd, H, Wd, t & 3, okp);      // SLAM gate of this pixel
+            if (okp && (t & 3) == 0) m_out[pix] = mp;
             if (pix < NP) {
                 const int n = (int)(pix / P);
-                const float mp = m[pix];
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int c = cb + 16 * jj;
@@ -680,11 +711,18 @@ la_conv7_wgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m,
     if (threadIdx.x < 98) atomicAdd(dw7 + threadIdx.x, red[threadIdx.x] + red[98 + threadIdx.x]);
 }
 
-// per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x
+// per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x.
+// dq = conv7x7^T(de), de = dm*m*(1-m), is computed here by the pixel's warp (lanes split the 49 taps, two warp sums)
+// instead of a separate la_conv7_dgrad_kernel launch + a dq round trip.
 template <typename T>
 __global__ void __launch_bounds__(256)
-la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, const unsigned char* __restrict__ cstar,
+la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dm, const float* __restrict__ m, const float* __restrict__ w7,
+                    int H, int W, const unsigned char* __restrict__ cstar,
                     const T* __restrict__ x, const float* __restrict__ s, int P, int S, T* __restrict__ dx, float* __restrict__ ds) {
+    __shared__ float w7s[98];
+    __shared__ float sh[8][LA_C];
+    if (threadIdx.x < 98) w7s[threadIdx.x] = w7[threadIdx.x];
+    __syncthreads();
     const int n = blockIdx.y, sl = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (P + S - 1) / S;
@@ -693,17 +731,27 @@ la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, c
     float a0 = 0.f, a1 = 0.f;
     for (int p = p0 + warp; p < p1; p += 8) {
         const long long pix = (long long)n * P + p;
+        const int y = p / W, xq = p - y * W;
+        float qa = 0.f, qb = 0.f;
+        for (int tap = lane; tap < 49; tap += 32) {
+            const int ky = tap / 7, kx = tap - ky * 7;
+            const int yy = y - (ky - 3), xx = xq - (kx - 3);
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const long long o = ((long long)n * H + yy) * W + xx;
+            const float mv = m[o];
+            const float de = dm[o] * mv * (1.f - mv);
+            qa += w7s[tap] * de; qb += w7s[49 + tap] * de;
+        }
+        qa = warp_sum(qa); qb = warp_sum(qb);
         const float2 gv = *reinterpret_cast<const float2*>(g + pix * LA_C + lane * 2);
-        const float2 dqv = *reinterpret_cast<const float2*>(dq + pix * 2);
         const int cs = cstar[pix];
-        const float du0 = gv.x + dqv.x * (1.f / LA_C) + (cs == lane * 2 ? dqv.y : 0.f);
-        const float du1 = gv.y + dqv.x * (1.f / LA_C) + (cs == lane * 2 + 1 ? dqv.y : 0.f);
+        const float du0 = gv.x + qa * (1.f / LA_C) + (cs == lane * 2 ? qb : 0.f);
+        const float du1 = gv.y + qa * (1.f / LA_C) + (cs == lane * 2 + 1 ? qb : 0.f);
         const float x0 = to_f32<T>(x[pix * LA_C + lane * 2]), x1 = to_f32<T>(x[pix * LA_C + lane * 2 + 1]);
         a0 += du0 * x0; a1 += du1 * x1;
         dx[pix * LA_C + lane * 2] = from_f32<T>(s0 * du0);
         dx[pix * LA_C + lane * 2 + 1] = from_f32<T>(s1 * du1);
     }
-    __shared__ float sh[8][LA_C];
     sh[warp][lane * 2] = a0; sh[warp][lane * 2 + 1] = a1;
     __syncthreads();
     if (threadIdx.x < LA_C) {
@@ -785,15 +833,15 @@ static int la_fwd_t(const void* x, const float* t_res, const float* fc1, const f
     la_pool_partial_kernel<T><<<dim3(S, N), 256, 0, st>>>((const T*)x, P, S, psum, pmax, pidx);
     la_gate_fwd_kernel<<<N, LA_C, 0, st>>>(psum, pmax, pidx, P, S, fc1, fc2, Cr, s_out, avg_out, max_out, pstar);
     la_stats_kernel<T><<<(unsigned)cdiv(NP, 8), 256, 0, st>>>((const T*)x, s_out, P, NP, q, cstar);
-    la_conv7_fwd_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(q, w7, N, H, W, m_out);
+    // the SLAM gate m = sigmoid(conv7x7(q)) is computed (and stored for the backward) by the apply kernel itself
     if (sizeof(T) == 2 && la_mma_enabled()) {
         const int tiles = (int)cdiv(NP, 64);
-        la_apply_mma_kernel<<<tiles < 296 ? tiles : 296, 256, 0, st>>>((const __nv_bfloat16*)x, s_out, m_out, t_res, Wm, bias, P, NP, tiles, z32,
-                                                                    (__nv_bfloat16*)z16);
+        la_apply_mma_kernel<<<tiles < 296 ? tiles : 296, 256, 0, st>>>((const __nv_bfloat16*)x, s_out, q, w7, m_out, t_res, Wm, bias, P, H, W, NP,
+                                                                    tiles, z32, (__nv_bfloat16*)z16);
     } else {
-        la_apply_kernel<T><<<(unsigned)cdiv(NP, 64), 256, 0, st>>>((const T*)x, s_out, m_out, t_res, Wm, bias, P, NP, z32, (T*)z16);
+        la_apply_kernel<T><<<(unsigned)cdiv(NP, 64), 256, 0, st>>>((const T*)x, s_out, q, w7, m_out, t_res, Wm, bias, P, H, W, NP, z32, (T*)z16);
     }
-    count_launch(5);
+    count_launch(4);
     return check_launch("la_chain_fwd");
 }
 
@@ -822,18 +870,32 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
                                                      db, dz_out);
     } else
         la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
-    la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
+    // The 7x7 weight gradient only feeds the optimiser: it runs on an internal side stream (forked / joined with events, so
+    // the call stays stream-ordered for the caller and capturable) next to the rest of the chain.  SR_LA_SIDE=0: same stream.
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    static int side_on = -1;
+    if (side_on < 0) { const char* e = getenv("SR_LA_SIDE"); side_on = e ? atoi(e) : 1; }
+    if (side_on && !side) {
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) { side = nullptr; side_on = 0; cudaGetLastError(); }
+    }
     {
         const int bands = (H + LA_WG_ROWS - 1) / LA_WG_ROWS;
         const size_t wg_smem = sizeof(float) * ((size_t)(LA_WG_ROWS + 6) * (W + 6) * 2 + (size_t)LA_WG_ROWS * W + 2 * 98);
         static bool wg_attr = false;
         if (!wg_attr) { cudaFuncSetAttribute(la_conv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); wg_attr = true; }
-        la_conv7_wgrad_kernel<<<N * bands, 256, wg_smem, st>>>(dm, m, q, N, H, W, d_w7);
+        cudaStream_t ws_st = st;
+        if (side_on) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(side, ev_fork, 0); ws_st = side; }
+        la_conv7_wgrad_kernel<<<N * bands, 256, wg_smem, ws_st>>>(dm, m, q, N, H, W, d_w7);
+        if (side_on) cudaEventRecord(ev_join, side);
     }
-    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds);
+    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dm, m, w7, H, W, cstar, (const T*)x, s, P, S, (T*)dx, ds);
     la_gate_bwd_kernel<<<N, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, N, Cr, d_fc1, d_fc2, da, dmx);
     la_fix_kernel<T><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((T*)dx, da, dmx, pstar, P, NP * LA_C);
-    count_launch(6);
+    if (side_on) cudaStreamWaitEvent(st, ev_join, 0);
+    count_launch(5);
     return check_launch("la_chain_bwd");
 }
 

@@ -2,6 +2,7 @@
 (oracle/ops_emu.py, which is the oracle's CLAM/SLAM/conv math + torch autograd on CPU)."""
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import ops_emu
 from sradsgan_b200._lib import ACT_LRELU, ACT_RELU, conv_geom
