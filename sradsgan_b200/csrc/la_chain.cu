@@ -711,18 +711,11 @@ la_conv7_wgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m,
     if (threadIdx.x < 98) atomicAdd(dw7 + threadIdx.x, red[threadIdx.x] + red[98 + threadIdx.x]);
 }
 
-// per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x.
-// dq = conv7x7^T(de), de = dm*m*(1-m), is computed here by the pixel's warp (lanes split the 49 taps, two warp sums)
-// instead of a separate la_conv7_dgrad_kernel launch + a dq round trip.
+// per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x
 template <typename T>
 __global__ void __launch_bounds__(256)
-la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dm, const float* __restrict__ m, const float* __restrict__ w7,
-                    int H, int W, const unsigned char* __restrict__ cstar,
+la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, const unsigned char* __restrict__ cstar,
                     const T* __restrict__ x, const float* __restrict__ s, int P, int S, T* __restrict__ dx, float* __restrict__ ds) {
-    __shared__ float w7s[98];
-    __shared__ float sh[8][LA_C];
-    if (threadIdx.x < 98) w7s[threadIdx.x] = w7[threadIdx.x];
-    __syncthreads();
     const int n = blockIdx.y, sl = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (P + S - 1) / S;
@@ -731,27 +724,17 @@ la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dm, c
     float a0 = 0.f, a1 = 0.f;
     for (int p = p0 + warp; p < p1; p += 8) {
         const long long pix = (long long)n * P + p;
-        const int y = p / W, xq = p - y * W;
-        float qa = 0.f, qb = 0.f;
-        for (int tap = lane; tap < 49; tap += 32) {
-            const int ky = tap / 7, kx = tap - ky * 7;
-            const int yy = y - (ky - 3), xx = xq - (kx - 3);
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const long long o = ((long long)n * H + yy) * W + xx;
-            const float mv = m[o];
-            const float de = dm[o] * mv * (1.f - mv);
-            qa += w7s[tap] * de; qb += w7s[49 + tap] * de;
-        }
-        qa = warp_sum(qa); qb = warp_sum(qb);
         const float2 gv = *reinterpret_cast<const float2*>(g + pix * LA_C + lane * 2);
+        const float2 dqv = *reinterpret_cast<const float2*>(dq + pix * 2);
         const int cs = cstar[pix];
-        const float du0 = gv.x + qa * (1.f / LA_C) + (cs == lane * 2 ? qb : 0.f);
-        const float du1 = gv.y + qa * (1.f / LA_C) + (cs == lane * 2 + 1 ? qb : 0.f);
+        const float du0 = gv.x + dqv.x * (1.f / LA_C) + (cs == lane * 2 ? dqv.y : 0.f);
+        const float du1 = gv.y + dqv.x * (1.f / LA_C) + (cs == lane * 2 + 1 ? dqv.y : 0.f);
         const float x0 = to_f32<T>(x[pix * LA_C + lane * 2]), x1 = to_f32<T>(x[pix * LA_C + lane * 2 + 1]);
         a0 += du0 * x0; a1 += du1 * x1;
         dx[pix * LA_C + lane * 2] = from_f32<T>(s0 * du0);
         dx[pix * LA_C + lane * 2 + 1] = from_f32<T>(s1 * du1);
     }
+    __shared__ float sh[8][LA_C];
     sh[warp][lane * 2] = a0; sh[warp][lane * 2 + 1] = a1;
     __syncthreads();
     if (threadIdx.x < LA_C) {
@@ -760,6 +743,8 @@ la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dm, c
         atomicAdd(ds + n * LA_C + threadIdx.x, v);
     }
 }
+// (Computing dq inside this kernel — lanes splitting the 49 taps per pixel — was measured: chain backward 79 -> 96 us; the
+// separate la_conv7_dgrad_kernel stays.)
 
 // gate backward (tiny): one block per image; weight gradients via fp32 atomics
 __global__ void __launch_bounds__(LA_C)
@@ -813,7 +798,14 @@ la_fix_kernel(T* __restrict__ dx, const float* __restrict__ da, const float* __r
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-static int la_slices(int P) { int s = (P + 255) / 256; return s < 1 ? 1 : (s > 32 ? 32 : s); }
+// pixel slices per image of the two per-image reductions (pool partials, ds): their kernels walk a slice with one warp per
+// pixel and dependent global loads, so they want MANY blocks (measured, SR_LA_SLICE_PX = pixels per slice)
+static int la_slices(int P) {
+    static int px = -1;
+    if (px < 0) { const char* e = getenv("SR_LA_SLICE_PX"); px = e ? atoi(e) : 96; if (px < 8) px = 8; }
+    int s = (P + px - 1) / px;
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
+}
 
 size_t la_workspace_bytes(int N, int H, int W) {
     const int P = H * W, S = la_slices(P);
@@ -891,11 +883,12 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
         la_conv7_wgrad_kernel<<<N * bands, 256, wg_smem, ws_st>>>(dm, m, q, N, H, W, d_w7);
         if (side_on) cudaEventRecord(ev_join, side);
     }
-    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dm, m, w7, H, W, cstar, (const T*)x, s, P, S, (T*)dx, ds);
+    la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
+    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds);
     la_gate_bwd_kernel<<<N, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, N, Cr, d_fc1, d_fc2, da, dmx);
     la_fix_kernel<T><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((T*)dx, da, dmx, pstar, P, NP * LA_C);
     if (side_on) cudaStreamWaitEvent(st, ev_join, 0);
-    count_launch(5);
+    count_launch(6);
     return check_launch("la_chain_bwd");
 }
 
