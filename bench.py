@@ -239,12 +239,16 @@ def main():
     step_fn = net.graphed_step if use_graph else net.train_step
 
     # ---- per-kernel attribution: one eagerly-launched step with CUDA events around every library launch ----
+    # (weight gradients normally run on a side stream next to the main one; for the attribution every kernel runs alone)
+    from sradsgan_b200 import ops as _ops
+    async_prev, _ops._WgradStream.enabled = _ops._WgradStream.enabled, False
     net.train_step(lr_dev, hr_dev)
     torch.cuda.synchronize()
     be.prof = []
     net.train_step(lr_dev, hr_dev)
     torch.cuda.synchronize()
     prof, be.prof = be.prof, None
+    _ops._WgradStream.enabled = async_prev
 
     # ---- device-resident timing (`value`) ----
     for _ in range(W):

@@ -179,8 +179,9 @@ la_apply_kernel(const T* __restrict__ x, const float* __restrict__ s, const floa
         const long long pix = p0 + pl;
         const bool okp = pix < NP;
         const int n_ = okp ? (int)(pix / P) : 0, pp = okp ? (int)(pix - (long long)n_ * P) : 0;
-        const float mp = la_conv7_quad(q, w7s, n_, pp / Wd, pp % Wd, H, Wd, t & 3, okp);      // SLAM gate of this pixel
-        if (okp && (t & 3) == 0) m_out[pix] = mp;
+        float mp;                                                                               // SLAM gate of this pixel
+        if (q) { mp = la_conv7_quad(q, w7s, n_, pp / Wd, pp % Wd, H, Wd, t & 3, okp); if (okp && (t & 3) == 0) m_out[pix] = mp; }
+        else mp = okp ? m_out[pix] : 0.f;                                                       // computed by la_conv7_fwd_kernel
         if (pix < NP) {
             const int n = (int)(pix / P);
 #pragma unroll
@@ -422,8 +423,9 @@ la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
             const long long pix = p0 + pl;
             const bool okp = pix < NP;
             const int n_ = okp ? (int)(pix / P) : 0, pp = okp ? (int)(pix - (long long)n_ * P) : 0;
-            const float mp = la_conv7_quad(q, w7s, n_, pp / Wd, pp % Wd, H, Wd, t & 3, okp);      // SLAM gate of this pixel
-            if (okp && (t & 3) == 0) m_out[pix] = mp;
+            float mp;                                                                               // SLAM gate of this pixel
+            if (q) { mp = la_conv7_quad(q, w7s, n_, pp / Wd, pp % Wd, H, Wd, t & 3, okp); if (okp && (t & 3) == 0) m_out[pix] = mp; }
+            else mp = okp ? m_out[pix] : 0.f;                                                       // computed by la_conv7_fwd_kernel
             if (pix < NP) {
                 const int n = (int)(pix / P);
 #pragma unroll
@@ -711,11 +713,47 @@ la_conv7_wgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m,
     if (threadIdx.x < 98) atomicAdd(dw7 + threadIdx.x, red[threadIdx.x] + red[98 + threadIdx.x]);
 }
 
+// gate backward (tiny, per image): d(sigmoid) -> MLP backward; weight gradients via fp32 atomics.  Called by ALL threads of a
+// block (block-uniform), the first LA_C of which do the work.  `ds` is read through L2 (it was produced by other blocks' atomics).
+__device__ __forceinline__ void la_gate_bwd_body(int n, const float* __restrict__ ds, const float* __restrict__ s, const float* __restrict__ avg,
+                                                 const float* __restrict__ mx, const float* __restrict__ fc1, const float* __restrict__ fc2, int Cr,
+                                                 float* __restrict__ d_fc1, float* __restrict__ d_fc2, float* __restrict__ da, float* __restrict__ dmx) {
+    const int c = threadIdx.x;
+    __shared__ float a[LA_C], m[LA_C], dov[LA_C], pa[16], pm[16], dha[16], dhm[16];
+    if (c < LA_C) {
+        a[c] = avg[n * LA_C + c]; m[c] = mx[n * LA_C + c];
+        const float sv = s[n * LA_C + c];
+        dov[c] = __ldcg(ds + n * LA_C + c) * sv * (1.f - sv);
+    }
+    __syncthreads();
+    if (c < Cr) {
+        float u = 0.f, v = 0.f, d = 0.f;
+        for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * m[k]; d += fc2[k * Cr + c] * dov[k]; }
+        pa[c] = u; pm[c] = v;
+        dha[c] = u > 0.f ? d : 0.f;
+        dhm[c] = v > 0.f ? d : 0.f;
+    }
+    __syncthreads();
+    if (c < LA_C) {
+        float dav = 0.f, dmv = 0.f;
+        for (int j = 0; j < Cr; ++j) {
+            atomicAdd(d_fc2 + c * Cr + j, dov[c] * (fmaxf(pa[j], 0.f) + fmaxf(pm[j], 0.f)));
+            atomicAdd(d_fc1 + j * LA_C + c, dha[j] * a[c] + dhm[j] * m[c]);
+            dav += fc1[j * LA_C + c] * dha[j];
+            dmv += fc1[j * LA_C + c] * dhm[j];
+        }
+        da[n * LA_C + c] = dav; dmx[n * LA_C + c] = dmv;
+    }
+}
+
 // per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x
 template <typename T>
 __global__ void __launch_bounds__(256)
 la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, const unsigned char* __restrict__ cstar,
-                    const T* __restrict__ x, const float* __restrict__ s, int P, int S, T* __restrict__ dx, float* __restrict__ ds) {
+                    const T* __restrict__ x, const float* __restrict__ s, int P, int S, T* __restrict__ dx, float* __restrict__ ds,
+                    int* __restrict__ done, const float* __restrict__ avg, const float* __restrict__ mx, const float* __restrict__ fc1,
+                    const float* __restrict__ fc2, int Cr, float* __restrict__ d_fc1, float* __restrict__ d_fc2, float* __restrict__ da,
+                    float* __restrict__ dmx) {
     const int n = blockIdx.y, sl = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (P + S - 1) / S;
@@ -741,39 +779,21 @@ la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, c
         float v = 0.f;
         for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
         atomicAdd(ds + n * LA_C + threadIdx.x, v);
+        __threadfence();
+    }
+    // The LAST slice block of an image to get here finishes the image: gate backward (formerly its own launch between this
+    // kernel and la_fix_kernel).  `done` is zeroed together with ds by the caller's memset.
+    __shared__ int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(done + n, 1) == S - 1) ? 1 : 0;
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        la_gate_bwd_body(n, ds, s, avg, mx, fc1, fc2, Cr, d_fc1, d_fc2, da, dmx);
     }
 }
 // (Computing dq inside this kernel — lanes splitting the 49 taps per pixel — was measured: chain backward 79 -> 96 us; the
 // separate la_conv7_dgrad_kernel stays.)
-
-// gate backward (tiny): one block per image; weight gradients via fp32 atomics
-__global__ void __launch_bounds__(LA_C)
-la_gate_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ s, const float* __restrict__ avg, const float* __restrict__ mx,
-                   const float* __restrict__ fc1, const float* __restrict__ fc2, int N, int Cr,
-                   float* __restrict__ d_fc1, float* __restrict__ d_fc2, float* __restrict__ da, float* __restrict__ dmx) {
-    const int c = threadIdx.x, n = blockIdx.x;
-    __shared__ float a[LA_C], m[LA_C], dov[LA_C], pa[16], pm[16], dha[16], dhm[16];
-    a[c] = avg[n * LA_C + c]; m[c] = mx[n * LA_C + c];
-    const float sv = s[n * LA_C + c];
-    dov[c] = ds[n * LA_C + c] * sv * (1.f - sv);
-    __syncthreads();
-    if (c < Cr) {
-        float u = 0.f, v = 0.f, d = 0.f;
-        for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * m[k]; d += fc2[k * Cr + c] * dov[k]; }
-        pa[c] = u; pm[c] = v;
-        dha[c] = u > 0.f ? d : 0.f;
-        dhm[c] = v > 0.f ? d : 0.f;
-    }
-    __syncthreads();
-    float dav = 0.f, dmv = 0.f;
-    for (int j = 0; j < Cr; ++j) {
-        atomicAdd(d_fc2 + c * Cr + j, dov[c] * (fmaxf(pa[j], 0.f) + fmaxf(pm[j], 0.f)));
-        atomicAdd(d_fc1 + j * LA_C + c, dha[j] * a[c] + dhm[j] * m[c]);
-        dav += fc1[j * LA_C + c] * dha[j];
-        dmv += fc1[j * LA_C + c] * dhm[j];
-    }
-    da[n * LA_C + c] = dav; dmx[n * LA_C + c] = dmv;
-}
 
 // dx += da/P  (+ dmx at the arg-max pixel)
 template <typename T>
@@ -811,7 +831,7 @@ size_t la_workspace_bytes(int N, int H, int W) {
     const int P = H * W, S = la_slices(P);
     // fwd: psum, pmax, pidx ; bwd: g, dm, dq, ds, da, dmx
     size_t fwd = (size_t)N * (S > 32 ? S : 32) * LA_C * 12 + (size_t)N * 16 + 64;   // + the fused kernel's partials / barrier counters
-    size_t bwd = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + ((size_t)N * P + 4) * 8 + (size_t)N * LA_C * 12;
+    size_t bwd = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + ((size_t)N * P + 4) * 8 + (size_t)N * LA_C * 12 + ((size_t)N + 4) * 4;
     return (fwd > bwd ? fwd : bwd) + 256;
 }
 
@@ -825,15 +845,21 @@ static int la_fwd_t(const void* x, const float* t_res, const float* fc1, const f
     la_pool_partial_kernel<T><<<dim3(S, N), 256, 0, st>>>((const T*)x, P, S, psum, pmax, pidx);
     la_gate_fwd_kernel<<<N, LA_C, 0, st>>>(psum, pmax, pidx, P, S, fc1, fc2, Cr, s_out, avg_out, max_out, pstar);
     la_stats_kernel<T><<<(unsigned)cdiv(NP, 8), 256, 0, st>>>((const T*)x, s_out, P, NP, q, cstar);
-    // the SLAM gate m = sigmoid(conv7x7(q)) is computed (and stored for the backward) by the apply kernel itself
+    // The SLAM gate m = sigmoid(conv7x7(q)) is computed (and stored for the backward) by the apply kernel itself when the
+    // chain is latency bound (training maps: a launch saved, 38.9 -> 37.5 us); on large inference batches the apply kernel
+    // walks many tiles per block and the inline gate would sit on every tile's critical path (x9 tiled inference 394 -> 367
+    // Mpix/s), so there the separate kernel runs first and the apply kernel reads m.
+    const int tiles = (int)cdiv(NP, 64);
+    const bool fuse_gate = tiles <= 4 * 296;
+    if (!fuse_gate) la_conv7_fwd_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(q, w7, N, H, W, m_out);
+    const float* qg = fuse_gate ? q : nullptr;
     if (sizeof(T) == 2 && la_mma_enabled()) {
-        const int tiles = (int)cdiv(NP, 64);
-        la_apply_mma_kernel<<<tiles < 296 ? tiles : 296, 256, 0, st>>>((const __nv_bfloat16*)x, s_out, q, w7, m_out, t_res, Wm, bias, P, H, W, NP,
+        la_apply_mma_kernel<<<tiles < 296 ? tiles : 296, 256, 0, st>>>((const __nv_bfloat16*)x, s_out, qg, w7, m_out, t_res, Wm, bias, P, H, W, NP,
                                                                     tiles, z32, (__nv_bfloat16*)z16);
     } else {
-        la_apply_kernel<T><<<(unsigned)cdiv(NP, 64), 256, 0, st>>>((const T*)x, s_out, q, w7, m_out, t_res, Wm, bias, P, H, W, NP, z32, (T*)z16);
+        la_apply_kernel<T><<<(unsigned)cdiv(NP, 64), 256, 0, st>>>((const T*)x, s_out, qg, w7, m_out, t_res, Wm, bias, P, H, W, NP, z32, (T*)z16);
     }
-    count_launch(4);
+    count_launch(fuse_gate ? 4 : 5);
     return check_launch("la_chain_fwd");
 }
 
@@ -846,8 +872,10 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
     const long long NP = (long long)N * P;
     const size_t npa = ((size_t)NP + 3) & ~(size_t)3;           // keep every sub-buffer 16-byte aligned
     float* g = ws; float* dm = g + (size_t)NP * LA_C; float* dq = dm + npa; float* ds = dq + npa * 2;
-    float* da = ds + (size_t)N * LA_C; float* dmx = da + (size_t)N * LA_C;
-    cudaMemsetAsync(ds, 0, sizeof(float) * N * LA_C, st);
+    const size_t n4 = ((size_t)N + 3) & ~(size_t)3;
+    int* done = reinterpret_cast<int*>(ds + (size_t)N * LA_C);      // per-image block counters, zeroed with ds
+    float* da = ds + (size_t)N * LA_C + n4; float* dmx = da + (size_t)N * LA_C;
+    cudaMemsetAsync(ds, 0, sizeof(float) * ((size_t)N * LA_C + n4), st);
     const int tiles = (int)cdiv(NP, 64);
     const int grid = tiles < 296 ? tiles : 296;
     const size_t smem = sizeof(float) * (3 * LA_C * (LA_C + 4) + 64);
@@ -884,11 +912,11 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
         if (side_on) cudaEventRecord(ev_join, side);
     }
     la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
-    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds);
-    la_gate_bwd_kernel<<<N, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, N, Cr, d_fc1, d_fc2, da, dmx);
+    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds, done, avg, mx, fc1, fc2, Cr, d_fc1, d_fc2,
+                                                       da, dmx);
     la_fix_kernel<T><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((T*)dx, da, dmx, pstar, P, NP * LA_C);
     if (side_on) cudaStreamWaitEvent(st, ev_join, 0);
-    count_launch(6);
+    count_launch(5);
     return check_launch("la_chain_bwd");
 }
 
