@@ -358,10 +358,29 @@ int conv_tc_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* 
     // stride-2 dgrad of a 3x3 / pad-1 conv: the input pixels split into 4 parity classes (iy%2, ix%2); each
     // class is a stride-1 convolution of dy with the subset of taps whose (iy + pad - ky) is even, written
     // to every second pixel of dx (the transposed-convolution analogue of the PixelShuffle epilogue).
+    // The four class launches are independent (disjoint output pixels) and, on the small maps of the deeper layers, far
+    // too small to fill the GPU one at a time (D.8: 7 tiles per class) — classes 1..3 are forked onto internal side streams
+    // (event fork / join: stream-ordered for the caller, capturable) and run next to class 0.  SR_S2_STREAMS=0: one stream.
+    static cudaStream_t cls_stream[3] = {nullptr, nullptr, nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    static int fork_on = -1;
+    if (fork_on < 0) { const char* e = getenv("SR_S2_STREAMS"); fork_on = e ? atoi(e) : 1; }
+    if (fork_on && !ev_fork) {
+        bool ok = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 3 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&cls_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { fork_on = 0; cudaGetLastError(); }
+    }
+    if (fork_on) cudaEventRecord(ev_fork, st);
+    int cls = 0;
+    bool forked[3] = {false, false, false};
     for (int py = 0; py < 2; ++py) {
-        for (int px = 0; px < 2; ++px) {
+        for (int px = 0; px < 2; ++px, ++cls) {
             const int Hp = (d->H - py + 1) / 2, Wp = (d->W - px + 1) / 2;     // pixels of this class
             if (Hp <= 0 || Wp <= 0) continue;
+            cudaStream_t cst = st;
+            if (fork_on && cls > 0) { cst = cls_stream[cls - 1]; cudaStreamWaitEvent(cst, ev_fork, 0); forked[cls - 1] = true; }
             TcParams q = p;
             q.M_total = d->N * Hp * Wp; q.Ho = Hp; q.Wo = Wp;
             q.stride = 1; q.pad_w = 0; q.pad_h = 0;
@@ -384,11 +403,15 @@ int conv_tc_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* 
             const int upper[2] = {Wp - d->Wo, Hp - d->Ho};     // exactly Hp x Wp base positions over the Ho x Wo map
             rc = make_im2col_map(&map_a, src, d->N, Hs, Ws, Cs, lower, upper, 1, 128);
             if (rc != SR_OK) return rc;
-            rc = launch_tc(q, map_a, map_b, out_bf16, st);
-            if (rc != SR_OK) return rc;
+            rc = launch_tc(q, map_a, map_b, out_bf16, cst);
+            if (fork_on && cls > 0) cudaEventRecord(ev_join[cls - 1], cst);
+            if (rc != SR_OK) break;
         }
+        if (rc != SR_OK) break;
     }
-    return SR_OK;
+    for (int i = 0; i < 3; ++i)
+        if (forked[i]) cudaStreamWaitEvent(st, ev_join[i], 0);      // always re-join (also on the error path: a capture must not dangle)
+    return rc;
 }
 
 }  // namespace sr

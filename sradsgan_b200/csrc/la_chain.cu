@@ -61,32 +61,48 @@ la_pool_partial_kernel(const T* __restrict__ x, int P, int S, float* __restrict_
     }
 }
 
-// per image: finish the pooling, run the bias-free MLP on both pooled vectors, gate = sigmoid(sum)
-__global__ void __launch_bounds__(LA_C)
+// per image: finish the pooling, run the bias-free MLP on both pooled vectors, gate = sigmoid(sum).
+// 256 threads: four threads per channel walk the slice partials (S is up to 32), combined through shared memory.
+__global__ void __launch_bounds__(256)
 la_gate_fwd_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, const int* __restrict__ pidx, int P, int S,
                    const float* __restrict__ fc1, const float* __restrict__ fc2, int Cr,
                    float* __restrict__ s_out, float* __restrict__ avg_out, float* __restrict__ max_out, int* __restrict__ pstar) {
-    const int n = blockIdx.x, c = threadIdx.x;
+    const int n = blockIdx.x, c = threadIdx.x & (LA_C - 1), part = threadIdx.x >> 6;
     __shared__ float a[LA_C], mx[LA_C], ha[16], hm[16];
+    __shared__ float ps[4][LA_C], pm[4][LA_C];
+    __shared__ int pi[4][LA_C];
     float s = 0.f, m = -INFINITY; int idx = 0x7fffffff;
-    for (int sl = 0; sl < S; ++sl) {
+    for (int sl = part; sl < S; sl += 4) {
         const long long o = ((long long)n * S + sl) * LA_C + c;
         s += psum[o];
         const float mv = pmax[o]; const int iv = pidx[o];
         if (mv > m || (mv == m && iv < idx)) { m = mv; idx = iv; }
     }
-    a[c] = s / (float)P; mx[c] = m;
-    avg_out[n * LA_C + c] = a[c]; max_out[n * LA_C + c] = m; pstar[n * LA_C + c] = idx;
+    ps[part][c] = s; pm[part][c] = m; pi[part][c] = idx;
     __syncthreads();
-    if (c < Cr) {
-        float u = 0.f, v = 0.f;
-        for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * mx[k]; }
-        ha[c] = fmaxf(u, 0.f); hm[c] = fmaxf(v, 0.f);
+    if (part == 0) {
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            s += ps[k][c];
+            const float mv = pm[k][c]; const int iv = pi[k][c];
+            if (mv > m || (mv == m && iv < idx)) { m = mv; idx = iv; }
+        }
+        a[c] = s / (float)P; mx[c] = m;
+        avg_out[n * LA_C + c] = a[c]; max_out[n * LA_C + c] = m; pstar[n * LA_C + c] = idx;
     }
     __syncthreads();
-    float o = 0.f;
-    for (int j = 0; j < Cr; ++j) o += fc2[c * Cr + j] * (ha[j] + hm[j]);
-    s_out[n * LA_C + c] = 1.f / (1.f + __expf(-o));
+    if (threadIdx.x < Cr) {
+        const int r = threadIdx.x;
+        float u = 0.f, v = 0.f;
+        for (int k = 0; k < LA_C; ++k) { u += fc1[r * LA_C + k] * a[k]; v += fc1[r * LA_C + k] * mx[k]; }
+        ha[r] = fmaxf(u, 0.f); hm[r] = fmaxf(v, 0.f);
+    }
+    __syncthreads();
+    if (part == 0) {
+        float o = 0.f;
+        for (int j = 0; j < Cr; ++j) o += fc2[c * Cr + j] * (ha[j] + hm[j]);
+        s_out[n * LA_C + c] = 1.f / (1.f + __expf(-o));
+    }
 }
 
 // per pixel (one warp): mean / max / first arg-max over channels of u = s*x
@@ -746,6 +762,13 @@ __device__ __forceinline__ void la_gate_bwd_body(int n, const float* __restrict_
     }
 }
 
+__global__ void __launch_bounds__(LA_C)
+la_gate_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ s, const float* __restrict__ avg, const float* __restrict__ mx,
+                   const float* __restrict__ fc1, const float* __restrict__ fc2, int Cr,
+                   float* __restrict__ d_fc1, float* __restrict__ d_fc2, float* __restrict__ da, float* __restrict__ dmx) {
+    la_gate_bwd_body(blockIdx.x, ds, s, avg, mx, fc1, fc2, Cr, d_fc1, d_fc2, da, dmx);
+}
+
 // per (image, slice): du = g + dq_avg/C + dq_max*[c==c*];  dx_pre = s*du;  ds[n][c] += sum_p du*x
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -783,6 +806,7 @@ la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, c
     }
     // The LAST slice block of an image to get here finishes the image: gate backward (formerly its own launch between this
     // kernel and la_fix_kernel).  `done` is zeroed together with ds by the caller's memset.
+    if (done == nullptr) return;              // SR_LA_GATE_TAIL=0: the gate backward runs as its own kernel
     __shared__ int is_last;
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(done + n, 1) == S - 1) ? 1 : 0;
@@ -843,7 +867,7 @@ static int la_fwd_t(const void* x, const float* t_res, const float* fc1, const f
     const long long NP = (long long)N * P;
     float* psum = ws; float* pmax = psum + (size_t)N * S * LA_C; int* pidx = reinterpret_cast<int*>(pmax + (size_t)N * S * LA_C);
     la_pool_partial_kernel<T><<<dim3(S, N), 256, 0, st>>>((const T*)x, P, S, psum, pmax, pidx);
-    la_gate_fwd_kernel<<<N, LA_C, 0, st>>>(psum, pmax, pidx, P, S, fc1, fc2, Cr, s_out, avg_out, max_out, pstar);
+    la_gate_fwd_kernel<<<N, 256, 0, st>>>(psum, pmax, pidx, P, S, fc1, fc2, Cr, s_out, avg_out, max_out, pstar);
     la_stats_kernel<T><<<(unsigned)cdiv(NP, 8), 256, 0, st>>>((const T*)x, s_out, P, NP, q, cstar);
     // The SLAM gate m = sigmoid(conv7x7(q)) is computed (and stored for the backward) by the apply kernel itself when the
     // chain is latency bound (training maps: a launch saved, 38.9 -> 37.5 us); on large inference batches the apply kernel
@@ -912,8 +936,11 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
         if (side_on) cudaEventRecord(ev_join, side);
     }
     la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
-    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds, done, avg, mx, fc1, fc2, Cr, d_fc1, d_fc2,
-                                                       da, dmx);
+    static int gate_tail = -1;
+    if (gate_tail < 0) { const char* e = getenv("SR_LA_GATE_TAIL"); gate_tail = e ? atoi(e) : 1; }
+    la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds, gate_tail ? done : nullptr, avg, mx, fc1, fc2,
+                                                       Cr, d_fc1, d_fc2, da, dmx);
+    if (!gate_tail) la_gate_bwd_kernel<<<N, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, Cr, d_fc1, d_fc2, da, dmx);
     la_fix_kernel<T><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((T*)dx, da, dmx, pstar, P, NP * LA_C);
     if (side_on) cudaStreamWaitEvent(st, ev_join, 0);
     count_launch(5);
