@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from .. import _lib, dp, ops
 from ..optim import FlatAdam
-from ..utils import CsvLogger, psnr, save_img1, weights_init_normal
+from ..utils import CsvLogger, ergas_batch, psnr, psnr_batch, save_img1, weights_init_normal
 
 
 class SRADSGAN(object):
@@ -410,8 +410,8 @@ class SRADSGAN(object):
 
     @torch.no_grad()
     def validate(self, epoch=0, mode='test', save_img=False):
-        """PSNR on the test set (SSIM / ERGAS / LPIPS need skimage/sewar/AlexNet weights, absent offline:
-        returned as 0). Returns (psnr, ssim, ergas, lpips) like the reference."""
+        """PSNR and ERGAS on the test set, computed on the device (SSIM / LPIPS need skimage / AlexNet weights, absent
+        offline: returned as 0). Returns (psnr, ssim, ergas, lpips) like the reference."""
         if self.generator is None:
             self.build(init=False)
             self.load_model()
@@ -419,11 +419,15 @@ class SRADSGAN(object):
         if loader is None:
             return 0.0, 0.0, 0.0, 0.0
         self.generator.eval()
-        vals = []
-        for batch in loader:
-            rec = self.generator(batch[0].to(self.device)).float().cpu()
-            vals += [psnr(rec[j], batch[1][j]) for j in range(rec.shape[0])]
-        return (float(np.mean(vals)) if vals else 0.0), 0.0, 0.0, 0.0
+        vals, ergs = [], []
+        for batch in loader:                      # metrics stay on the device; ONE read-back after the loop
+            rec = self.generator(batch[0].to(self.device, non_blocking=True)).float()
+            gt = batch[1].to(self.device, non_blocking=True)
+            vals.append(psnr_batch(rec, gt))
+            ergs.append(ergas_batch(rec, gt, self.scale_factor))
+        if not vals:
+            return 0.0, 0.0, 0.0, 0.0
+        return float(torch.cat(vals).mean().item()), 0.0, float(torch.cat(ergs).mean().item()), 0.0
 
     def mfeNew_validate(self, epoch=100, modelpath=None):
         self.build(init=False)

@@ -27,9 +27,29 @@ def psnr(pred, gt):
     return 100 if mse == 0 else 10 * log10(1.0 / mse)
 
 
+def psnr_batch(pred, gt):
+    """per-image `psnr` of a batch, computed where the tensors live (validation keeps the images on the
+    GPU and reads back ONE small tensor at the end instead of round-tripping every image through the host).
+    Returns a float64 tensor of shape (B,); identical values to `psnr` image by image (100 where the MSE is zero)."""
+    diff = pred.clamp(0, 1).double() - gt.clamp(0, 1).double()
+    mse = (diff * diff).flatten(1).mean(dim=1)
+    return torch.where(mse == 0, torch.full_like(mse, 100.0), 10.0 * torch.log10(1.0 / mse.clamp_min(1e-300)))
+
+
+def ergas_batch(pred, gt, scale=4):
+    """reference utils/utils.py:954-962 (`compare_ergas2`, the variant the trainer logs) on [0,255]-quantised images, per
+    image, on the device: 100 * sqrt(mse / mean(img1)^2 / channels) / scale with img1 = ground truth."""
+    a = (gt * 255.0).clamp(0, 255).floor().double()
+    b = (pred * 255.0).clamp(0, 255).floor().double()
+    mse = ((a - b) ** 2).flatten(1).mean(dim=1)
+    mean2 = a.flatten(1).mean(dim=1) ** 2
+    return 100.0 * torch.sqrt(mse / mean2.clamp_min(1e-300) / pred.shape[1]) / scale
+
+
 def quantize_u8(img):
-    """reference utils/utils.py:169-175: img*255, clamp to [0,255], astype(uint8) (truncation), CHW -> HWC"""
-    return (img * 255.0).clamp(0, 255).detach().cpu().numpy().transpose(1, 2, 0).astype(np.uint8)
+    """reference utils/utils.py:169-175: img*255, clamp to [0,255], astype(uint8) (truncation), CHW -> HWC.
+    The quantisation runs where the tensor lives; only the uint8 image crosses to the host."""
+    return (img.detach() * 255.0).clamp(0, 255).to(torch.uint8).permute(1, 2, 0).contiguous().cpu().numpy()
 
 
 def save_img1(img, save_dir, img_path, cuda=True):

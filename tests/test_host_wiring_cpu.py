@@ -147,3 +147,23 @@ def test_train_step_matches_oracle_and_golden(emu, golden, fuse):
             if k in O.NOISE_GRAD_KEYS:
                 continue
             assert abs(summarize(dsd[k].float(), 8)["norm"] - w["norm"]) <= 2e-3 * max(1e-6, w["norm"]), (it, k)
+
+
+def test_device_side_metrics_match_the_reference_definitions():
+    """utils.psnr_batch / ergas_batch / quantize_u8 == the per-image host definitions of the reference
+    (utils/utils.py:700-709 PSNR, :954-962 compare_ergas2 on the uint8 images, :169-175 save_img1 truncation)."""
+    from sradsgan_b200 import utils as U
+    g = torch.Generator().manual_seed(5)
+    gt = torch.rand(3, 3, 20, 24, generator=g)
+    pred = gt + 0.05 * torch.randn(3, 3, 20, 24, generator=g)
+    pred[2] = gt[2]                                            # zero-MSE image -> 100 dB
+    got = U.psnr_batch(pred, gt)
+    for j in range(3):
+        assert abs(got[j].item() - O.psnr(pred[j], gt[j])) < 1e-9
+        assert abs(got[j].item() - U.psnr(pred[j], gt[j])) < 1e-9
+    e = U.ergas_batch(pred, gt, scale=4)
+    for j in range(3):
+        a = O.quantize_u8(gt[j]).astype(np.float64); b = O.quantize_u8(pred[j]).astype(np.float64)
+        want = 100.0 * np.sqrt(np.mean((a - b) ** 2) / np.mean(a) ** 2 / 3) / 4
+        assert abs(e[j].item() - want) < 1e-9 * max(1.0, want)
+        assert np.array_equal(U.quantize_u8(pred[j]), O.quantize_u8(pred[j]))
