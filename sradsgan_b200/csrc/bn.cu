@@ -13,8 +13,6 @@
 
 namespace sr {
 
-int colsum(const void* x, int dtype, long long rows, int C, float* sum, float* sq, int accumulate, cudaStream_t st);   // elementwise.cu
-
 // block = 32 channels x 8 row-lanes; shifted by the first row (pivot) to avoid E[x^2]-E[x]^2 cancellation
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -157,45 +155,6 @@ bn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long
     }
 }
 
-// vectorised variant for C in {64, 128, 256, 512}: thread = 4 consecutive channels of a row (one 8 / 16 byte load per tensor),
-// the rows of a block iteration share the channels' coefficients held in registers; rows meet in shared memory, then one
-// atomic pair per channel (the lane-per-channel kernel above reads 2-byte elements, 64 B per warp and row)
-template <typename T>
-__global__ void __launch_bounds__(256)
-bn_bwd_reduce_vec_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long rows, int C, const float* __restrict__ scale,
-                         const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd, float slope,
-                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    __shared__ float red[2][256][4];
-    const int tpr = C >> 2, rpb = 256 / tpr;
-    const int tr = threadIdx.x / tpr, tc = (threadIdx.x - tr * tpr) * 4;
-    float sc[4], sh[4], mu[4], rs[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { sc[k] = scale[tc + k]; sh[k] = shift[tc + k]; mu[k] = mean[tc + k]; rs[k] = rstd[tc + k]; }
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long r = (long long)blockIdx.x * rpb + tr; r < rows; r += (long long)gridDim.x * rpb) {
-        float xv[4], g[4];
-        load4<T>(x + r * C + tc, xv);
-        load4<T>(gy + r * C + tc, g);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!(xv[k] * sc[k] + sh[k] > 0.f)) g[k] *= slope;
-            a[k] += g[k]; b[k] += g[k] * (xv[k] - mu[k]) * rs[k];
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { red[0][threadIdx.x][k] = a[k]; red[1][threadIdx.x][k] = b[k]; }
-    __syncthreads();
-    if (threadIdx.x < tpr) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float s = 0.f, q = 0.f;
-            for (int i = 0; i < rpb; ++i) { s += red[0][i * tpr + threadIdx.x][k]; q += red[1][i * tpr + threadIdx.x][k]; }
-            atomicAdd(dbeta + tc + k, s);
-            atomicAdd(dgamma + tc + k, q);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Double backward (WGAN-GP: d/d(gy, x, gamma) of <u, dx> where dx = bn_act_bwd(gy, x, gamma), reference
 // model/sradsgan.py:621 create_graph=True + :639/:886).  With N rows per channel, r = rstd, xh = (x-mean) r,
@@ -313,11 +272,6 @@ static int bn_fwd_t(const void* x, long long rows, int C, const float* gamma, co
     cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, st);
     const int cy = (int)cdiv(C, 32);
     long long bx = std::min<long long>(cdiv(148 * 8, cy), cdiv(rows, 8));
-    if (C == 64 || C == 128 || C == 256 || C == 512) {
-        const int rc = colsum(x, sizeof(T) == 2 ? SR_BF16 : SR_F32, rows, C, sum, sq, 1, st);      // vectorised sum / sum of squares (elementwise.cu)
-        if (rc != SR_OK) return rc;
-        count_launch(-1);                                                                          // counted there; keep "3 per forward"
-    } else
     bn_stats_kernel<T><<<dim3((unsigned)bx, (unsigned)cy), 256, 0, st>>>((const T*)x, rows, C, sum, sq);
     bn_finalize_kernel<T><<<(unsigned)cdiv(C, 128), 128, 0, st>>>((const T*)x, sum, sq, rows, C, gamma, beta, eps, momentum, rm, rv,
                                                                   save, save + C, save + 2 * C, save + 3 * C);
@@ -339,10 +293,6 @@ static int bn_bwd_t(const void* gy, const void* x, long long rows, int C, const 
     cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
     const int cy = (int)cdiv(C, 32);
     long long bx = std::min<long long>(cdiv(148 * 8, cy), cdiv(rows, 8));
-    if (C == 64 || C == 128 || C == 256 || C == 512) {
-        const unsigned vb = (unsigned)std::min<long long>(148 * 4, cdiv(rows, (long long)(1024 / C) * 4));
-        bn_bwd_reduce_vec_kernel<T><<<vb, 256, 0, st>>>((const T*)gy, (const T*)x, rows, C, scale, shift, mean, rstd, slope, dgamma, dbeta);
-    } else
     bn_bwd_reduce_kernel<T><<<dim3((unsigned)bx, (unsigned)cy), 256, 0, st>>>((const T*)gy, (const T*)x, rows, C, scale, shift, mean, rstd,
                                                                               slope, dgamma, dbeta);
     const long long total = rows * C;
