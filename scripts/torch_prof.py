@@ -63,3 +63,13 @@ for ph in names[1:] + ["end", "?"]:
     print("== %-18s total %8.2f ms | sr:: %8.2f ms | other %8.2f ms | launches %d" % (ph, tot / 1e3, ours / 1e3, (tot - ours) / 1e3, sum(v[0] for v in agg[ph].values())))
     for k, v in sorted(agg[ph].items(), key=lambda kv: -kv[1][1])[:24]:
         print("      %-100s %5d %9.3f ms" % (k, v[0], v[1] / 1e3))
+# whole-step table of everything that is NOT a library kernel, by (op, shapes)
+tot = collections.defaultdict(lambda: [0, 0.0])
+for ph in agg:
+    for k, v in agg[ph].items():
+        if not k.startswith("sr::"):
+            key = ph + " | " + k
+            tot[key][0] += v[0]; tot[key][1] += v[1]
+print("== non-library kernels of the whole step, by phase/op/shape (top 90 by launches)")
+for k, v in sorted(tot.items(), key=lambda kv: (-kv[1][0], -kv[1][1]))[:90]:
+    print("      %-125s %5d %9.3f ms" % (k[:125], v[0], v[1] / 1e3))
