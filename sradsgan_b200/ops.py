@@ -58,7 +58,9 @@ class _WgradStream:
     all-reduce — makes the main stream wait for them.  Works the same under CUDA-graph capture (a forked branch of the graph).
     The operands are kept referenced until the join, so the caching allocator cannot hand their memory to main-stream work."""
     enabled = os.environ.get("SR_WGRAD_ASYNC", "1") == "1"
+    two_streams = os.environ.get("SR_WGRAD_STREAMS", "2") == "2"
     stream = None
+    stream2 = None
     keep = []
 
 
@@ -71,7 +73,10 @@ def side_stream(device):
 
 def wgrad_join():
     if _WgradStream.keep:
-        torch.cuda.current_stream().wait_stream(_WgradStream.stream)
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(_WgradStream.stream)
+        if _WgradStream.stream2 is not None:
+            cur.wait_stream(_WgradStream.stream2)
         _WgradStream.keep.clear()
 
 
@@ -82,8 +87,15 @@ def _wgrad_into(x, gy, g, tw, tb):
         return
     ws = _WgradStream
     side_stream(x.device)
-    ws.stream.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(ws.stream):
+    st = ws.stream
+    if (g.Cin <= 4 or g.Cout <= 4) and ws.two_streams:
+        # thin layers (RGB input, 1-channel critic map) run direct / SIMT kernels that do not touch the split-K workspace:
+        # they get their own stream and overlap with the tensor-core weight gradients of the other layers
+        if ws.stream2 is None or ws.stream2.device != x.device:
+            ws.stream2 = torch.cuda.Stream(device=x.device)
+        st = ws.stream2
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
         be.conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
     ws.keep.append((x, gy))
 
