@@ -62,6 +62,7 @@ class _WgradStream:
     stream = None
     stream2 = None
     keep = []
+    pending = []
 
 
 def side_stream(device):
@@ -72,12 +73,13 @@ def side_stream(device):
 
 
 def wgrad_join():
-    if _WgradStream.keep:
+    ws = _WgradStream
+    if ws.keep:
         cur = torch.cuda.current_stream()
-        cur.wait_stream(_WgradStream.stream)
-        if _WgradStream.stream2 is not None:
-            cur.wait_stream(_WgradStream.stream2)
-        _WgradStream.keep.clear()
+        for st in ws.pending:          # only streams that received work since the last join (a stream that is not part of
+            cur.wait_stream(st)        # the running graph capture must not be waited on)
+        ws.pending.clear()
+        ws.keep.clear()
 
 
 def _wgrad_into(x, gy, g, tw, tb):
@@ -98,6 +100,8 @@ def _wgrad_into(x, gy, g, tw, tb):
     with torch.cuda.stream(st):
         be.conv_wgrad_into(x, gy, g, tw, tb, impl=config.conv_impl)
     ws.keep.append((x, gy))
+    if st not in ws.pending:
+        ws.pending.append(st)
 
 
 def _wgrad(x, gy, g, w, b, has_bias, need_w, need_b):
