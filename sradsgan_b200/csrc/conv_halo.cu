@@ -16,6 +16,7 @@
 // Warp roles, TMEM double buffering and the epilogue are those of conv_tc.cu.
 // Reference call sites: the 3x3 stride-1 nn.Conv2d layers of model/sradsgan.py (RAB :222-223, GAB_UP :381,
 // Discriminator :476 odd blocks, VGG19 features) and their input gradients.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -33,6 +34,7 @@ struct HaloParams {
     int a_stage_bytes, a_box_bytes, num_a_stages, num_b_stages, resident;
     int dual;                        // 1: two MMA-issuer warps work on two pixel tiles at once (shared weights)
     int n_pair_items, n_items;       // per CTA lane: items [0, n_pair_items) are tile pairs, the rest single tiles
+    int split_ok;                    // dual + streamed weights + >= 2 channel blocks: a SINGLE tile is split along K between the two issuers
     const float* bias;
     const void* residual;
     const void* mask;                // nullable bf16 tensor shaped like the output: out *= act'(mask)
@@ -74,6 +76,9 @@ __device__ __forceinline__ void hl_tile_origin(const HaloParams& p, int p_tile, 
 
 // Epilogue warp.  dual: serves issuer `grp` (its own double-buffered accumulators), all 32-column chunks.
 // single: both groups serve the one issuer, chunk parity = grp.
+// split (dual, a single tile whose channel blocks were divided between the two issuers): both groups wait for BOTH
+// accumulators, group g sums and stores the chunks of parity g, and after a barrier among the eight epilogue warps group g
+// releases issuer g's buffer.  Every warp tracks both issuers' buffer indices so the three item kinds can interleave.
 template <typename OutT, int ACT>
 __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
                                             const float* bias_s, int quarter, int grp, int lane) {
@@ -83,66 +88,93 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
     const int r = p.shuffle_r > 1 ? p.shuffle_r : 1;
     const int cq = p.Cout / (r * r);
     const int chunks = p.block_n >> 5;
-    const int c_first = p.dual ? 0 : grp, c_step = p.dual ? 1 : 2;
     const int acc_stride = p.dual ? 128 : 256;
-    const int bar0 = p.dual ? grp * 2 : 0;       // this warp's pair of accumulator barriers / TMEM buffers
     OutT* out = reinterpret_cast<OutT*>(p.out);
     const OutT* res = reinterpret_cast<const OutT*>(p.residual);
     const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(p.mask);
-    int acc = 0; uint32_t acc_phase = 0;
+    int accs[2] = {0, 0}; uint32_t phs[2] = {0, 0};
+    auto advance = [&](int w) { if (++accs[w] == 2) { accs[w] = 0; phs[w] ^= 1; } };
     int t0, t1, nb;
     for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
-        const int p_tile = (p.dual && grp == 1) ? t1 : t0;
-        if (p_tile < 0) continue;
-        int n, y0, x0;
-        hl_tile_origin(p, p_tile, n, y0, x0);
-        const int oy = y0 + tr, ox = x0 + cp - 1;
-        const bool valid = tr < p.TR && cp >= 1 && cp <= p.TW && oy < p.H && ox < p.W;
-        const long long row_idx = (((long long)n * p.H + oy) * p.W + ox) * p.Cout;
-        mbar_wait(acc_full + bar0 + acc, acc_phase);
-        tc_fence_after();
-        const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((bar0 + acc) * acc_stride);
-        auto emit = [&](const uint32_t (&v)[32], int c) {
-            if (!valid) return;
-            if (p.narrow) {              // thin output (RGB / 1-channel critic map): only the first Cout accumulator columns are real
-                if (c == 0) {
-                    OutT* o = out + ((((long long)n * p.H + oy) * p.W) + ox) * p.Cout;
+        const bool split = p.split_ok && t1 < 0;
+        const int own = p.dual ? grp : 0;        // issuer whose buffer this group reads (and releases)
+        const int p_tile = split ? t0 : ((p.dual && grp == 1) ? t1 : t0);
+        if (p_tile >= 0) {
+            int n, y0, x0;
+            hl_tile_origin(p, p_tile, n, y0, x0);
+            const int oy = y0 + tr, ox = x0 + cp - 1;
+            const bool valid = tr < p.TR && cp >= 1 && cp <= p.TW && oy < p.H && ox < p.W;
+            const long long row_idx = (((long long)n * p.H + oy) * p.W + ox) * p.Cout;
+            auto emit = [&](const uint32_t (&v)[32], int c) {
+                if (!valid) return;
+                if (p.narrow) {              // thin output (RGB / 1-channel critic map): only the first Cout accumulator columns are real
+                    if (c == 0) {
+                        OutT* o = out + ((((long long)n * p.H + oy) * p.W) + ox) * p.Cout;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < p.Cout) o[j] = from_f32<OutT>(tc_act<ACT>(__uint_as_float(v[j]) + bias_s[j], p.slope));
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (jj < p.Cout) o[jj] = from_f32<OutT>(tc_act<ACT>(__uint_as_float(v[jj]) + bias_s[jj], p.slope));
+                    }
+                    return;
                 }
-                return;
-            }
-            const int col = nb * p.block_n + c * 32;
-            long long idx;
-            if (r > 1) {
-                const int sub = col / cq, ch0 = col - sub * cq;
-                const int si = sub / r, sj = sub - si * r;
-                idx = ((((long long)n * p.H * r + (oy * r + si)) * ((long long)p.W * r)) + (ox * r + sj)) * cq + ch0;
+                const int col = nb * p.block_n + c * 32;
+                long long idx;
+                if (r > 1) {
+                    const int sub = col / cq, ch0 = col - sub * cq;
+                    const int si = sub / r, sj = sub - si * r;
+                    idx = ((((long long)n * p.H * r + (oy * r + si)) * ((long long)p.W * r)) + (ox * r + sj)) * cq + ch0;
+                } else {
+                    idx = row_idx + col;
+                }
+                tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx,
+                                          mask ? mask + idx : nullptr, p.mask_slope);
+            };
+            uint32_t va[32], vb[32];
+            if (split) {
+                mbar_wait(acc_full + accs[0], phs[0]);
+                mbar_wait(acc_full + 2 + accs[1], phs[1]);
+                tc_fence_after();
+                const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+                const uint32_t base0 = lane_base + (uint32_t)(accs[0] * acc_stride), base1 = lane_base + (uint32_t)((2 + accs[1]) * acc_stride);
+                for (int c = grp; c < chunks; c += 2) {
+                    tmem_ld32_nowait(base0 + (uint32_t)(c * 32), va);
+                    tmem_ld32_nowait(base1 + (uint32_t)(c * 32), vb);
+                    tmem_ld_wait(va);
+                    tmem_ld_wait(vb);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) va[k] = __float_as_uint(__uint_as_float(va[k]) + __uint_as_float(vb[k]));
+                    emit(va, c);
+                }
+                tc_fence_before();
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // both groups are done reading both buffers
+                if (lane == 0) mbar_arrive(acc_empty + grp * 2 + accs[grp]);
             } else {
-                idx = row_idx + col;
+                const int c_first = p.dual ? 0 : grp, c_step = p.dual ? 1 : 2;
+                const int buf = own * 2 + accs[own];
+                mbar_wait(acc_full + buf, phs[own]);
+                tc_fence_after();
+                const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * acc_stride);
+                int c = c_first;
+                if (c < chunks) tmem_ld32_nowait(t_base + (uint32_t)(c * 32), va);
+                while (c < chunks) {
+                    tmem_ld_wait(va);
+                    if (c + c_step < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + c_step) * 32), vb);
+                    emit(va, c);
+                    c += c_step;
+                    if (c >= chunks) break;
+                    tmem_ld_wait(vb);
+                    if (c + c_step < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + c_step) * 32), va);
+                    emit(vb, c);
+                    c += c_step;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + buf);
             }
-            tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx,
-                                      mask ? mask + idx : nullptr, p.mask_slope);
-        };
-        uint32_t va[32], vb[32];
-        int c = c_first;
-        if (c < chunks) tmem_ld32_nowait(t_base + (uint32_t)(c * 32), va);
-        while (c < chunks) {
-            tmem_ld_wait(va);
-            if (c + c_step < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + c_step) * 32), vb);
-            emit(va, c);
-            c += c_step;
-            if (c >= chunks) break;
-            tmem_ld_wait(vb);
-            if (c + c_step < chunks) tmem_ld32_nowait(t_base + (uint32_t)((c + c_step) * 32), va);
-            emit(vb, c);
-            c += c_step;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + bar0 + acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // buffer bookkeeping of BOTH issuers (identical in every epilogue warp)
+        if (!p.dual) { advance(0); }
+        else if (split) { advance(0); advance(1); }
+        else { if (t0 >= 0) advance(0); if (t1 >= 0) advance(1); }
     }
 }
 
@@ -202,9 +234,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int sb = 0; uint32_t pb = 0;
             int t0, t1, nb;
             for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
+                const bool split = p.split_ok && t1 < 0;
                 for (int cb = 0; cb < p.c_blocks; ++cb) {
                     for (int w = 0; w < issuers; ++w) {
-                        const int tile = w ? t1 : t0;
+                        const int tile = split ? ((cb & 1) == w ? t0 : -1) : (w ? t1 : t0);     // split: channel block cb belongs to issuer cb & 1
                         if (tile < 0) continue;
                         int n, y0, x0;
                         hl_tile_origin(p, tile, n, y0, x0);
@@ -253,7 +286,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             bool res_ready = false;
             int t0, t1, nb;
             for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
-                const bool has = (w ? t1 : t0) >= 0;
+                const bool split = p.split_ok && t1 < 0;
+                const bool has = split || (w ? t1 : t0) >= 0;
+                bool first = true;            // first MMA group of this issuer in this item overwrites the accumulator
                 uint32_t d_tmem = 0;
                 if (has) {
                     mbar_wait(acc_empty + w * 2 + acc, acc_phase ^ 1);
@@ -263,7 +298,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int cb = 0; cb < p.c_blocks; ++cb) {
                     uint64_t adesc0 = 0;
                     const int st = w * ring_a + sa;
-                    if (has) {
+                    const bool mine = split ? ((cb & 1) == w) : has;       // this issuer multiplies channel block cb
+                    if (mine) {
                         mbar_wait(a_full + st, pa);
                         adesc0 = make_kmajor_sw128_desc(smem_u32(a_base + (size_t)st * p.a_stage_bytes));
                     }
@@ -294,17 +330,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             mbar_wait(b_full + sb, pb);
                             tc_fence_after();
                             if (lane == 0) {
-                                if (has) {
+                                if (mine) {
                                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)sb * b_bytes));
-                                    umma_f16_x4(d_tmem, adesc0 + tap_off[tap], bdesc, idesc, (cb | tap) ? 1u : 0u);
+                                    umma_f16_x4(d_tmem, adesc0 + tap_off[tap], bdesc, idesc, first ? 0u : 1u);
                                 }
                                 umma_commit(b_empty + sb);      // both issuers release every weight stage (count = issuers)
                             }
+                            if (mine) first = false;
                             __syncwarp();
                             if (++sb == p.num_b_stages) { sb = 0; pb ^= 1; }
                         }
                     }
-                    if (has) {
+                    if (mine) {
                         if (lane == 0) umma_commit(a_empty + st);
                         __syncwarp();
                         if (++sa == ring_a) { sa = 0; pa ^= 1; }
@@ -421,6 +458,9 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
         p.n_pair_items = 0;
         p.n_items = resident ? p.p_tiles : p.p_tiles * p.n_blocks;
     }
+    static int splitk = -1;
+    if (splitk < 0) { const char* e = getenv("SR_HALO_SPLITK"); splitk = e ? atoi(e) : 1; }
+    p.split_ok = (splitk && p.dual && !resident && p.c_blocks >= 2) ? 1 : 0;
     const int total_items = resident ? p.n_items * p.n_blocks : p.n_items;
     if (total_items < grid) { grid = total_items; if (resident) grid -= grid % p.n_blocks; }
     if (grid < 1) grid = p.n_blocks;
