@@ -110,7 +110,7 @@ def cpu_reference_step(batch, steps, warmup):
                       "%.2f s/step" % (steps, batch, BATCH, cores, mean)}, mean
 
 
-def inference_bench(size, scale=9, tile=128, overlap=16, tile_batch=8):
+def inference_bench(size, scale=9, tile=128, overlap=16, tile_batch=32):
     """Second half of BASELINE.json's metric: x9 generator inference on a synthetic size^2 LR tile (configs[3]) through
     overlapped tiling (the reference cannot run this: SGAM materialises an (HW)^2 attention).  Input resident on
     the device; output Mpix/s = (size*scale)^2 / time of one full pass (one warm-up pass over 2 tile batches)."""

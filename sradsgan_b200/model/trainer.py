@@ -560,7 +560,7 @@ def tile_starts(size, tile, overlap):
 
 
 @torch.no_grad()
-def tiled_forward(generator, lr, scale, tile, overlap=16, tile_batch=8):
+def tiled_forward(generator, lr, scale, tile, overlap=16, tile_batch=32):
     """Overlapped-tile inference (new): LR tiles of `tile`^2 with `overlap` LR pixels of
     overlap, feathered (linear ramp) blending of the SR tiles.  Parity is defined per tile: each tile's
     output equals the generator run on that tile alone.  Tiles (all the same shape) go through the generator
