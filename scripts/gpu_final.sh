@@ -23,3 +23,4 @@ PY
 timeout -s KILL 300 python scripts/conv_bench.py > $OUT/conv_bench.txt 2>&1
 timeout -s KILL 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python scripts/profile_step.py > $OUT/ncu_step.log 2>&1
 python scripts/summarize_launches.py $OUT/launches.csv 60 > $OUT/launches_summary.txt 2>&1
+timeout -s KILL 300 python scripts/infer_sweep.py > $OUT/infer_sweep.txt 2>&1; grep tile $OUT/infer_sweep.txt | tee -a $OUT/summary.txt
