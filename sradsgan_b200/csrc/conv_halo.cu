@@ -447,6 +447,9 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     }
     p.resident = resident ? 1 : 0;
     p.dual = (bn <= 128 && (resident || p.n_blocks == 1)) ? 1 : 0;
+    static int nodual_res = -1;             // experiment knob: resident-weights layers on ONE issuer with a two-deep activation ring
+    if (nodual_res < 0) { const char* e = getenv("SR_HALO_NODUAL_RES"); nodual_res = e ? atoi(e) : 0; }
+    if (nodual_res && resident) p.dual = 0;
     const int lane_ctas = resident ? grid / p.n_blocks : grid;
     if (p.dual) {
         const int pairs_total = p.p_tiles / 2;
