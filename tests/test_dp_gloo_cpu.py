@@ -93,3 +93,58 @@ def test_two_rank_gradient_allreduce_and_replica_consistency(overlap):
         assert init_diff == 0.0                        # rank 0's initial weights were broadcast
         assert replica_diff == 0.0                     # identical updates on both ranks
         assert moved > 0                               # and the step did change the weights
+
+
+def _edsr_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import edsr_oracle as E, ops_emu
+        from sradsgan_b200 import _lib, ops
+        from sradsgan_b200.model.edsr import EDSR
+        _lib.set_backend(ops_emu.EmuBackend())
+        ops.set_precision("fp32")
+        net = EDSR(_args(model_name="EDSR", lr=1e-4))
+        net.num_residuals = 1
+        net.seed = 200 + rank                     # different initial weights per rank: build() must broadcast rank 0's
+        net.build(init=True)
+        p0 = net.optimizer_G.flat_param.clone()
+        lr, hr = E.synthetic_batch(2, 4, 32, seed=17 + rank)
+        net._g_phase(lr, hr)
+        local = net.optimizer_G.flat_grad.clone()
+        scale = net.reducer_G.finish()
+        reduced = net.optimizer_G.flat_grad.clone() * scale
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        mean = sum(gathered) / world
+        err = ((reduced - mean).norm() / mean.norm()).item()
+        net.train_step(lr, hr)
+        flat = net.optimizer_G.flat_param
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        init = [torch.empty_like(p0) for _ in range(world)]
+        dist.all_gather(init, p0)
+        q.put((rank, err, (both[0] - both[1]).abs().max().item(), (init[0] - init[1]).abs().max().item(), (flat - p0).abs().max().item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_edsr_two_rank_gradient_allreduce_and_replica_consistency():
+    """the same data-parallel plumbing under the EDSR trainer (one network, one bucket)"""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_edsr_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, replica_diff, init_diff, moved in res:
+        assert err < 1e-5, (rank, err)
+        assert init_diff == 0.0 and replica_diff == 0.0 and moved > 0
