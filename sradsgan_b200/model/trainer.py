@@ -41,6 +41,7 @@ class SRADSGAN(object):
         self.log_interval = getattr(args, "log_interval", 50)
         self.vgg_state = getattr(args, "vgg_state", None)
         self.seed = getattr(args, "seed", 0)
+        self.gpu_input_pipeline = getattr(args, "gpu_input_pipeline", False)
         # chain training (the paper's x2 -> x3 -> x4 ... warm starts; reference :716-721 does it by hand-editing two paths)
         self.pretrained_G = getattr(args, "pretrained_G", None)
         self.pretrained_D = getattr(args, "pretrained_D", None)
@@ -319,16 +320,21 @@ class SRADSGAN(object):
     def load_dataset(self, dataset='train', max_samples=20000):
         """reference :643-656. Folder datasets are outside the hot path: a synthetic source
         is used when `synthetic_steps` > 0, otherwise a minimal PIL folder reader."""
-        from ..data import FolderSRDataset, SyntheticSRDataset
+        from ..data import DevicePrefetcher, FolderHRDataset, FolderSRDataset, SyntheticSRDataset
         bs = self.batch_size if dataset == 'train' else self.test_batch_size
+        device_pipeline = getattr(self, "gpu_input_pipeline", False) and not self.synthetic_steps
         if self.synthetic_steps:
             ds = SyntheticSRDataset(self.synthetic_steps * bs, self.crop_size, self.scale_factor, seed=1234 + _rank())
         else:
             names = self.train_dataset if dataset == 'train' else self.test_dataset
-            ds = FolderSRDataset(self.data_dir, names, self.crop_size, self.scale_factor, max_samples=max_samples)
-        return torch.utils.data.DataLoader(ds, num_workers=0 if self.synthetic_steps else self.num_threads, batch_size=bs,
-                                           shuffle=(dataset == 'train' and not self.synthetic_steps), drop_last=True,
-                                           pin_memory=True)
+            cls = FolderHRDataset if device_pipeline else FolderSRDataset
+            ds = cls(self.data_dir, names, self.crop_size, self.scale_factor, max_samples=max_samples)
+        loader = torch.utils.data.DataLoader(ds, num_workers=0 if self.synthetic_steps else self.num_threads, batch_size=bs,
+                                             shuffle=(dataset == 'train' and not self.synthetic_steps), drop_last=True,
+                                             pin_memory=True)
+        # --gpu_input_pipeline: workers only decode + crop; LR / bicubic synthesis (PIL-exact) and the copies run on the device,
+        # double-buffered behind the training step (SURVEY.md §8 f3)
+        return DevicePrefetcher(loader, self.device, self.scale_factor) if device_pipeline else loader
 
     # ------------------------------------------------------------------------------------------
     # training loop (reference :658-1056)
