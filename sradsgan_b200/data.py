@@ -83,7 +83,8 @@ def synthesize_lr_bc(hr_u8, scale):
     h, w = hr.shape[-2:]
     lr = pil_bicubic(hr, h // scale, w // scale)
     bc = pil_bicubic(lr, h, w)
-    return lr / 255.0, hr / 255.0, bc / 255.0
+    d = hr.new_full((1,), 255.0)      # tensor / tensor: IEEE division like `to_tensor` on the host (a Python-scalar divisor is turned
+    return lr / d, hr / d, bc / d      # into a multiplication by the reciprocal on CUDA: 1 ulp off)
 
 
 class FolderHRDataset(FolderSRDataset):
