@@ -58,6 +58,7 @@ class SRADSGAN(object):
         self.optimizer_G = self.optimizer_D = None
         self._alpha_override = None
         self._graph = None
+        self._pack_plans = None          # ops.PackPlan per network, built by _capture (batched weight re-packing)
 
     # ------------------------------------------------------------------------------------------
     # construction
