@@ -326,19 +326,21 @@ def main():
                 "measured": "CUDA events around each launch of this kernel class on the launching stream, one eagerly launched step",
                 "step_frac_of_tensor_roofline": (FLOP_PER_IMG * B * K / (ms * 1e-3) / 1e12) / peak_tf}
 
+    # the sub-lines (second half of the metric, second workload, CPU baseline) are single-GPU measurements: N = 1 only.
+    # (At N > 1 the other ranks have left by now: a trainer built here must not enter a collective.)
     infer = None
-    if not args.no_inference:
+    if not args.no_inference and world == 1:
         infer = inference_bench(args.infer_size)
 
     edsr = None
-    if not args.no_edsr:
+    if not args.no_edsr and world == 1:
         try:
             edsr = edsr_bench(B, 5, 3, peak_tf)
         except Exception as e:      # the second workload must never take the headline number down with it
             edsr = {"error": "%s: %s" % (type(e).__name__, e)}
 
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_reference_step(batch=2, steps=1, warmup=0)
 
     imgs = B * world * K
