@@ -15,7 +15,6 @@ import os
 import time
 from collections import OrderedDict
 
-import numpy as np
 import torch
 import torch.nn as nn
 

@@ -11,7 +11,6 @@ What is deliberately not reproduced because it changes no result: D / VGG weight
 step (zeroed / never used, :865), the second traversal of the GP double-backward graph (the two
 backward passes are fused into one with weight 1+lambda), per-iteration `.item()` syncs and empty_cache().
 """
-import math
 import os
 import time
 from collections import OrderedDict

@@ -3,7 +3,6 @@ import os
 import time
 from math import log10
 
-import numpy as np
 import torch
 
 
