@@ -59,6 +59,7 @@ def parse_args(argv=None):
     parser.add_argument('--gpu_input_pipeline', action='store_true', help='decode+crop on the workers, PIL-exact bicubic LR synthesis and copies on the device')
     parser.add_argument('--pretrained_G', type=str, default=None, help='generator state_dict to warm-start from (chain training)')
     parser.add_argument('--pretrained_D', type=str, default=None, help='discriminator state_dict to warm-start from')
+    parser.add_argument('--no_graphs', dest='graphs', action='store_false', help='launch every kernel of an iteration from Python instead of replaying the captured CUDA graph (default: graphs on)')
     parser.add_argument('--chain_scales', type=str, default='', help="e.g. '2,3,4': train these scales one after the other, each warm-started from the previous")
     return check_args(parser.parse_args(argv))
 

@@ -159,6 +159,7 @@ class EDSR(SRADSGAN):
             dp.all_reduce_flat(self.optimizer_G.flat_grad)
             g["graphs"][1].replay()
         self.optimizer_G.step_count += 1
+        self.optimizer_G.touch()          # masters changed through raw pointers: eager users of cached packed operands re-pack
         return g["out"]
 
     def _capture(self, imgs_lr, imgs_hr, key):
@@ -213,51 +214,9 @@ class EDSR(SRADSGAN):
         os.makedirs(model_dir, exist_ok=True)
         if self.epoch != 0:                                                             # :176-179
             self.load_epoch_network(model_dir + '/generator_param_epoch_%d.pkl' % self.epoch, self.generator, strict=True)
-        self.logger = CsvLogger(os.path.join(self.save_dir, 'logs')) if _rank() == 0 else None
-        lr_sz = self.crop_size // self.scale_factor
-        input_lr = torch.empty(self.batch_size, self.num_channels, lr_sz, lr_sz, device=self.device)      # :187-191
-        input_hr = torch.empty(self.batch_size, self.num_channels, self.crop_size, self.crop_size, device=self.device)
-        dataloader = self.load_dataset('train', max_samples=self.max_train_samples)
-        print('Training is started.')
-        step, start_time = 0, time.time()
-        epoch = self.epoch
-        best = {"psnr": 0.0, "step": 0, "no_improve": 0}
-        avg_loss_G = []
-        while epoch < self.num_epochs and self.lr >= 0.00001:                           # :207
-            sum_G = torch.zeros((), device=self.device)
-            n_it = 0
-            for i, batch in enumerate(dataloader):
-                imgs_lr = input_lr.copy_(batch[0], non_blocking=True)                   # :238-240
-                imgs_hr = input_hr.copy_(batch[1], non_blocking=True)
-                out = self.train_step(imgs_lr, imgs_hr)
-                sum_G += out["loss_G"]; n_it += 1
-                step += 1
-                if self.logger is not None and (step % self.log_interval == 0 or step == 1):
-                    lg = out["loss_G"].item()
-                    print("[Epoch %d/%d] [Batch %d/%d] [G loss: %f]" % (epoch, self.num_epochs, i, len(dataloader), lg))   # :268-270
-                    self.logger.scalar_summary('loss_G', lg, step)
-                    if step % self.sample_interval == 0 or step == 1:
-                        self.logger.print_format_results('train', OrderedDict(
-                            model=self.model_name, epoch=epoch, iters=step, G_lr=self.optimizer_G.param_groups[0]['lr'],
-                            time=time.time() - start_time, G_loss=lg, D_loss=0,
-                            psnr=psnr(out["gen_hr"][0].float().cpu(), imgs_hr[0].cpu())))
-            avg_loss_G.append((sum_G / max(n_it, 1)).item())
-            val_psnr = self.validate(epoch=epoch, mode='train', save_img=((epoch + 1) % self.save_epochs == 0))[0]
-            if val_psnr > best["psnr"]:
-                best.update(psnr=val_psnr, step=epoch, no_improve=0)
-            else:
-                best["no_improve"] += 1
-            if _rank() == 0:
-                self.save_epoch_network(model_dir, self.generator, 'generator', epoch + 1)
-            epoch += 1
-            if best["no_improve"] >= 5:                                                  # LR halving heuristic (:347-372)
-                self.load_epoch_network(model_dir + '/generator_param_epoch_%d.pkl' % (best["step"] + 1), self.generator)
-                for g in self.optimizer_G.param_groups:
-                    g["lr"] /= 2.0
-                self.lr /= 2.0
-                epoch = best["step"] + 1
-                best["no_improve"] = 0
-        print("Training is finished.")
+        # the epoch loop (:207-372: staging copies, iteration, logging, validation, per-epoch checkpoint, the no-improvement
+        # rollback + LR halving) is the SRADSGAN trainer's, run on this class's step (graph replay by default)
+        avg_loss_G, _ = self._fit(model_dir, {"generator": self.generator})
         if _rank() == 0:
             self.save_model(epoch=None)
         return avg_loss_G

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import _lib, dp, ops
 from ..optim import FlatAdam
-from ..utils import CsvLogger, ergas_batch, psnr, psnr_batch, save_img1, weights_init_normal
+from ..utils import CsvLogger, eval_metrics_u8, psnr, save_img1, weights_init_normal
 
 
 class SRADSGAN(object):
@@ -41,6 +41,9 @@ class SRADSGAN(object):
         self.vgg_state = getattr(args, "vgg_state", None)
         self.seed = getattr(args, "seed", 0)
         self.gpu_input_pipeline = getattr(args, "gpu_input_pipeline", False)
+        # train() replays the captured CUDA graph of the iteration (graphed_step) unless --no_graphs: the drop-in entry point
+        # owns the fast path; eager launches remain for debugging / profiling
+        self.use_graphs = bool(getattr(args, "graphs", True))
         # chain training (the paper's x2 -> x3 -> x4 ... warm starts; reference :716-721 does it by hand-editing two paths)
         self.pretrained_G = getattr(args, "pretrained_G", None)
         self.pretrained_D = getattr(args, "pretrained_D", None)
@@ -241,26 +244,41 @@ class SRADSGAN(object):
         g = self._graph
         g["lr"].copy_(imgs_lr, non_blocking=True)
         g["hr"].copy_(imgs_hr, non_blocking=True)
-        g["alpha_host"].copy_(torch.from_numpy(np.random.random((imgs_hr.size(0), 1, 1, 1))).float())   # reference :609
-        g["alpha"].copy_(g["alpha_host"], non_blocking=True)
+        # GP interpolation factors (reference :609, numpy RNG): two pinned staging buffers used alternately, each guarded by
+        # an event recorded after its host->device copy — the host runs many replays ahead of the device and must not
+        # overwrite a buffer whose copy is still queued
+        slot = g["alpha_slot"] = 1 - g.get("alpha_slot", 1)
+        g["alpha_evt"][slot].synchronize()
+        g["alpha_host"][slot].copy_(torch.from_numpy(np.random.random((imgs_hr.size(0), 1, 1, 1))).float())
+        g["alpha"].copy_(g["alpha_host"][slot], non_blocking=True)
+        g["alpha_evt"][slot].record()
         if len(g["graphs"]) == 1:
             g["graphs"][0].replay()
         else:
-            g["graphs"][0].replay()
-            dp.all_reduce_flat(self.optimizer_G.flat_grad)
-            g["graphs"][1].replay()
-            dp.all_reduce_flat(self.optimizer_D.flat_grad)
-            g["graphs"][2].replay()
+            self._replay_dp(g)
         self.optimizer_G.step_count += 1
         self.optimizer_D.step_count += 1
+        # the replay updated the fp32 masters through raw pointers: eager users of cached packed operands (validate(),
+        # generator(x)) must re-pack (the graph itself re-packs its own operands at the start of every replay)
+        self.optimizer_G.touch()
+        self.optimizer_D.touch()
         return g["out"]
+
+    def _replay_dp(self, g):
+        """data parallel: G phase | all-reduce(G) | Adam_G + D phase | all-reduce(D) | Adam_D — collectives are never captured"""
+        g["graphs"][0].replay()
+        dp.all_reduce_flat(self.optimizer_G.flat_grad)
+        g["graphs"][1].replay()
+        dp.all_reduce_flat(self.optimizer_D.flat_grad)
+        g["graphs"][2].replay()
 
     def _capture(self, imgs_lr, imgs_hr, key):
         dev = imgs_lr.device
         world = dp.world_size()
         st = {"key": key, "lr": torch.empty_like(imgs_lr), "hr": torch.empty_like(imgs_hr),
               "alpha": torch.empty(imgs_hr.size(0), 1, 1, 1, device=dev),
-              "alpha_host": torch.empty(imgs_hr.size(0), 1, 1, 1).pin_memory()}
+              "alpha_host": [torch.empty(imgs_hr.size(0), 1, 1, 1).pin_memory() for _ in range(2)],
+              "alpha_evt": [torch.cuda.Event(), torch.cuda.Event()]}
         st["lr"].copy_(imgs_lr); st["hr"].copy_(imgs_hr); st["alpha"].uniform_()
         prev_override = self._alpha_override
         self._alpha_override = st["alpha"]
@@ -319,19 +337,30 @@ class SRADSGAN(object):
     # ------------------------------------------------------------------------------------------
     def load_dataset(self, dataset='train', max_samples=20000):
         """reference :643-656. Folder datasets are outside the hot path: a synthetic source
-        is used when `synthetic_steps` > 0, otherwise a minimal PIL folder reader."""
+        is used when `synthetic_steps` > 0, otherwise a minimal PIL folder reader.  Data parallel: the TRAINING set is
+        sharded per rank (DistributedSampler; `_train_sampler.set_epoch` is called by the loop) — every rank sees a disjoint
+        slice per epoch, so the effective batch is batch_size * world.  Evaluation sets are read in full by every rank."""
         from ..data import DevicePrefetcher, FolderHRDataset, FolderSRDataset, SyntheticSRDataset
-        bs = self.batch_size if dataset == 'train' else self.test_batch_size
+        train = dataset == 'train'
+        bs = self.batch_size if train else self.test_batch_size
         device_pipeline = getattr(self, "gpu_input_pipeline", False) and not self.synthetic_steps
         if self.synthetic_steps:
             ds = SyntheticSRDataset(self.synthetic_steps * bs, self.crop_size, self.scale_factor, seed=1234 + _rank())
         else:
-            names = self.train_dataset if dataset == 'train' else self.test_dataset
+            names = self.train_dataset if train else self.test_dataset
             cls = FolderHRDataset if device_pipeline else FolderSRDataset
             ds = cls(self.data_dir, names, self.crop_size, self.scale_factor, max_samples=max_samples)
+        sampler = None
+        shuffle = train and not self.synthetic_steps
+        if train and dp.is_dist() and not self.synthetic_steps:
+            from torch.utils.data.distributed import DistributedSampler
+            sampler = DistributedSampler(ds, num_replicas=dp.world_size(), rank=_rank(), shuffle=True, seed=self.seed, drop_last=True)
+            shuffle = False
+        if train:
+            self._train_sampler = sampler
+        gen = torch.Generator().manual_seed(self.seed * 7919 + _rank())      # shuffle order / worker seeds differ per rank
         loader = torch.utils.data.DataLoader(ds, num_workers=0 if self.synthetic_steps else self.num_threads, batch_size=bs,
-                                             shuffle=(dataset == 'train' and not self.synthetic_steps), drop_last=True,
-                                             pin_memory=True)
+                                             shuffle=shuffle, sampler=sampler, drop_last=True, pin_memory=self.cuda, generator=gen)
         # --gpu_input_pipeline: workers only decode + crop; LR / bicubic synthesis (PIL-exact) and the copies run on the device,
         # double-buffered behind the training step (SURVEY.md §8 f3)
         return DevicePrefetcher(loader, self.device, self.scale_factor) if device_pipeline else loader
@@ -339,6 +368,10 @@ class SRADSGAN(object):
     # ------------------------------------------------------------------------------------------
     # training loop (reference :658-1056)
     # ------------------------------------------------------------------------------------------
+    def step_fn(self):
+        """what one iteration of train() executes: the CUDA-graph replay (default) or the eagerly launched step (--no_graphs)"""
+        return self.graphed_step if (self.use_graphs and self.cuda) else self.train_step
+
     def train(self):
         self.build()
         model_dir = os.path.join(self.save_dir, 'model')
@@ -348,112 +381,231 @@ class SRADSGAN(object):
             self.load_epoch_network(model_dir + '/discriminator_param_epoch_%d.pkl' % self.epoch, self.discriminator, strict=True)
         elif self.pretrained_G or self.pretrained_D:                                # :716-721 (chain training warm start)
             self.load_pretrained(self.pretrained_G, self.pretrained_D)
+        avg_loss_G, avg_loss_D = self._fit(model_dir, {"generator": self.generator, "discriminator": self.discriminator})
+        if _rank() == 0:
+            self.save_model(epoch=None)                                              # :1056
+        return avg_loss_G, avg_loss_D
+
+    def _fit(self, model_dir, nets):
+        """the epoch loop of the reference's train() (:804-1036), shared with the EDSR trainer (model/edsr.py:207-372).
+        `nets`: label -> module saved every epoch; `nets['generator']` is the one the rollback heuristic reloads."""
         self.logger = CsvLogger(os.path.join(self.save_dir, 'logs')) if _rank() == 0 else None
         lr_sz = self.crop_size // self.scale_factor
-        input_lr = torch.empty(self.batch_size, self.num_channels, lr_sz, lr_sz, device=self.device)      # :739-741
-        input_hr = torch.empty(self.batch_size, self.num_channels, self.crop_size, self.crop_size, device=self.device)
+        run = self.step_fn()
+        graphs = run == self.graphed_step
+        if not graphs:       # the reference's pre-allocated staging tensors (:739-741); graphed_step owns its static buffers
+            input_lr = torch.empty(self.batch_size, self.num_channels, lr_sz, lr_sz, device=self.device)
+            input_hr = torch.empty(self.batch_size, self.num_channels, self.crop_size, self.crop_size, device=self.device)
         dataloader = self.load_dataset('train', max_samples=self.max_train_samples)
         print('Training is started.')
         step, start_time = 0, time.time()
         epoch = self.epoch
-        best = {"psnr": 0.0, "step": 0, "no_improve": 0}
+        # reference :795-800 — best-so-far of the four validation metrics and the no-improvement counter
+        best = {"psnr": 0.0, "ssim": 0.0, "ergas": 10000.0, "lpips": 10000.0, "step": 0, "no_improve": 0}
+        has_D = self.optimizer_D is not None
         avg_loss_G, avg_loss_D = [], []
         while epoch < self.num_epochs and self.lr >= 0.00001:                       # :804
+            if getattr(self, "_train_sampler", None) is not None:
+                self._train_sampler.set_epoch(epoch)
             sum_G = torch.zeros((), device=self.device)
             sum_D = torch.zeros((), device=self.device)
             n_it = 0
             for i, batch in enumerate(dataloader):
-                inp, target = batch[0], batch[1]
-                imgs_lr = input_lr.copy_(inp, non_blocking=True)                    # :821-823
-                imgs_hr = input_hr.copy_(target, non_blocking=True)
-                out = self.train_step(imgs_lr, imgs_hr)
+                if graphs:                                                          # one copy: loader batch -> the graph's inputs
+                    imgs_lr, imgs_hr = batch[0], batch[1]
+                else:
+                    imgs_lr = input_lr.copy_(batch[0], non_blocking=True)           # :821-823
+                    imgs_hr = input_hr.copy_(batch[1], non_blocking=True)
+                out = run(imgs_lr, imgs_hr)
                 sum_G += out["loss_G"]; sum_D += out["loss_D"]; n_it += 1
                 step += 1
                 if self.logger is not None and (step % self.log_interval == 0 or step == 1):
                     lg, ld = out["loss_G"].item(), out["loss_D"].item()             # the only host sync, every N steps
                     print("[Epoch %d/%d] [Batch %d/%d] [D loss: %f] [G loss: %f]" % (epoch, self.num_epochs, i, len(dataloader), ld, lg))
                     self.logger.scalar_summary('loss_G', lg, step)
-                    self.logger.scalar_summary('loss_D', ld, step)
+                    if has_D:
+                        self.logger.scalar_summary('loss_D', ld, step)
                     if step % self.sample_interval == 0 or step == 1:
                         self.logger.print_format_results('train', OrderedDict(
                             model=self.model_name, epoch=epoch, iters=step, G_lr=self.optimizer_G.param_groups[0]['lr'],
-                            D_lr=self.optimizer_D.param_groups[0]['lr'], time=time.time() - start_time, G_loss=lg, D_loss=ld,
-                            srwgan_psnr=psnr(out["gen_hr"][0].float().cpu(), imgs_hr[0].cpu())))
+                            D_lr=self.optimizer_D.param_groups[0]['lr'] if has_D else 0.0, time=time.time() - start_time,
+                            G_loss=lg, D_loss=ld,
+                            srwgan_psnr=psnr(out["gen_hr"][0].float().cpu(), batch[1][0].float().cpu())))
             avg_loss_G.append((sum_G / max(n_it, 1)).item())
             avg_loss_D.append((sum_D / max(n_it, 1)).item())
-            val_psnr = self.validate(epoch=epoch, mode='train', save_img=((epoch + 1) % self.save_epochs == 0))[0]
-            if val_psnr > best["psnr"]:
-                best.update(psnr=val_psnr, step=epoch, no_improve=0)
-            else:
-                best["no_improve"] += 1
+            val = self.validate(epoch=epoch, mode='train', save_img=((epoch + 1) % self.save_epochs == 0))
+            self._update_best(best, val, epoch)
             if _rank() == 0:
-                self.save_epoch_network(model_dir, self.generator, 'generator', epoch + 1)          # :1005-1008
-                self.save_epoch_network(model_dir, self.discriminator, 'discriminator', epoch + 1)
+                for label, net in nets.items():
+                    self.save_epoch_network(model_dir, net, label, epoch + 1)        # :1005-1008
+            if dp.is_dist():
+                torch.distributed.barrier()          # a rollback below reads the checkpoint rank 0 has just written
             epoch += 1
             if best["no_improve"] >= 5:                                              # :1011-1036 LR halving heuristic
-                self.load_epoch_network(model_dir + '/generator_param_epoch_%d.pkl' % (best["step"] + 1), self.generator)
+                self.load_epoch_network(model_dir + '/generator_param_epoch_%d.pkl' % (best["step"] + 1), nets["generator"])
                 for g in self.optimizer_G.param_groups:
                     g["lr"] /= 2.0
-                if self.lr < 0.0001:
+                if has_D and self.lr < 0.0001:
                     for g in self.optimizer_D.param_groups:
                         g["lr"] /= 2.0
                 self.lr /= 2.0
                 epoch = best["step"] + 1
                 best["no_improve"] = 0
         print("Training is finished.")
-        if _rank() == 0:
-            self.save_model(epoch=None)                                              # :1056
         return avg_loss_G, avg_loss_D
+
+    @staticmethod
+    def _update_best(best, val, epoch):
+        """reference :986-1003: the counter is reset when PSNR, else SSIM, else ERGAS, else LPIPS improves (in that `elif`
+        order); metrics this build does not compute are None and never participate.  A validation pass that produced no
+        samples (synthetic training, no test folder) returns None and leaves the heuristic untouched — otherwise every
+        epoch would count as 'no improvement' and the run would roll back to epoch 1 for ever."""
+        if val is None:
+            return
+        v_psnr, v_ssim, v_ergas, v_lpips = val
+        if v_psnr is not None and v_psnr - best["psnr"] > 0:
+            best.update(psnr=v_psnr, no_improve=0, step=epoch)
+        elif v_ssim is not None and v_ssim - best["ssim"] > 0:
+            best.update(ssim=v_ssim, no_improve=0, step=epoch)
+        elif v_ergas is not None and v_ergas - best["ergas"] < 0:
+            best.update(ergas=v_ergas, no_improve=0, step=epoch)
+        elif v_lpips is not None and v_lpips - best["lpips"] < 0:
+            best.update(lpips=v_lpips, no_improve=0, step=epoch)
+        else:
+            best["no_improve"] += 1
 
     # ------------------------------------------------------------------------------------------
     # evaluation / inference (reference :1058-1194, :1259-1640)
     # ------------------------------------------------------------------------------------------
-    def _eval_loader(self):
+    def _eval_loader(self, names=None):
+        prev = self.test_dataset
         try:
+            if names is not None:
+                self.test_dataset = names
             return self.load_dataset('test')
         except (FileNotFoundError, OSError):
             return None
+        finally:
+            self.test_dataset = prev
+
+    @torch.no_grad()
+    def _evaluate(self, loader, save_dir=None, epoch=0, classname=None):
+        """generator over one evaluation loader; the per-image metrics of the reference's loops (:1111-1122, :1481-1494 —
+        skimage compare_mse / compare_psnr / compare_ssim on the uint8 images, compare_ergas2) for the SR output AND the
+        bicubic baseline stay on the device (utils.eval_metrics_u8); ONE read-back per loader.
+        LPIPS needs AlexNet weights that cannot be fetched offline: not computed (None).
+        Returns {"sr": {metric: mean}, "bicubic": {...}, "n": images} or None when the loader is empty."""
+        self.generator.eval()
+        acc = {"sr": [], "bicubic": []}
+        for batch in loader:
+            lr = batch[0].to(self.device, non_blocking=True)
+            gt = batch[1].to(self.device, non_blocking=True)
+            rec = self.generator(lr).float()
+            acc["sr"].append(eval_metrics_u8(rec, gt, self.scale_factor))
+            if len(batch) > 2 and torch.is_tensor(batch[2]):
+                acc["bicubic"].append(eval_metrics_u8(batch[2].to(self.device, non_blocking=True), gt, self.scale_factor))
+            if save_dir is not None:                                                 # :1506-1509
+                for i in range(rec.shape[0]):
+                    name = os.path.splitext(os.path.basename(str(batch[-1][i])))[0]
+                    d = os.path.join(save_dir, 'validate', classname or '')
+                    save_img1(rec[i], d, os.path.join(d, '%s_x%d_%d.png' % (name, self.scale_factor, epoch)))
+        if not acc["sr"]:
+            return None
+        out = {"n": int(sum(m["mse"].numel() for m in acc["sr"]))}
+        for who, ms in acc.items():
+            if ms:
+                cat = torch.stack([torch.cat([m[k] for m in ms]) for k in ("mse", "psnr", "ssim", "ergas")])   # one D2H copy
+                sums = cat.sum(dim=1).tolist()
+                out[who] = dict(zip(("mse", "psnr", "ssim", "ergas"), [v / cat.shape[1] for v in sums]))
+        return out
+
+    def _log_val(self, label, epoch, res, t0):
+        """the 'val' log line of the reference (:1166-1185 / :1548-1565)"""
+        if self.logger is None and _rank() == 0:
+            self.logger = CsvLogger(os.path.join(self.save_dir, 'logs'))
+        if self.logger is None:
+            return
+        rlt = OrderedDict(model=label, epoch=epoch, iters=epoch, time=time.time() - t0)
+        for who, tag in (("bicubic", "bicubic"), ("sr", self.model_name.lower())):
+            for k in ("mse", "psnr", "ssim", "ergas"):
+                if who in res:
+                    rlt['%s_%s' % (tag, k)] = res[who][k]
+        self.logger.print_format_results('val', rlt)
 
     @torch.no_grad()
     def validate(self, epoch=0, mode='test', save_img=False):
-        """PSNR and ERGAS on the test set, computed on the device (SSIM / LPIPS need skimage / AlexNet weights, absent
-        offline: returned as 0). Returns (psnr, ssim, ergas, lpips) like the reference."""
+        """reference :1058-1194.  Returns (psnr, ssim, ergas, lpips) of the SR output averaged over the test set (lpips is None:
+        not computed offline), or None when there is nothing to validate on (synthetic training, missing test folder) — the
+        caller's early-stopping heuristic then leaves its counters alone."""
         if self.generator is None:
             self.build(init=False)
             self.load_model()
         loader = self._eval_loader() if not self.synthetic_steps else None
         if loader is None:
-            return 0.0, 0.0, 0.0, 0.0
-        self.generator.eval()
-        vals, ergs = [], []
-        for batch in loader:                      # metrics stay on the device; ONE read-back after the loop (SURVEY.md §8 f2)
-            rec = self.generator(batch[0].to(self.device, non_blocking=True)).float()
-            gt = batch[1].to(self.device, non_blocking=True)
-            vals.append(psnr_batch(rec, gt))
-            ergs.append(ergas_batch(rec, gt, self.scale_factor))
-        if not vals:
-            return 0.0, 0.0, 0.0, 0.0
-        return float(torch.cat(vals).mean().item()), 0.0, float(torch.cat(ergs).mean().item()), 0.0
+            return None
+        t0 = time.time()
+        res = self._evaluate(loader)
+        if res is None:
+            return None
+        self._log_val(self.model_name, epoch, res, t0)
+        return res["sr"]["psnr"], res["sr"]["ssim"], res["sr"]["ergas"], None
 
     def mfeNew_validate(self, epoch=100, modelpath=None):
         self.build(init=False)
         if modelpath is not None:
             self.generator.load_state_dict(torch.load(modelpath, map_location=self.device), strict=False)   # :1270
+            ops.bump_weight_generation()
         return self.validate(epoch=epoch, mode='test')
 
+    @torch.no_grad()
     def mfeNew_validateByClass(self, epoch=100, save_img=False, modelpath=None):
-        return self.mfeNew_validate(epoch=epoch, modelpath=modelpath)
+        """reference :1393-1601: every class sub-folder of the first test dataset (UCMerced_LandUse's 21 land-use classes,
+        :1430-1438) is evaluated separately — one 'val' log line per class, then the total over all images.
+        Returns {class name: metrics, ..., "Total": metrics} with metrics = {"sr": {...}, "bicubic": {...}, "n": images}."""
+        self.generator = self.new_generator()
+        if modelpath is not None:
+            self.generator.load_state_dict(torch.load(modelpath, map_location="cpu"), strict=False)          # :1401-1402
+        self.generator.to(self.device).eval()
+        ops.bump_weight_generation()
+        root = os.path.join(self.data_dir, self.test_dataset[0])
+        classes = [d for d in sorted(os.listdir(root)) if os.path.isdir(os.path.join(root, d))] if os.path.isdir(root) else []
+        t0 = time.time()
+        results, tot = OrderedDict(), None
+        for cname in classes:
+            loader = self._eval_loader([os.path.join(self.test_dataset[0], cname)])
+            res = self._evaluate(loader, self.save_dir if save_img else None, epoch, cname) if loader is not None else None
+            if res is None:
+                continue
+            results[cname] = res
+            self._log_val(cname, epoch, res, t0)
+            if tot is None:
+                tot = {"n": 0, "sr": dict.fromkeys(res["sr"], 0.0), "bicubic": dict.fromkeys(res.get("bicubic", {}), 0.0)}
+            tot["n"] += res["n"]
+            for who in ("sr", "bicubic"):
+                for k, v in res.get(who, {}).items():
+                    tot[who][k] += v * res["n"]
+        if tot is not None:
+            for who in ("sr", "bicubic"):
+                tot[who] = {k: v / tot["n"] for k, v in tot[who].items()}
+            if not tot["bicubic"]:
+                del tot["bicubic"]
+            results["Total"] = tot
+            self._log_val("Total", epoch, tot, t0)
+        return results
 
     def mfe_test_single(self, img_fn, modelpath=None, tile=None, overlap=16):
         """reference :1603-1640: CenterCrop(test_crop_size) -> batch of `batch_size` identical copies ->
-        G -> save [0] as uint8 (truncation).  `tile` (new): run large inputs as overlapped LR tiles of that
-        size, which the reference cannot do because SGAM materialises an (HW)x(HW) attention."""
+        G -> save [0] as uint8 (truncation), plus the PIL-bicubic baseline image (:1630,:1638).  `tile` (new): run large
+        inputs as overlapped LR tiles of that size, which the reference cannot do because SGAM materialises an (HW)x(HW)
+        attention.  Returns the SR image (3, H*s, W*s) on the device."""
         from PIL import Image
         import torchvision.transforms as transforms
+        from ..data import pil_bicubic
         self.generator = self.new_generator()
         if modelpath is not None:
             self.generator.load_state_dict(torch.load(modelpath, map_location="cpu"), strict=False)   # :1612-1613
         self.generator.to(self.device).eval()
+        ops.bump_weight_generation()
         img = transforms.Compose([transforms.CenterCrop(self.test_crop_size), transforms.ToTensor()])(Image.open(img_fn))
         input_img = img.unsqueeze(0).expand(self.batch_size, -1, -1, -1).contiguous().to(self.device)   # :1628-1629
         with torch.no_grad():
@@ -462,8 +614,12 @@ class SRADSGAN(object):
             else:
                 recon = self.generator(input_img)
         img_name = img_fn.split("/")[-1]
-        out_path = os.path.join(self.save_dir, 'SR_SRADSGAN_%s' % img_name)
-        save_img1(recon[0].float().cpu(), self.save_dir, out_path)                   # :1637
+        save_img1(recon[0].float(), self.save_dir, os.path.join(self.save_dir, 'SR_%s_%s' % (self.model_name, img_name)))   # :1637
+        # bicubic baseline (`img_interp`, utils/utils.py:755-783: ToPILImage -> PIL resize -> ToTensor), on the device
+        u8 = (input_img[:1] * 255.0).clamp(0, 255).floor()
+        h, w = u8.shape[-2:]
+        bc = pil_bicubic(u8, h * self.scale_factor, w * self.scale_factor) / 255.0
+        save_img1(bc[0], self.save_dir, os.path.join(self.save_dir, 'SR_Bicubic_%s' % img_name))                         # :1638
         return recon[0]
 
     # ------------------------------------------------------------------------------------------
@@ -507,7 +663,9 @@ class SRADSGAN(object):
         complete `train()` of the reference (fresh Adam state, `num_epochs` epochs, own save_dir/x<scale>) whose generator
         and critic start from the previous stage's final weights.  Returns {scale: (avg_loss_G, avg_loss_D)}."""
         base_dir, results, prev = self.save_dir, {}, None
+        base_lr = self.lr                 # train()'s rollback heuristic halves self.lr: every stage starts from the configured rate
         for s in scales:
+            self.lr = base_lr
             self.scale_factor = int(s)
             self.save_dir = os.path.join(base_dir, "x%d" % s)
             self.epoch = 0

@@ -155,7 +155,8 @@ def _capturing(t):
 
 
 def _ver(w):
-    return (_generation, getattr(w, "_sr_gen", 0), w._version, w.data_ptr())
+    ref = getattr(w, "_sr_genref", None)        # one mutable stamp per optimiser (FlatAdam.gen), bumped in O(1)
+    return (_generation, ref[0] if ref is not None else getattr(w, "_sr_gen", 0), w._version, w.data_ptr())
 
 
 def packed(w, mode, dtype, shuffle_r=0):

@@ -38,6 +38,11 @@ class FlatAdam:
             p._sr_flat_grad = p.grad       # ops.py: first-order backward passes accumulate straight into this view
             self.offsets[n] = (off, k)
             off += (k + 3) // 4 * 4
+        # ops.packed(): packed bf16 operands are validated against this stamp.  Every update of the masters through raw
+        # pointers (step(), a CUDA-graph replay of step()) must call touch().
+        self.gen = [ops.next_generation()]
+        for p in self.params:
+            p._sr_genref = self.gen
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps}]
         self.clamp = clamp
         self.step_count = 0
@@ -83,10 +88,12 @@ class FlatAdam:
         g = self.param_groups[0]
         _lib.backend().adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
                                  g["betas"][1], g["eps"], self.step_count, grad_scale, self.clamp, step_tensor=self.step_t)
-        # the parameters changed through raw pointers: invalidate THIS network's packed operands only
-        gen = ops.next_generation()
-        for p in self.params:
-            p._sr_gen = gen
+        self.touch()
+
+    def touch(self):
+        """the parameters changed through raw pointers (this step, or a graph replay of it): invalidate THIS network's
+        cached packed operands"""
+        self.gen[0] = ops.next_generation()
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),

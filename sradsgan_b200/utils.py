@@ -45,6 +45,42 @@ def ergas_batch(pred, gt, scale=4):
     return 100.0 * torch.sqrt(mse / mean2.clamp_min(1e-300) / pred.shape[1]) / scale
 
 
+def to_u8_levels(img):
+    """grey levels 0..255 as float64 on the tensor's device: `*255 -> clamp -> truncate`, what `ToPILImage` / `save_img1`
+    make of a float image (reference model/sradsgan.py:1103-1110, utils/utils.py:169-175; out-of-range generator outputs are
+    clamped where the reference's `.byte()` would wrap)."""
+    return (img.detach().float() * 255.0).clamp(0, 255).floor().double()
+
+
+def ssim_u8_batch(a, b):
+    """skimage.measure.compare_ssim(img1, img2, multichannel=True) of uint8 images (reference model/sradsgan.py:1113, :1483),
+    per image, on the device.  a, b: (B, C, H, W) grey levels 0..255 (float64).  skimage defaults: 7x7 uniform window,
+    K1 = 0.01, K2 = 0.03, data_range 255, sample covariance (x 49/48), mean over the pixels whose window lies inside the image
+    (its 3-pixel border crop makes the filter's boundary mode irrelevant) and over the channels."""
+    import torch.nn.functional as F
+    win, c1, c2 = 7, (0.01 * 255.0) ** 2, (0.03 * 255.0) ** 2
+    norm = win * win / (win * win - 1.0)
+    mean = lambda t: F.avg_pool2d(t, win, stride=1)
+    ux, uy = mean(a), mean(b)
+    vx = norm * (mean(a * a) - ux * ux)
+    vy = norm * (mean(b * b) - uy * uy)
+    vxy = norm * (mean(a * b) - ux * uy)
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
+    return s.flatten(1).mean(dim=1)
+
+
+def eval_metrics_u8(pred, gt, scale=4):
+    """the four per-image numbers the reference's validation loops log (model/sradsgan.py:1111-1114, :1481-1484), computed on
+    the device from the uint8-quantised images: skimage compare_mse / compare_psnr (data_range 255) / compare_ssim and
+    utils.compare_ergas2.  pred, gt: (B, C, H, W) float [0, 1].  Returns a dict of float64 tensors of shape (B,)."""
+    a, b = to_u8_levels(gt), to_u8_levels(pred)
+    mse = ((a - b) ** 2).flatten(1).mean(dim=1)
+    ps = torch.where(mse == 0, torch.full_like(mse, float("inf")), 10.0 * torch.log10(255.0 ** 2 / mse.clamp_min(1e-300)))
+    mean2 = a.flatten(1).mean(dim=1) ** 2
+    ergas = 100.0 * torch.sqrt(mse / mean2.clamp_min(1e-300) / pred.shape[1]) / scale
+    return {"mse": mse, "psnr": ps, "ssim": ssim_u8_batch(a, b), "ergas": ergas}
+
+
 def quantize_u8(img):
     """reference utils/utils.py:169-175: img*255, clamp to [0,255], astype(uint8) (truncation), CHW -> HWC.
     The quantisation runs where the tensor lives; only the uint8 image crosses to the host."""
