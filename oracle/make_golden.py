@@ -188,5 +188,41 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+FULLSIZE = dict(scale=4, batch=16, hr=216, gseed=0, dseed=1, vseed=2, data_seed=1234, np_seed=4242, gamma=0.5)
+
+
+def fullsize():
+    """ONE iteration of the UNMODIFIED reference at the benchmarked configuration (BASELINE.json configs[1]: full 12x3
+    generator, discriminator, VGG19[:12], batch 16, LR 54^2 / HR 216^2; weights per SURVEY.md §8d) -> losses, output /
+    gradient / parameter summaries in tests/golden/sradsgan_fullsize_golden.pt.  tests/test_oracle_golden.py holds the oracle
+    to it on CPU, tests/test_gpu_fullsize_parity.py holds `graphed_step` to the oracle AND to these numbers on the GPU."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = ref_shim.load_reference()
+    c = FULLSIZE
+    gsd = O.tie_upsampling(O.make_state(O.generator_spec(c["scale"]), seed=c["gseed"], init="ref", gamma=c["gamma"]))
+    dsd = O.make_state(O.discriminator_spec(), seed=c["dseed"], init="ref")
+    vsd = O.make_state(O.vgg_spec(), seed=c["vseed"], init="fan")
+    G = build_ref_generator(ref, gsd, c["scale"], 12, 3)
+    D = build_ref_discriminator(ref, dsd)
+    V = build_ref_vgg(vsd)
+    opt_G = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.9, 0.999))
+    opt_D = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.9, 0.999))
+    lr, hr = O.synthetic_batch(c["batch"], c["scale"], c["hr"], seed=c["data_seed"])
+    with torch.no_grad():
+        y0 = G(lr)
+    rec = ref_train_step(ref, G, D, V, opt_G, opt_D, lr, hr, np_seed=c["np_seed"])
+    rec["psnr_vs_hr"] = O.psnr(y0, hr)
+    rec["G_params"] = {k: summarize(p, 8) for k, p in G.named_parameters()}
+    rec["D_state"] = {k: summarize(p.float(), 8) for k, p in D.state_dict().items()}
+    out = {"cfg": c, "step": rec}
+    path = os.path.join(GOLDEN_DIR, "sradsgan_fullsize_golden.pt")
+    torch.save(out, path)
+    print("fullsize", {k: v for k, v in rec.items() if isinstance(v, float)})
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--fullsize" in sys.argv:
+        fullsize()
+    else:
+        main()

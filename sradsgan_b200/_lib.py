@@ -168,11 +168,17 @@ class CudaBackend:
         tc = self.lib.sr_conv_uses_tcgen05(ctypes.byref(d), {"fwd": 0, "dgrad": 1, "wgrad": 2}[kind])
         m = d.N * d.Ho * d.Wo
         flops = 2.0 * m * d.Cout * d.Cin * d.kh * d.kw
+        return self._timed_rec("conv_%s_%s" % (kind, "tcgen05" if tc else "simt"), flops, 0.0, call)
+
+    def _timed_rec(self, kind, flops, nbytes, call):
+        """bench.py attribution record: (kernel family, algorithmic FLOPs, algorithmic bytes, start event, end event)"""
+        if self.prof is None or torch.cuda.is_current_stream_capturing():
+            return call()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = call()
         e1.record()
-        self.prof.append(("conv_%s_%s" % (kind, "tcgen05" if tc else "simt"), flops, e0, e1))
+        self.prof.append((kind, flops, nbytes, e0, e1))
         return out
 
     def launch_count(self):
@@ -297,9 +303,11 @@ class CudaBackend:
         ws = torch.empty(self.lib.sr_la_chain_workspace_bytes(n, h, w), dtype=torch.uint8, device=dev)
         args = [fc1, fc2, w7, W, b]
         args = [a.detach().float().contiguous() for a in args]
-        _check(self.lib.sr_la_chain_fwd(_ptr(x), _dt(x), _ptr(t), *[_ptr(a) for a in args], n, h, w, c, cr, _ptr(z32), _ptr(z16),
-                                        _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]), _ptr(sv["max"]), _ptr(sv["pstar"]),
-                                        _ptr(sv["q"]), _ptr(sv["cstar"]), _ptr(ws), _stream()), "la_chain_fwd")
+        nbytes = float(x.numel()) * (x.element_size() + 4 + 4 + (x.element_size() if want_lowp else 0))
+        self._timed_rec("la_chain_fwd", 0.0, nbytes, lambda: _check(
+            self.lib.sr_la_chain_fwd(_ptr(x), _dt(x), _ptr(t), *[_ptr(a) for a in args], n, h, w, c, cr, _ptr(z32), _ptr(z16),
+                                     _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]), _ptr(sv["max"]), _ptr(sv["pstar"]),
+                                     _ptr(sv["q"]), _ptr(sv["cstar"]), _ptr(ws), _stream()), "la_chain_fwd"))
         return z32, z16, sv
 
     def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
@@ -328,10 +336,13 @@ class CudaBackend:
             dz, dz_ptr = None, None
         ws = torch.empty(self.lib.sr_la_chain_workspace_bytes(n, h, w), dtype=torch.uint8, device=dev)
         wts = [a.detach().float().contiguous() for a in (fc1, fc2, w7, W)]
-        _check(self.lib.sr_la_chain_bwd(_ptr(gz32), _ptr(gz16), _ptr(x), _dt(x), _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]),
-                                        _ptr(sv["max"]), _ptr(sv["pstar"]), _ptr(sv["q"]), _ptr(sv["cstar"]),
-                                        *[_ptr(a) for a in wts], n, h, w, c, cr, _ptr(dx), _ptr(d_fc1), _ptr(d_fc2), _ptr(d_w7),
-                                        _ptr(dW), _ptr(db), _ptr(dz_ptr), _ptr(ws), _stream()), "la_chain_bwd")
+        es = x.element_size()
+        nbytes = float(x.numel()) * ((4 if gz32 is not None else 0) + (es if gz16 is not None else 0) + es + es + (4 if dz_ptr is not None else 0))
+        self._timed_rec("la_chain_bwd", 0.0, nbytes, lambda: _check(
+            self.lib.sr_la_chain_bwd(_ptr(gz32), _ptr(gz16), _ptr(x), _dt(x), _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]),
+                                     _ptr(sv["max"]), _ptr(sv["pstar"]), _ptr(sv["q"]), _ptr(sv["cstar"]),
+                                     *[_ptr(a) for a in wts], n, h, w, c, cr, _ptr(dx), _ptr(d_fc1), _ptr(d_fc2), _ptr(d_w7),
+                                     _ptr(dW), _ptr(db), _ptr(dz_ptr), _ptr(ws), _stream()), "la_chain_bwd"))
         return dx, d_fc1, d_fc2, d_w7, dW, db, dz
 
     def act_bwd(self, gy, y, act, slope, shuffle_r, g, out_dtype):
@@ -370,9 +381,10 @@ class CudaBackend:
         y = torch.empty_like(x)
         save = torch.empty((4, c), dtype=torch.float32, device=x.device)
         ws = torch.empty((2 * c,), dtype=torch.float32, device=x.device)
-        _check(self.lib.sr_bn_act_fwd(_ptr(x), _dt(x), n * h * w, c, _ptr(gamma.detach().float().contiguous()),
-                                      _ptr(beta.detach().float().contiguous()), float(eps), float(momentum), float(slope),
-                                      _ptr(running_mean), _ptr(running_var), _ptr(y), _ptr(save), _ptr(ws), _stream()), "bn_act_fwd")
+        self._timed_rec("bn_act_fwd", 0.0, 3.0 * x.numel() * x.element_size(), lambda: _check(
+            self.lib.sr_bn_act_fwd(_ptr(x), _dt(x), n * h * w, c, _ptr(gamma.detach().float().contiguous()),
+                                   _ptr(beta.detach().float().contiguous()), float(eps), float(momentum), float(slope),
+                                   _ptr(running_mean), _ptr(running_var), _ptr(y), _ptr(save), _ptr(ws), _stream()), "bn_act_fwd"))
         return y, save
 
     def bn_act_bwd(self, gy, x, save, slope):
@@ -382,8 +394,9 @@ class CudaBackend:
         dx = torch.empty_like(x)
         dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
-        _check(self.lib.sr_bn_act_bwd(_ptr(gy), _ptr(x), _dt(x), n * h * w, c, _ptr(save), float(slope), _ptr(dx), _ptr(dgamma),
-                                      _ptr(dbeta), _stream()), "bn_act_bwd")
+        self._timed_rec("bn_act_bwd", 0.0, 5.0 * x.numel() * x.element_size(), lambda: _check(
+            self.lib.sr_bn_act_bwd(_ptr(gy), _ptr(x), _dt(x), n * h * w, c, _ptr(save), float(slope), _ptr(dx), _ptr(dgamma),
+                                   _ptr(dbeta), _stream()), "bn_act_bwd"))
         return dx, dgamma, dbeta
 
     def bn_act_bwd_bwd(self, u, gy, x, save, dgamma, dbeta, slope):

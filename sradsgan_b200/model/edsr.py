@@ -164,7 +164,8 @@ class EDSR(SRADSGAN):
 
     def _capture(self, imgs_lr, imgs_hr, key):
         world = dp.world_size()
-        st = {"key": key, "lr": torch.empty_like(imgs_lr), "hr": torch.empty_like(imgs_hr)}
+        st = {"key": key, "lr": torch.empty(imgs_lr.shape, dtype=torch.float32, device=self.device),
+              "hr": torch.empty(imgs_hr.shape, dtype=torch.float32, device=self.device)}
         st["lr"].copy_(imgs_lr); st["hr"].copy_(imgs_hr)
         oG = self.optimizer_G
         state = [oG.flat_param, oG.exp_avg, oG.exp_avg_sq, oG.step_t]

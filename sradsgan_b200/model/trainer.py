@@ -273,9 +273,10 @@ class SRADSGAN(object):
         g["graphs"][2].replay()
 
     def _capture(self, imgs_lr, imgs_hr, key):
-        dev = imgs_lr.device
+        dev = self.device                 # the batch may still be in (pinned) host memory: the static inputs live on the device
         world = dp.world_size()
-        st = {"key": key, "lr": torch.empty_like(imgs_lr), "hr": torch.empty_like(imgs_hr),
+        st = {"key": key, "lr": torch.empty(imgs_lr.shape, dtype=torch.float32, device=dev),
+              "hr": torch.empty(imgs_hr.shape, dtype=torch.float32, device=dev),
               "alpha": torch.empty(imgs_hr.size(0), 1, 1, 1, device=dev),
               "alpha_host": [torch.empty(imgs_hr.size(0), 1, 1, 1).pin_memory() for _ in range(2)],
               "alpha_evt": [torch.cuda.Event(), torch.cuda.Event()]}

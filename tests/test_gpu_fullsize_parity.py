@@ -1,0 +1,329 @@
+"""GPU: parity AT THE BENCHMARKED CONFIGURATION (BASELINE.json configs[1]: full 12x3 generator + discriminator + VGG19[:12],
+batch 16, LR 54^2 / HR 216^2) of what bench.py times — `SRADSGAN.graphed_step` (CUDA-graph replay, side-stream weight gradients,
+batched weight re-packing) — against `oracle.train_step` (reference model/sradsgan.py:829-892, :595-641) on the same seeded
+inputs, weights and GP interpolation factors; plus x9 tiles at the bench's tile size (SGAM flash kernels at N = 16 384),
+`tiled_forward` per tile against the ORACLE, and `mfe_test_single`'s uint8 image (reference :1603-1640).
+
+Tolerances are the north star's: per-layer relative L2 error <= 1e-2 (bf16 mode) / <= 1e-4 (fp32 mode), generator-output PSNR
+within 0.01 dB.  Every measured error is also written to gpurun_out/parity_fullsize_<mode>.txt."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sradsgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+B, SCALE, HR = 16, 4, 216
+NP_SEED = 4242
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _args(**kw):
+    base = dict(model_name="SRADSGAN", train_dataset=[], test_dataset=[], crop_size=HR, test_crop_size=HR, hr_height=HR,
+                hr_width=HR, num_threads=0, num_channels=3, scale_factor=SCALE, epoch=0, num_epochs=1, save_epochs=1,
+                batch_size=B, test_batch_size=1, lr=2e-4, b1=0.9, b2=0.999, data_dir="", root_dir="", save_dir="/tmp/sr_full",
+                gpu_mode=True, n_cpu=0, sample_interval=1000, clip_value=0.01, lambda_gp=10, gp=True, penalty_type="LS",
+                grad_penalty_Lp_norm="L2", relativeGan=False, loss_Lp_norm="L1", weight_gan=1e-3, weight_content=1e-2,
+                max_train_samples=10, precision="bf16", seed=0)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def _states():
+    """the weights of SURVEY.md §8(d): reference init N(0, 0.02) for G and D (`weights_init_normal`), CGAM / SGAM gamma = 0.5 so
+    the global attention is exercised, seeded default-scale VGG19[:12]"""
+    G = O.tie_upsampling(O.make_state(O.generator_spec(SCALE), seed=0, init="ref", gamma=0.5))
+    D = O.make_state(O.discriminator_spec(), seed=1, init="ref")
+    V = O.make_state(O.vgg_spec(), seed=2, init="fan")
+    return G, D, V
+
+
+@pytest.fixture(scope="module")
+def oracle_step():
+    """ONE oracle iteration at the bench configuration (a few seconds on the box's host cores), shared by both modes."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    G, D, V = _states()
+    lr, hr = O.synthetic_batch(B, SCALE, HR, seed=1234)
+    taps = {}
+    with torch.no_grad():
+        y0 = O.generator_forward(G, lr, SCALE, taps=taps)
+        d_taps = {}
+        Dfwd = {k: v.clone() for k, v in D.items()}
+        d_out = O.discriminator_forward(Dfwd, hr, update_stats=False, taps=d_taps)
+        feat = O.vgg_features(V, hr)
+    np.random.seed(NP_SEED)
+    alpha = torch.from_numpy(np.random.random((B, 1, 1, 1))).float()
+    st = O.TrainState(G, D, V, SCALE)
+    out = O.train_step(st, lr, hr, alpha)
+    return {"lr": lr, "hr": hr, "taps": taps, "y0": y0, "d_taps": d_taps, "d_out": d_out, "feat": feat, "out": out,
+            "G_after": G, "D_after": D}
+
+
+def _build(prec):
+    from sradsgan_b200 import ops
+    from sradsgan_b200.model.sradsgan import SRADSGAN
+    G, D, V = _states()
+    net = SRADSGAN(_args(vgg_state=V, precision=prec))
+    net.build(init=False)
+    net.generator.load_state_dict(G, strict=True)
+    net.discriminator.load_state_dict(D, strict=True)
+    ops.bump_weight_generation()
+    return net, G, D
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_graphed_training_step_at_bench_config_vs_oracle(oracle_step, prec):
+    from sradsgan_b200 import ops
+    prev = ops.config.compute_dtype
+    rep, bad = [], []
+
+    def check(cond, msg):
+        if not cond:
+            bad.append(str(msg))
+
+    try:
+        net, G0, D0 = _build(prec)
+        tol = TOL[prec]
+        ref = oracle_step
+        lr, hr = ref["lr"].cuda(), ref["hr"].cuda()
+
+        # ---- per-layer taps of the generator forward at B=16 / 54^2 (the shapes every tile / wave decision is made for) ----
+        names = {"MSB": "MSB", "conv1": "conv1", "GAB_UP.ca": "GAB_UP.ca", "GAB_UP.sa": "GAB_UP.sa"}
+        for gi, grp in enumerate(net.generator.res_groups):
+            names["res_groups.%d" % gi] = "res_groups.%d" % gi
+            for bi in range(len(grp.RG)):
+                names["res_groups.%d.RG.%d" % (gi, bi)] = "res_groups.%d.RG.%d" % (gi, bi)
+        got, hooks = {}, []
+        for mname, mod in net.generator.named_modules():
+            if mname in names:
+                hooks.append(mod.register_forward_hook(lambda m, i, o, k=names[mname]: got.__setitem__(k, rel(o.float(), ref["taps"][k]))))
+        hooks.append(net.generator.GAB_UP.register_forward_pre_hook(lambda m, i: got.__setitem__("out_all", rel(i[0].float(), ref["taps"]["out_all"]))))
+        with torch.no_grad():
+            y0 = net.generator(lr).float()
+        for h in hooks:
+            h.remove()
+        worst = max((v, k) for k, v in got.items())
+        rep.append("generator taps (%d): worst %.3e at %s; output %.3e" % (len(got), worst[0], worst[1], rel(y0, ref["y0"])))
+        check(worst[0] < tol, "per-layer error %g at %s" % worst)
+        check(rel(y0, ref["y0"]) < tol, 'rel(y0, ref["y0"]) < tol')
+        check(abs(O.psnr(y0.cpu(), ref["hr"]) - O.psnr(ref["y0"], ref["hr"])) < 0.01, 'abs(O.psnr(y0.cpu(), ref["hr"]) - O.psnr(ref["y0"], ref["hr"])) < 0.01')
+
+        # ---- discriminator block outputs / VGG features at B=16, 216^2 (BatchNorm over 16 x H x W samples) ----
+        D = net.discriminator
+        D.block_taps = {}
+        conv_out = {}
+        hooks = [m.register_forward_hook(lambda mod, i, o, k=int(n): conv_out.__setitem__(k, o.detach())) for n, m in D.model.named_children()
+                 if type(m).__name__ == "Conv2d"]
+        bufs = {k: v.clone() for k, v in D.state_dict().items() if "running" in k or "tracked" in k}
+        with torch.no_grad():
+            d_out = D(hr).float()
+        for h in hooks:
+            h.remove()
+        block_taps, D.block_taps = D.block_taps, None
+        D.load_state_dict(bufs, strict=False)                      # the probe forward must not advance the running statistics
+        d_err = {}
+        lay = O.discriminator_layout()
+        for li, l in enumerate(lay):
+            if l[0] == "lrelu":
+                prev_l = lay[li - 1]
+                idx = prev_l[1] + 1                                # Sequential index of this LeakyReLU
+                if idx in block_taps:
+                    d_err["block@%d" % idx] = rel(block_taps[idx].float(), F.leaky_relu(ref["d_taps"]["model.%d" % prev_l[1]], 0.2))
+            elif l[0] == "conv" and l[1] in conv_out:
+                d_err["conv@%d" % l[1]] = rel(conv_out[l[1]].float(), ref["d_taps"]["model.%d" % l[1]])
+            elif l[0] in ("ca", "sa") and l[1] in block_taps:
+                d_err["%s@%d" % (l[0], l[1])] = rel(block_taps[l[1]].float(), ref["d_taps"]["model.%d" % l[1]])
+        d_err["out"] = rel(d_out, ref["d_out"])
+        worst = max((v, k) for k, v in d_err.items())
+        rep.append("discriminator taps (%d): worst %.3e at %s; %s" % (len(d_err), worst[0], worst[1],
+                                                                     " ".join("%s=%.1e" % kv for kv in sorted(d_err.items()))))
+        check(len(d_err) >= 18, 'len(d_err) >= 18')
+        check(worst[0] < tol, "discriminator per-layer error %g at %s" % worst)
+        with torch.no_grad():
+            f = net.feature_extractor(hr).float()
+        rep.append("vgg features: %.3e" % rel(f, ref["feat"]))
+        check(rel(f, ref["feat"]) < tol, 'rel(f, ref["feat"]) < tol')
+
+        # ---- the iteration bench.py times: graph replay ----
+        np.random.seed(NP_SEED)
+        out = net.graphed_step(lr, hr)
+        torch.cuda.synchronize()
+        assert net._graph is not None and net._graph["launches"] > 0
+        want = ref["out"]
+        gen = out["gen_hr"].float()
+        rep.append("gen_hr: %.3e, dPSNR %.5f dB" % (rel(gen, want["gen_hr"]), abs(O.psnr(gen.cpu(), ref["hr"]) - O.psnr(want["gen_hr"], ref["hr"]))))
+        check(rel(gen, want["gen_hr"]) < tol, 'rel(gen, want["gen_hr"]) < tol')
+        check(abs(O.psnr(gen.cpu(), ref["hr"]) - O.psnr(want["gen_hr"], ref["hr"])) < 0.01, 'abs(O.psnr(gen.cpu(), ref["hr"]) - O.psnr(want["gen_hr"], ref["hr"])) < 0.01')
+        ltol = {"fp32": 2e-4, "bf16": 1e-2}[prec]
+        for k in ("loss_G", "loss_D", "pixel", "content", "adv", "gp"):
+            e = abs(out[k].item() - want[k]) / max(abs(want[k]), 1e-3)
+            rep.append("%-8s got % .6e want % .6e rel %.2e" % (k, out[k].item(), want[k], e))
+            check(e < ltol, (k, out[k].item(), want[k]))
+
+        # ---- the same numbers as recorded from the UNMODIFIED reference (oracle/make_golden.py --fullsize) ----
+        from oracle.make_golden import summarize
+        gold = torch.load(os.path.join(ROOT, "tests", "golden", "sradsgan_fullsize_golden.pt"), weights_only=False)["step"]
+        for k in ("loss_G", "loss_D", "pixel", "content", "adv", "gp"):
+            check(abs(out[k].item() - gold[k]) / max(abs(gold[k]), 1e-3) < ltol, ("reference golden", k, out[k].item(), gold[k]))
+        sm = summarize(gen.cpu(), gold["gen_hr"]["samples"].numel())
+        e = abs(sm["norm"] - gold["gen_hr"]["norm"]) / gold["gen_hr"]["norm"]
+        rep.append("gen_hr norm vs the reference's recorded norm: rel %.2e; PSNR vs reference %.5f dB" % (e, abs(O.psnr(gen.cpu(), ref["hr"]) - gold["psnr_vs_hr"])))
+        check(e < tol, "gen_hr norm vs reference golden")
+        check(abs(O.psnr(gen.cpu(), ref["hr"]) - gold["psnr_vs_hr"]) < 0.01, "PSNR vs reference golden")
+
+        # ---- gradients of the step, per parameter (left in the flat buffers by the replay) ----
+        for tag, opt, ref_sd in (("G", net.optimizer_G, ref["G_after"]), ("D", net.optimizer_D, ref["D_after"])):
+            errs = []
+            for n, p in zip(opt.names, opt.params):
+                if n in O.NOISE_GRAD_KEYS:
+                    continue
+                errs.append((rel(p.grad, ref_sd[n].grad), n))
+            errs.sort(reverse=True)
+            med = errs[len(errs) // 2][0]
+            rep.append("%s gradients (%d tensors): worst %.3e at %s, median %.3e; top5 %s" % (
+                tag, len(errs), errs[0][0], errs[0][1], med, " ".join("%s=%.1e" % (n, e) for e, n in errs[:5])))
+            gtol = {"fp32": 2e-3, "bf16": 5e-2}[prec]
+            check(errs[0][0] < gtol, "%s gradient error %g at %s" % (tag, errs[0][0], errs[0][1]))
+            check(med < {"fp32": 2e-4, "bf16": 1e-2}[prec], "%s median gradient error %g" % (tag, med))
+
+        # ---- state after the step: D's BatchNorm buffers (4 train-mode forwards), parameters ----
+        dsd = net.discriminator.state_dict()
+        for k, v in ref["D_after"].items():
+            if "running" in k:
+                e = rel(dsd[k].float(), v)
+                check(e < tol, (k, e))
+            elif k.endswith("num_batches_tracked"):
+                check(int(dsd[k]) == int(v) == 4, 'int(dsd[k]) == int(v) == 4')
+        rep.append("D BatchNorm running statistics: within %.0e" % tol)
+        gsd = net.generator.state_dict()
+        upd = []
+        for k, v in ref["G_after"].items():
+            if k in O.NOISE_GRAD_KEYS or k.endswith("gamma"):
+                continue
+            d_ref = (v.detach() - G0[k]).flatten()
+            d_got = (gsd[k].float().cpu() - G0[k]).flatten()
+            # step 1 of Adam moves every element by ~lr * sign(grad): count the elements that moved the same way
+            agree = ((d_ref * d_got) > 0).float().mean().item()
+            upd.append((agree, k))
+        upd.sort()
+        rep.append("G parameters after Adam: update-direction agreement min %.4f (%s), mean %.5f" % (upd[0][0], upd[0][1], float(np.mean([u[0] for u in upd]))))
+        check(np.mean([u[0] for u in upd]) > {"fp32": 0.999, "bf16": 0.98}[prec], "Adam update-direction agreement")
+        if prec == "fp32":
+            worst = max((rel(gsd[k].float(), v.detach()), k) for k, v in ref["G_after"].items() if k not in O.NOISE_GRAD_KEYS)
+            rep.append("G parameters after Adam (fp32 mode): worst rel %.3e at %s" % worst)
+            check(worst[0] < 2e-3, 'worst[0] < 2e-3')
+    finally:
+        ops.config.compute_dtype = prev
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_fullsize_%s.txt" % prec), "w") as fh:
+            fh.write("\n".join(rep) + "\n")
+        print("\n".join(rep))
+    assert not bad, "; ".join(bad)
+
+
+def test_x9_tiles_vs_oracle_with_flash_sgam():
+    """BASELINE.json configs[3] at the bench's tile size: the x9 generator on 128^2 LR tiles (SGAM flash kernels over
+    N = 16 384 tokens; the reference materialises a 1 GiB attention matrix for the same tile) and `tiled_forward` over a
+    144x128 image whose two tiles are each compared with the ORACLE run on that tile."""
+    from sradsgan_b200 import ops
+    from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup
+    from sradsgan_b200.model.trainer import tiled_forward, tile_starts
+    prev = ops.config.compute_dtype
+    ops.set_precision("bf16")
+    try:
+        torch.set_num_threads(os.cpu_count() or 1)
+        scale, tile, ov = 9, 128, 16
+        sd = O.tie_upsampling(O.make_state(O.generator_spec(scale), seed=3, init="ref", gamma=0.5))
+        Gn = GeneratorResNet(ResGroup, upscale_factor=scale)
+        Gn.load_state_dict(sd, strict=True)
+        Gn.cuda().eval()
+        x = torch.rand(1, 3, 144, 128, generator=torch.Generator().manual_seed(11))
+        ys = tile_starts(144, tile, ov)
+        assert ys == [0, 16]
+        with torch.no_grad():
+            full = tiled_forward(Gn, x.cuda(), scale, tile, ov).float().cpu()
+            refs = [O.generator_forward(sd, x[:, :, y0:y0 + tile, :], scale) for y0 in ys]
+            alone = Gn(x[:, :, :tile, :].cuda().contiguous()).float().cpu()
+        e_tile = rel(alone, refs[0])
+        # rows owned by exactly one tile: [0, 16) LR rows by tile 0, [128, 144) by tile 1
+        e_top = rel(full[:, :, :16 * scale], refs[0][:, :, :16 * scale])
+        e_bot = rel(full[:, :, 128 * scale:], refs[1][:, :, (128 - 16) * scale:])
+        # the overlap (LR rows 16..128) is a convex combination of the two tiles' outputs
+        lo = torch.minimum(refs[0][:, :, 16 * scale:], refs[1][:, :, :(128 - 16) * scale])
+        hi = torch.maximum(refs[0][:, :, 16 * scale:], refs[1][:, :, :(128 - 16) * scale])
+        mid = full[:, :, 16 * scale:128 * scale]
+        slack = 1e-2 * refs[0].abs().mean()
+        inside = ((mid >= lo - slack) & (mid <= hi + slack)).float().mean().item()
+        msg = "x9 128^2 tile vs oracle %.3e; tiled: top %.3e bottom %.3e; blended inside [lo, hi]: %.5f" % (e_tile, e_top, e_bot, inside)
+        print(msg)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", "parity_x9_tiles.txt"), "w").write(msg + "\n")
+        assert e_tile < 1e-2 and e_top < 1e-2 and e_bot < 1e-2
+        assert inside > 0.999
+    finally:
+        ops.config.compute_dtype = prev
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_mfe_test_single_uint8_vs_oracle(tmp_path, prec):
+    """reference :1603-1640: CenterCrop -> batch_size identical copies -> G -> save_img1 (truncating uint8).  The saved image
+    == quantize_u8(oracle): fp32 mode bit-exact up to a handful of pixels sitting on a grey-level boundary, bf16 mode within
+    one grey level; the mismatch counts are written to gpurun_out/."""
+    from PIL import Image
+    import torchvision.transforms as T
+    from sradsgan_b200 import ops
+    from sradsgan_b200.model.sradsgan import SRADSGAN
+    prev = ops.config.compute_dtype
+    try:
+        rs = np.random.RandomState(7)
+        # smooth synthetic image (random low-frequency field): generator outputs spread over many grey levels
+        base = torch.from_numpy(rs.rand(1, 3, 9, 9)).float()
+        img = F.interpolate(base, size=(80, 80), mode="bicubic", align_corners=False).clamp(0, 1)[0]
+        arr = (img.permute(1, 2, 0).numpy() * 255).astype(np.uint8)
+        fn = str(tmp_path / "tile.tif")
+        Image.fromarray(arr).save(fn)
+        x = T.Compose([T.CenterCrop(64), T.ToTensor()])(Image.open(fn))
+        sd = O.tie_upsampling(O.make_state(O.generator_spec(4), seed=21, init="ref", gamma=0.5))
+        # the N(0, 0.02) init yields ~1e-3 outputs: rescale the (linear) output conv so that the SR image spreads over the grey
+        # levels around 0.5 instead of truncating to one value
+        with torch.no_grad():
+            y_raw = O.generator_forward(sd, x[None], 4)[0]
+        a = 0.2 / y_raw.std().item()
+        sd["conv3.0.weight"] = sd["conv3.0.weight"] * a
+        sd["conv3.0.bias"] = sd["conv3.0.bias"] * a + (0.5 - a * y_raw.mean().item())
+        mp = str(tmp_path / "g.pkl")
+        torch.save(sd, mp)
+        net = SRADSGAN(_args(precision=prec, test_crop_size=64, batch_size=2, save_dir=str(tmp_path / "out")))
+        out = net.mfe_test_single(fn, modelpath=mp)
+        assert tuple(out.shape) == (3, 256, 256)
+        with torch.no_grad():
+            y = O.generator_forward(sd, x[None], 4)[0]
+        want = O.quantize_u8(y)
+        got = np.asarray(Image.open(str(tmp_path / "out" / "SR_SRADSGAN_tile.tif")))
+        assert got.shape == want.shape == (256, 256, 3)
+        diff = np.abs(got.astype(int) - want.astype(int))
+        mism, mx = int((diff > 0).sum()), int(diff.max())
+        levels = len(np.unique(want))
+        msg = "mfe_test_single %s: %d of %d uint8 values differ from quantize_u8(oracle) (max |diff| %d, %d distinct grey levels)" % (
+            prec, mism, got.size, mx, levels)
+        print(msg)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", "parity_mfe_test_single_%s.txt" % prec), "w").write(msg + "\n")
+        assert levels > 20
+        if prec == "fp32":
+            assert mx <= 1 and mism <= got.size // 2000          # only values within 1e-4 relative of a grey-level boundary may flip
+        else:
+            assert mx <= 3            # bf16 mode: ~1e-2 relative error of a signal spanning ~100 grey levels; the count is reported
+    finally:
+        ops.config.compute_dtype = prev

@@ -99,3 +99,36 @@ def test_two_training_iterations_golden(golden):
                 continue
             got = summarize(D[k].grad, 8)
             assert abs(got["norm"] - w["norm"]) <= 2e-3 * max(1e-7, w["norm"]), (it, k)
+
+
+def test_full_size_iteration_golden():
+    """the oracle at the BENCHMARKED configuration (full 12x3 G + D + VGG19[:12], batch 16, LR 54^2 / HR 216^2) == one
+    iteration of the unmodified reference recorded by `python -m oracle.make_golden --fullsize` (≈40 s of CPU work): losses,
+    generator-output PSNR, gradients and post-step parameters.  The GPU suite holds `graphed_step` to the same numbers."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sradsgan_fullsize_golden.pt"), weights_only=False)
+    c, want = g["cfg"], g["step"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    G = O.tie_upsampling(O.make_state(O.generator_spec(c["scale"]), seed=c["gseed"], init="ref", gamma=c["gamma"]))
+    D = O.make_state(O.discriminator_spec(), seed=c["dseed"], init="ref")
+    V = O.make_state(O.vgg_spec(), seed=c["vseed"], init="fan")
+    lr, hr = O.synthetic_batch(c["batch"], c["scale"], c["hr"], seed=c["data_seed"])
+    st = O.TrainState(G, D, V, c["scale"])
+    np.random.seed(c["np_seed"])
+    alpha = torch.from_numpy(np.random.random((c["batch"], 1, 1, 1))).float()
+    rec = O.train_step(st, lr, hr, alpha)
+    for k in ("loss_G", "loss_D", "pixel", "content", "adv", "gp"):
+        assert abs(rec[k] - want[k]) <= 1e-5 * max(1.0, abs(want[k])), (k, rec[k], want[k])
+    _close_summary(rec["gen_hr"], want["gen_hr"], rtol=1e-5)
+    assert abs(O.psnr(rec["gen_hr"], hr) - want["psnr_vs_hr"]) < 1e-4
+    for k, w in want["G_grads"].items():
+        if k not in O.NOISE_GRAD_KEYS and k in G:
+            got = summarize(G[k].grad, 8)
+            assert abs(got["norm"] - w["norm"]) <= 1e-3 * max(1e-12, w["norm"]), k
+    for k, w in want["D_grads"].items():
+        if k not in O.NOISE_GRAD_KEYS:
+            got = summarize(D[k].grad, 8)
+            assert abs(got["norm"] - w["norm"]) <= 2e-3 * max(1e-12, w["norm"]), k
+    for k, w in want["D_state"].items():
+        if "running" in k:
+            _close_summary(D[k].float(), w, rtol=1e-5)
