@@ -185,6 +185,50 @@ int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float lr, float beta1, float beta2, float eps, int step, const int32_t* step_dev,
                  float grad_scale, float clamp_lo, float clamp_hi, void* stream);
 
+/* CGAM, the channel global attention of GAB_UP (model/sradsgan.py:178-213, light=False; C = 64), fp32 throughout:
+ * y = gamma * (softmax_j(max_j E_ij - E_ij) X) + x with E = X X^T the 64 x 64 gram over the P pixels of each image.
+ * x, y32, dy, dx: [N][P][64] fp32 NHWC; y16 (nullable): the same values in y16_dtype for the next convolutions;
+ * A [N][64][64]: the attention, written by _fwd and read by _bwd; gamma: DEVICE fp32 scalar; dgamma[0] (+)= its gradient
+ * (accumulate != 0 adds).  workspace >= sr_cgam_workspace_bytes(N, P).  Replaces torch.bmm x2 / max / softmax (+ autograd). */
+size_t sr_cgam_workspace_bytes(int N, int P);
+int sr_cgam_fwd(const float* x, const float* gamma, int N, int P, float* y32, void* y16, int y16_dtype, float* A, void* workspace,
+                void* stream);
+int sr_cgam_bwd(const float* dy, const float* x, const float* A, const float* gamma, int N, int P, float* dx, float* dgamma,
+                int accumulate, void* workspace, void* stream);
+
+/* ---- loss reductions and elementwise glue of one iteration (csrc/losses.cu) --------------------------------------------
+ * Reductions are deterministic (per-block partials, the last block adds them in a fixed order) and need a caller-owned
+ * workspace of sr_reduce_workspace_bytes() bytes that was ZERO when first used (every launch re-arms it) and is used by one
+ * stream at a time.  `out` / `g` are DEVICE fp32 scalars; nothing synchronises.
+ *
+ * sr_diff_mean_fwd: out[0] = mean |a - b|^p, p = 1 (nn.L1Loss) or 2 (nn.MSELoss) — criterion_content of
+ *   model/sradsgan.py:685-688 applied to (gen_hr, imgs_hr) :834 and to the VGG19 features :838.  a: n elements, NHWC;
+ *   b: the same layout, or (b_nchw_C > 0) an NCHW tensor with b_nchw_C channels and b_HW pixels per plane (the HR batch as the
+ *   host framework holds it).  sr_diff_mean_bwd: da[i] = g[0] * scale * d(mean|a-b|^p)/da[i]  (sign(0) = 0). */
+size_t sr_reduce_workspace_bytes(void);
+int sr_diff_mean_fwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, int p, int b_nchw_C, int64_t b_HW,
+                     float* out, void* workspace, void* stream);
+int sr_diff_mean_bwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, int p, int b_nchw_C, int64_t b_HW,
+                     const float* g, float scale, void* da, int da_dtype, void* stream);
+/* out[0] = scale * mean(x): GANLoss('wgan-gp') (:46-52; scale = -1 for real targets);  dx[i] = g[0] * scale / n. */
+int sr_mean_fwd(const void* x, int dtype, int64_t n, float scale, float* out, void* workspace, void* stream);
+int sr_mean_bwd(const float* g, float scale, int64_t n, void* dx, int dtype, void* stream);
+/* WGAN-GP penalty (:623-637): grad [pixels][C] (NHWC view of the B x C x H x W input gradient, C <= 4), per-pixel norm over
+ * the C colour channels (norm 0 = L2, 1 = L1, 2 = Linf), penalty 0 = 'LS' (n-1)^2 or 1 = 'hinge' relu(n-1), mean over pixels.
+ * _bwd: dgrad = g[0] * scale * d(penalty)/d(grad) — the cotangent that enters the double backward through D (:639,:886). */
+int sr_gp_penalty_fwd(const void* grad, int dtype, int64_t pixels, int C, int norm, int penalty, float* out, void* workspace,
+                      void* stream);
+int sr_gp_penalty_bwd(const void* grad, int dtype, int64_t pixels, int C, int norm, int penalty, const float* g, float scale,
+                      void* dgrad, int out_dtype, void* stream);
+/* out (NHWC) = alpha[n] * real + (1 - alpha[n]) * fake: the WGAN-GP interpolates (:611).  n elements, per_image elements per
+ * sample; real is NHWC, or NCHW with real_nchw_C channels / HW pixels per plane when real_nchw_C > 0; fake is NHWC. */
+int sr_lerp_nhwc(const void* real, int real_dtype, int real_nchw_C, const void* fake, int fake_dtype, const float* alpha, int64_t n,
+                 int64_t per_image, int64_t HW, void* out, int out_dtype, void* stream);
+/* x: NCHW fp32 [N][C][HW] (C <= 4, the batch as the data loader delivers it, :821-823) -> out: NHWC [N][HW][C] in out_dtype. */
+int sr_nchw_to_nhwc(const float* x, int64_t N, int C, int64_t HW, void* out, int out_dtype, void* stream);
+/* out = a + b elementwise (b may be NULL: a cast), independent dtypes — sums of gradient branches of different precision. */
+int sr_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, void* out, int out_dtype, void* stream);
+
 /* Diagnostics (not on the product path): D[128][64] (fp32) = A_view * B^T on tcgen05, where A is a
  * [rows_a][64] bf16 matrix staged by TMA with the 128-byte swizzle and A_view row r is smem row
  * shift_rows + (r/8)*(sbo_bytes/128) + r%8 — probes which shared-memory operand descriptors the tensor core

@@ -206,6 +206,89 @@ class EmuBackend:
         cl = lambda t: t.to(x.dtype).contiguous(memory_format=torch.channels_last)
         return cl(d_gy), cl(d_x), d_gamma
 
+    # -- loss reductions / glue (csrc/losses.cu) ------------------------------------------------------
+    def diff_mean(self, a, b, p):
+        self.launches += 1
+        d = a.float() - b.float()
+        return (d.abs() if p == 1 else d * d).mean()
+
+    def diff_mean_bwd(self, a, b, p, g, scale=1.0):
+        self.launches += 1
+        d = a.float() - b.float()
+        k = g.float() * scale / a.numel()
+        r = torch.sign(d) * k if p == 1 else 2.0 * d * k
+        return r.to(a.dtype)
+
+    def mean(self, x, scale=1.0):
+        self.launches += 1
+        return x.float().mean() * scale
+
+    def mean_bwd(self, g, scale, like):
+        self.launches += 1
+        return torch.full_like(like, 1.0) * (g.float() * scale / like.numel()).to(like.dtype)
+
+    @staticmethod
+    def _gp_math(grad, norm, penalty):
+        g = grad.float()
+        n = g.norm(2, 1) if norm == 0 else (g.norm(1, 1) if norm == 1 else g.abs().max(1)[0])
+        return ((n - 1) ** 2 if penalty == 0 else torch.relu(n - 1)).mean()
+
+    def gp_penalty(self, grad, norm, penalty):
+        self.launches += 1
+        with torch.no_grad():
+            return self._gp_math(grad, norm, penalty)
+
+    def gp_penalty_bwd(self, grad, norm, penalty, g, scale=1.0):
+        self.launches += 1
+        with torch.enable_grad():
+            gr = grad.detach().float().requires_grad_(True)
+            (d,) = torch.autograd.grad(self._gp_math(gr, norm, penalty), gr)
+        return (d * (g.float() * scale)).to(grad.dtype).contiguous(memory_format=torch.channels_last)
+
+    def lerp(self, real, fake, alpha, out_dtype):
+        self.launches += 1
+        a = alpha.float().view(-1, 1, 1, 1)
+        return (a * real.float() + ((1 - a) * fake.float())).to(out_dtype).contiguous(memory_format=torch.channels_last)
+
+    def nchw_to_nhwc(self, x, out_dtype):
+        self.launches += 1
+        return x.to(out_dtype).contiguous(memory_format=torch.channels_last)
+
+    def add_cast(self, a, b, out_dtype):
+        self.launches += 1
+        r = a.float() if b is None else a.float() + b.float()
+        return r.to(out_dtype)
+
+    # -- CGAM (csrc/cgam.cu): the oracle's formula + torch autograd ----------------------------------------
+    @staticmethod
+    def _cgam_math(x, gamma):
+        b, c, h, w = x.shape
+        q = x.reshape(b, c, -1)
+        e = torch.bmm(q, q.permute(0, 2, 1))
+        att = torch.softmax(torch.max(e, -1, keepdim=True)[0].expand_as(e) - e, dim=-1)
+        return gamma * torch.bmm(att, q).reshape(b, c, h, w) + x, att
+
+    def cgam_fwd(self, x, gamma, lowp_dtype=None):
+        self.launches += 3
+        with torch.no_grad():
+            y, att = self._cgam_math(x.float().contiguous(), gamma.detach().float())
+        y32 = y.contiguous(memory_format=torch.channels_last)
+        y16 = y32.to(lowp_dtype) if lowp_dtype is not None and lowp_dtype != torch.float32 else None
+        return y32, y16, att
+
+    def cgam_bwd(self, dy, x, A, gamma, dgamma_into=None):
+        self.launches += 3
+        with torch.enable_grad():
+            xs = x.detach().float().contiguous().requires_grad_(True)
+            gs = gamma.detach().float().clone().requires_grad_(True)
+            y, _ = self._cgam_math(xs, gs)
+            dx, dg = torch.autograd.grad(y, [xs, gs], dy.float())
+        dx = dx.contiguous(memory_format=torch.channels_last)
+        if dgamma_into is not None:
+            dgamma_into.add_(dg.reshape(dgamma_into.shape))
+            return dx, None
+        return dx, dg.reshape(1)
+
     def colsum(self, x2d, want_sq=False):
         self.launches += 1
         f = x2d.float()

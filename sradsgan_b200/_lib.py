@@ -21,6 +21,8 @@ EXPORTS = [
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
     "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate", "sr_set_workspace",
     "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep", "sr_pack_weights_batched", "sr_maxpool2x2_fwd", "sr_maxpool2x2_bwd",
+    "sr_reduce_workspace_bytes", "sr_diff_mean_fwd", "sr_diff_mean_bwd", "sr_mean_fwd", "sr_mean_bwd", "sr_gp_penalty_fwd", "sr_gp_penalty_bwd",
+    "sr_lerp_nhwc", "sr_nchw_to_nhwc", "sr_add_cast", "sr_cgam_workspace_bytes", "sr_cgam_fwd", "sr_cgam_bwd",
 ]
 
 
@@ -94,6 +96,24 @@ def load():
     lib.sr_sgam_ds.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.sr_sgam_bwd_prep.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     for name in ("sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep"):
+        getattr(lib, name).restype = i32
+    lib.sr_reduce_workspace_bytes.restype = ctypes.c_size_t
+    lib.sr_reduce_workspace_bytes.argtypes = []
+    lib.sr_diff_mean_fwd.argtypes = [vp, i32, vp, i32, i64, i32, i32, i64, vp, vp, vp]
+    lib.sr_diff_mean_bwd.argtypes = [vp, i32, vp, i32, i64, i32, i32, i64, vp, f32, vp, i32, vp]
+    lib.sr_mean_fwd.argtypes = [vp, i32, i64, f32, vp, vp, vp]
+    lib.sr_mean_bwd.argtypes = [vp, f32, i64, vp, i32, vp]
+    lib.sr_gp_penalty_fwd.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp]
+    lib.sr_gp_penalty_bwd.argtypes = [vp, i32, i64, i32, i32, i32, vp, f32, vp, i32, vp]
+    lib.sr_lerp_nhwc.argtypes = [vp, i32, i32, vp, i32, vp, i64, i64, i64, vp, i32, vp]
+    lib.sr_nchw_to_nhwc.argtypes = [vp, i64, i32, i64, vp, i32, vp]
+    lib.sr_add_cast.argtypes = [vp, i32, vp, i32, i64, vp, i32, vp]
+    lib.sr_cgam_workspace_bytes.restype = ctypes.c_size_t
+    lib.sr_cgam_workspace_bytes.argtypes = [i32, i32]
+    lib.sr_cgam_fwd.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp, vp]
+    lib.sr_cgam_bwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, vp]
+    for name in ("sr_diff_mean_fwd", "sr_diff_mean_bwd", "sr_mean_fwd", "sr_mean_bwd", "sr_gp_penalty_fwd", "sr_gp_penalty_bwd", "sr_lerp_nhwc",
+                 "sr_nchw_to_nhwc", "sr_add_cast", "sr_cgam_fwd", "sr_cgam_bwd"):
         getattr(lib, name).restype = i32
     lib.sr_set_workspace.argtypes = [vp, ctypes.c_uint64]
     lib.sr_set_workspace.restype = i32
@@ -257,12 +277,18 @@ class CudaBackend:
                                          _stream()), "conv2d_dgrad_act"))
         return dx
 
+    def _same_dtype(self, x, dy):
+        """weight-gradient operands must share a dtype: the SMALLER tensor is cast (the RGB-side fp32 input of a thin layer,
+        not the 64-channel gradient next to it)"""
+        if x.dtype == dy.dtype:
+            return x, dy
+        if x.numel() <= dy.numel():
+            return self.add_cast(x, None, dy.dtype), dy
+        return x, self.add_cast(dy, None, x.dtype)
+
     def conv_wgrad(self, x, dy, g, want_bias=True, impl=IMPL_AUTO):
         _require_cuda(x, dy)
-        x = _nhwc(x)
-        dy = _nhwc(dy)
-        if x.dtype != dy.dtype:
-            dy = dy.to(x.dtype)
+        x, dy = self._same_dtype(_nhwc(x), _nhwc(dy))
         dw = torch.empty((g.Cout, g.Cin, g.kh, g.kw), dtype=torch.float32, device=x.device)
         db = torch.empty((g.Cout,), dtype=torch.float32, device=x.device) if want_bias else None
         d = self._desc(g, _dt(x), SR_F32, impl=impl)
@@ -274,10 +300,7 @@ class CudaBackend:
     def conv_wgrad_into(self, x, dy, g, dw, db, impl=IMPL_AUTO):
         """dw (+)= wgrad, db (+)= colsum(dy): accumulate into existing fp32 buffers (FlatAdam's flat gradient views)"""
         _require_cuda(x, dy, dw)
-        x = _nhwc(x)
-        dy = _nhwc(dy)
-        if x.dtype != dy.dtype:
-            dy = dy.to(x.dtype)
+        x, dy = self._same_dtype(_nhwc(x), _nhwc(dy))
         if dw.dtype != torch.float32 or not dw.is_contiguous() or (db is not None and (db.dtype != torch.float32 or not db.is_contiguous())):
             raise ValueError("conv_wgrad_into: contiguous fp32 gradient buffers required")
         d = self._desc(g, _dt(x), SR_F32, impl=impl)
@@ -456,6 +479,162 @@ class CudaBackend:
         _check(self.lib.sr_sgam_bwd_prep(_ptr(dy), _ptr(o16), _ptr(gamma), n * h * w, _ptr(do16), _ptr(d), _ptr(dgamma), _stream()),
                "sgam_bwd_prep")
         return do16, d, dgamma
+
+    # -- loss reductions / elementwise glue (csrc/losses.cu) ---------------------------------------------
+    def reduce_ws(self, device):
+        """persistent, initially zero workspace of the deterministic reductions (every launch re-arms its ticket)"""
+        ws = getattr(self, "_reduce_ws", None)
+        if ws is None or ws.device != device:
+            ws = self._reduce_ws = torch.zeros(int(self.lib.sr_reduce_workspace_bytes()), dtype=torch.uint8, device=device)
+        return ws
+
+    @staticmethod
+    def _dense(t):
+        """(tensor, nchw_C, HW): a dense tensor as the kernels index it — NHWC / flat (nchw_C = 0) or NCHW (nchw_C = C)"""
+        if t.dim() == 4 and t.shape[1] > 1 and t.shape[2] * t.shape[3] > 1:
+            if t.is_contiguous(memory_format=torch.channels_last):
+                return t, 0, t.shape[2] * t.shape[3]
+            if t.is_contiguous():
+                return t, t.shape[1], t.shape[2] * t.shape[3]
+            return t.contiguous(memory_format=torch.channels_last), 0, t.shape[2] * t.shape[3]
+        return t.contiguous(), 0, 1
+
+    def _diff_args(self, a, b):
+        _require_cuda(a, b)
+        if a.shape != b.shape:
+            raise ValueError("diff_mean: shapes differ")
+        a, ca, hw = self._dense(a)
+        b, cb, _ = self._dense(b)
+        if ca:                                  # `a` is the tensor the gradient is written for: kept NHWC / flat
+            if cb:
+                ca = cb = 0                     # both NCHW: the same flat order
+            else:
+                a, ca = a.contiguous(memory_format=torch.channels_last), 0
+        return a, b, cb, hw
+
+    def diff_mean(self, a, b, p):
+        """mean |a - b|^p -> fp32 0-dim tensor"""
+        a, b, cb, hw = self._diff_args(a, b)
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        nbytes = float(a.numel()) * (a.element_size() + b.element_size())
+        self._timed_rec("loss_reduce", 0.0, nbytes, lambda: _check(
+            self.lib.sr_diff_mean_fwd(_ptr(a), _dt(a), _ptr(b), _dt(b), a.numel(), int(p), int(cb), int(hw), _ptr(out),
+                                      _ptr(self.reduce_ws(a.device)), _stream()), "diff_mean_fwd"))
+        return out
+
+    def diff_mean_bwd(self, a, b, p, g, scale=1.0):
+        """g * scale * d(mean|a-b|^p)/da, shaped / laid out / typed like a"""
+        a2, b2, cb, hw = self._diff_args(a, b)
+        da = torch.empty_like(a2)
+        g = g.detach().float().contiguous()
+        nbytes = float(a2.numel()) * (2 * a2.element_size() + b2.element_size())
+        self._timed_rec("loss_reduce", 0.0, nbytes, lambda: _check(
+            self.lib.sr_diff_mean_bwd(_ptr(a2), _dt(a2), _ptr(b2), _dt(b2), a2.numel(), int(p), int(cb), int(hw), _ptr(g), float(scale),
+                                      _ptr(da), _dt(da), _stream()), "diff_mean_bwd"))
+        return da
+
+    def mean(self, x, scale=1.0):
+        _require_cuda(x)
+        x, _, _ = self._dense(x)
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        _check(self.lib.sr_mean_fwd(_ptr(x), _dt(x), x.numel(), float(scale), _ptr(out), _ptr(self.reduce_ws(x.device)), _stream()), "mean_fwd")
+        return out
+
+    def mean_bwd(self, g, scale, like):
+        dx = torch.empty_like(like)
+        if not (dx.is_contiguous() or dx.is_contiguous(memory_format=torch.channels_last)):
+            dx = torch.empty(like.shape, dtype=like.dtype, device=like.device)
+        g = g.detach().float().contiguous()
+        _check(self.lib.sr_mean_bwd(_ptr(g), float(scale), dx.numel(), _ptr(dx), _dt(dx), _stream()), "mean_bwd")
+        return dx
+
+    def gp_penalty(self, grad, norm, penalty):
+        """grad: (N, C<=4, H, W) -> mean over pixels of the penalty of the per-pixel channel norm (fp32 0-dim)"""
+        _require_cuda(grad)
+        grad = _nhwc(grad)
+        n, c, h, w = grad.shape
+        out = torch.empty((), dtype=torch.float32, device=grad.device)
+        self._timed_rec("loss_reduce", 0.0, float(grad.numel()) * grad.element_size(), lambda: _check(
+            self.lib.sr_gp_penalty_fwd(_ptr(grad), _dt(grad), n * h * w, c, int(norm), int(penalty), _ptr(out),
+                                       _ptr(self.reduce_ws(grad.device)), _stream()), "gp_penalty_fwd"))
+        return out
+
+    def gp_penalty_bwd(self, grad, norm, penalty, g, scale=1.0):
+        grad = _nhwc(grad)
+        n, c, h, w = grad.shape
+        d = torch.empty_like(grad)
+        g = g.detach().float().contiguous()
+        self._timed_rec("loss_reduce", 0.0, 2.0 * grad.numel() * grad.element_size(), lambda: _check(
+            self.lib.sr_gp_penalty_bwd(_ptr(grad), _dt(grad), n * h * w, c, int(norm), int(penalty), _ptr(g), float(scale), _ptr(d), _dt(d),
+                                       _stream()), "gp_penalty_bwd"))
+        return d
+
+    def lerp(self, real, fake, alpha, out_dtype):
+        """alpha*real + (1-alpha)*fake per sample -> (N, C, H, W) NHWC in out_dtype; real may be NCHW or NHWC, fake NHWC"""
+        _require_cuda(real, fake, alpha)
+        real, cr, hw = self._dense(real)
+        fake = _nhwc(fake)
+        n = real.shape[0]
+        alpha = alpha.detach().reshape(-1).float().contiguous()
+        if alpha.numel() != n or real.shape != fake.shape:
+            raise ValueError("lerp: alpha must hold one value per sample; real and fake must have the same shape")
+        out = torch.empty(fake.shape, dtype=out_dtype, device=fake.device, memory_format=torch.channels_last)
+        _check(self.lib.sr_lerp_nhwc(_ptr(real), _dt(real), int(cr), _ptr(fake), _dt(fake), _ptr(alpha), real.numel(), real.numel() // n,
+                                     int(hw), _ptr(out), _dt(out), _stream()), "lerp_nhwc")
+        return out
+
+    def nchw_to_nhwc(self, x, out_dtype):
+        """contiguous NCHW fp32 (C <= 4) -> the same logical tensor with NHWC memory in out_dtype"""
+        _require_cuda(x)
+        n, c, h, w = x.shape
+        out = torch.empty((n, c, h, w), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+        _check(self.lib.sr_nchw_to_nhwc(_ptr(x), n, c, h * w, _ptr(out), _dt(out), _stream()), "nchw_to_nhwc")
+        return out
+
+    def add_cast(self, a, b, out_dtype):
+        """a + b (b may be None) in out_dtype; a and b dense with the same memory layout"""
+        _require_cuda(a, b)
+        if b is not None and (a.shape != b.shape or a.stride() != b.stride()):
+            b = b.contiguous(memory_format=torch.channels_last) if a.is_contiguous(memory_format=torch.channels_last) and a.dim() == 4 else b.contiguous()
+            if a.stride() != b.stride():
+                a = a.contiguous()
+                b = b.contiguous()
+        out = torch.empty_like(a, dtype=out_dtype)
+        _check(self.lib.sr_add_cast(_ptr(a), _dt(a), _ptr(b), _dt(b) if b is not None else _dt(a), a.numel(), _ptr(out), _dt(out), _stream()),
+               "add_cast")
+        return out
+
+    # -- CGAM (csrc/cgam.cu) ---------------------------------------------------------------------------
+    def cgam_fwd(self, x, gamma, lowp_dtype=None):
+        """x: (N, 64, H, W) fp32 NHWC -> (y32, y16 | None, A [N,64,64])"""
+        _require_cuda(x, gamma)
+        x = _nhwc(x.float())
+        n, c, h, w = x.shape
+        if c != 64:
+            raise ValueError("cgam: 64 channels required")
+        y32 = torch.empty_like(x)
+        y16 = torch.empty_like(x, dtype=lowp_dtype) if lowp_dtype is not None and lowp_dtype != torch.float32 else None
+        A = torch.empty((n, 64, 64), dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(self.lib.sr_cgam_workspace_bytes(n, h * w)), dtype=torch.uint8, device=x.device)
+        g = gamma.detach().float().contiguous()
+        self._timed_rec("cgam", 0.0, float(x.numel()) * (4 + 4 + 4 + (2 if y16 is not None else 0)), lambda: _check(
+            self.lib.sr_cgam_fwd(_ptr(x), _ptr(g), n, h * w, _ptr(y32), _ptr(y16), _dt(y16) if y16 is not None else SR_F32, _ptr(A),
+                                 _ptr(ws), _stream()), "cgam_fwd"))
+        return y32, y16, A
+
+    def cgam_bwd(self, dy, x, A, gamma, dgamma_into=None):
+        """-> (dx fp32 NHWC, dgamma [1] fp32 or None when accumulated into dgamma_into)"""
+        x = _nhwc(x.float())
+        dy = _nhwc(dy.float())
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x)
+        dg = dgamma_into if dgamma_into is not None else torch.empty((1,), dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(self.lib.sr_cgam_workspace_bytes(n, h * w)), dtype=torch.uint8, device=x.device)
+        g = gamma.detach().float().contiguous()
+        self._timed_rec("cgam", 0.0, float(x.numel()) * 4 * 5, lambda: _check(
+            self.lib.sr_cgam_bwd(_ptr(dy), _ptr(x), _ptr(A), _ptr(g), n, h * w, _ptr(dx), _ptr(dg), 1 if dgamma_into is not None else 0,
+                                 _ptr(ws), _stream()), "cgam_bwd"))
+        return dx, (None if dgamma_into is not None else dg)
 
     # -- reductions / optimiser ----------------------------------------------------------------
     def colsum(self, x2d, want_sq=False):

@@ -70,6 +70,22 @@ int maxpool2_bwd(const void*, const void*, int, int, int, int, int, void*, cudaS
 int colsum(const void*, int, long long, int, float*, float*, int, cudaStream_t);
 int adam_step(float*, const float*, float*, float*, long long, float, float, float, float, int, const int*, float, float, float, cudaStream_t);
 
+// cgam.cu
+size_t cgam_workspace_bytes(int, int);
+int cgam_fwd(const float*, const float*, int, int, float*, void*, int, float*, float*, cudaStream_t);
+int cgam_bwd(const float*, const float*, const float*, const float*, int, int, float*, float*, int, float*, cudaStream_t);
+// losses.cu
+size_t reduce_workspace_bytes();
+int diff_mean_fwd(const void*, int, const void*, int, long long, int, int, long long, float*, float*, cudaStream_t);
+int diff_mean_bwd(const void*, int, const void*, int, long long, int, int, long long, const float*, float, void*, int, cudaStream_t);
+int mean_fwd(const void*, int, long long, float, float*, float*, cudaStream_t);
+int mean_bwd(const float*, float, long long, void*, int, cudaStream_t);
+int gp_penalty_fwd(const void*, int, long long, int, int, int, float*, float*, cudaStream_t);
+int gp_penalty_bwd(const void*, int, long long, int, int, int, const float*, float, void*, int, cudaStream_t);
+int lerp_nhwc(const void*, int, int, const void*, int, const float*, long long, long long, long long, void*, int, cudaStream_t);
+int nchw_to_nhwc(const float*, long long, int, long long, void*, int, cudaStream_t);
+int add_cast(const void*, int, const void*, int, long long, void*, int, cudaStream_t);
+
 // sgam.cu
 struct SgCommon {
     const void* a; const void* b; int ab_f32;
@@ -378,6 +394,103 @@ int sr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
     SR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
     return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step < 1 ? 1 : step, step_dev, grad_scale,
                      clamp_lo, clamp_hi, (cudaStream_t)stream);
+}
+
+static bool dt_ok(int d) { return d == SR_F32 || d == SR_BF16; }
+
+size_t sr_cgam_workspace_bytes(int N, int P) { return cgam_workspace_bytes(N, P); }
+
+int sr_cgam_fwd(const float* x, const float* gamma, int N, int P, float* y32, void* y16, int y16_dtype, float* A, void* workspace,
+                void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && gamma && y32 && A && workspace && N > 0 && P > 0 && (!y16 || dt_ok(y16_dtype)), "cgam_fwd: bad arguments");
+    return cgam_fwd(x, gamma, N, P, y32, y16, y16_dtype, A, (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_cgam_bwd(const float* dy, const float* x, const float* A, const float* gamma, int N, int P, float* dx, float* dgamma, int accumulate,
+                void* workspace, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(dy && x && A && gamma && dx && dgamma && workspace && N > 0 && P > 0, "cgam_bwd: bad arguments");
+    return cgam_bwd(dy, x, A, gamma, N, P, dx, dgamma, accumulate, (float*)workspace, (cudaStream_t)stream);
+}
+
+size_t sr_reduce_workspace_bytes(void) { return reduce_workspace_bytes(); }
+
+int sr_diff_mean_fwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, int p, int b_nchw_C, int64_t b_HW, float* out,
+                     void* workspace, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && b && out && workspace && n > 0 && (p == 1 || p == 2) && dt_ok(a_dtype) && dt_ok(b_dtype), "diff_mean_fwd: bad arguments");
+    SR_REQUIRE(b_nchw_C == 0 || (b_nchw_C > 0 && b_HW > 0 && n % ((int64_t)b_nchw_C * b_HW) == 0), "diff_mean_fwd: bad NCHW geometry");
+    return diff_mean_fwd(a, a_dtype, b, b_dtype, n, p, b_nchw_C, b_HW, out, (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_diff_mean_bwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, int p, int b_nchw_C, int64_t b_HW, const float* g,
+                     float scale, void* da, int da_dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && b && g && da && n > 0 && (p == 1 || p == 2) && dt_ok(a_dtype) && dt_ok(b_dtype) && dt_ok(da_dtype), "diff_mean_bwd: bad arguments");
+    SR_REQUIRE(b_nchw_C == 0 || (b_nchw_C > 0 && b_HW > 0 && n % ((int64_t)b_nchw_C * b_HW) == 0), "diff_mean_bwd: bad NCHW geometry");
+    return diff_mean_bwd(a, a_dtype, b, b_dtype, n, p, b_nchw_C, b_HW, g, scale, da, da_dtype, (cudaStream_t)stream);
+}
+
+int sr_mean_fwd(const void* x, int dtype, int64_t n, float scale, float* out, void* workspace, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && out && workspace && n > 0 && dt_ok(dtype), "mean_fwd: bad arguments");
+    return mean_fwd(x, dtype, n, scale, out, (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_mean_bwd(const float* g, float scale, int64_t n, void* dx, int dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(g && dx && n > 0 && dt_ok(dtype), "mean_bwd: bad arguments");
+    return mean_bwd(g, scale, n, dx, dtype, (cudaStream_t)stream);
+}
+
+int sr_gp_penalty_fwd(const void* grad, int dtype, int64_t pixels, int C, int norm, int penalty, float* out, void* workspace, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(grad && out && workspace && pixels > 0 && C >= 1 && C <= 4 && norm >= 0 && norm <= 2 && (penalty == 0 || penalty == 1) && dt_ok(dtype),
+               "gp_penalty_fwd: bad arguments (C must be 1..4)");
+    return gp_penalty_fwd(grad, dtype, pixels, C, norm, penalty, out, (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_gp_penalty_bwd(const void* grad, int dtype, int64_t pixels, int C, int norm, int penalty, const float* g, float scale, void* dgrad,
+                      int out_dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(grad && g && dgrad && pixels > 0 && C >= 1 && C <= 4 && norm >= 0 && norm <= 2 && (penalty == 0 || penalty == 1) && dt_ok(dtype) && dt_ok(out_dtype),
+               "gp_penalty_bwd: bad arguments (C must be 1..4)");
+    return gp_penalty_bwd(grad, dtype, pixels, C, norm, penalty, g, scale, dgrad, out_dtype, (cudaStream_t)stream);
+}
+
+int sr_lerp_nhwc(const void* real, int real_dtype, int real_nchw_C, const void* fake, int fake_dtype, const float* alpha, int64_t n,
+                 int64_t per_image, int64_t HW, void* out, int out_dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(real && fake && alpha && out && n > 0 && per_image > 0 && n % per_image == 0 && dt_ok(real_dtype) && dt_ok(fake_dtype) && dt_ok(out_dtype),
+               "lerp_nhwc: bad arguments");
+    SR_REQUIRE(real_nchw_C == 0 || (HW > 0 && per_image == (int64_t)real_nchw_C * HW), "lerp_nhwc: bad NCHW geometry");
+    return lerp_nhwc(real, real_dtype, real_nchw_C, fake, fake_dtype, alpha, n, per_image, HW, out, out_dtype, (cudaStream_t)stream);
+}
+
+int sr_nchw_to_nhwc(const float* x, int64_t N, int C, int64_t HW, void* out, int out_dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && out && N > 0 && C >= 1 && C <= 4 && HW > 0 && dt_ok(out_dtype), "nchw_to_nhwc: bad arguments (C must be 1..4)");
+    return nchw_to_nhwc(x, N, C, HW, out, out_dtype, (cudaStream_t)stream);
+}
+
+int sr_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, void* out, int out_dtype, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && out && n > 0 && dt_ok(a_dtype) && dt_ok(out_dtype) && (!b || dt_ok(b_dtype)), "add_cast: bad arguments");
+    SR_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0),
+               "add_cast: 16-byte aligned buffers required");
+    return add_cast(a, a_dtype, b, b ? b_dtype : a_dtype, n, out, out_dtype, (cudaStream_t)stream);
 }
 
 int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows, int sbo_bytes, int base_offset, float* out,

@@ -30,7 +30,7 @@ class GANLoss(nn.Module):
         elif self.gan_type == 'lsgan':
             self.loss = nn.MSELoss()
         elif self.gan_type == 'wgan-gp':
-            self.loss = lambda inp, target: -1 * inp.float().mean() if target else inp.float().mean()
+            self.loss = lambda inp, target: ops.mean_loss(inp, -1.0 if target else 1.0)
         else:
             raise NotImplementedError('GAN type [{:s}] is not found'.format(self.gan_type))
 
@@ -170,6 +170,8 @@ class CGAM(nn.Module):
 
     def forward(self, x):
         b, c, h, w = x.shape
+        if not self.light and c == 64:
+            return ops.cgam_attention(x, self.gamma)         # gram / softmax / apply kernels (csrc/cgam.cu), fp32
         xf = x.float()
         if self.light:
             pooled = torch.cat([F.adaptive_avg_pool2d(xf, 1), F.adaptive_max_pool2d(xf, 1)], 1)

@@ -99,8 +99,7 @@ class SRADSGAN(object):
         self.reducer_D = dp.BucketReducer(self.optimizer_D, overlap=False)
 
     def criterion_content(self, a, b):
-        d = a.float() - b.float()
-        return d.abs().mean() if self.loss_Lp_norm == "L1" else (d * d).mean()     # :685-688
+        return ops.diff_mean_loss(a, b, 1 if self.loss_Lp_norm == "L1" else 2)     # :685-688 (nn.L1Loss / nn.MSELoss)
 
     # ------------------------------------------------------------------------------------------
     # WGAN-GP (reference :595-641)
@@ -111,21 +110,15 @@ class SRADSGAN(object):
             alpha = self._alpha_override.to(real_samples.device, torch.float32).view(b, 1, 1, 1)
         else:
             alpha = torch.from_numpy(np.random.random((b, 1, 1, 1))).float().to(real_samples.device)   # :609
-        interpolates = (alpha * real_samples + ((1 - alpha) * fake_samples)).requires_grad_(True)      # :611
+        interpolates = ops.gp_interpolates(real_samples, fake_samples, alpha).requires_grad_(True)     # :611
         d_interpolates = discriminator(interpolates)
         grad_outputs = torch.ones_like(d_interpolates)
         with ops.input_grad_only():      # only d/d(interpolates) is wanted here; weight gradients come from .backward()
             gradients = torch.autograd.grad(outputs=d_interpolates, inputs=interpolates, grad_outputs=grad_outputs,
                                             create_graph=True, retain_graph=True, only_inputs=True)[0]     # :621
-        gradients = gradients.float()
-        if grad_penalty_Lp_norm == 'Linf':
-            grad_norm, _ = torch.max(torch.abs(gradients), 1)
-        elif grad_penalty_Lp_norm == 'L1':
-            grad_norm = gradients.norm(1, 1)
-        else:
-            grad_norm = gradients.norm(2, 1)                                                           # :630
-        constraint = (grad_norm - 1).pow(2) if penalty_type == 'LS' else torch.relu(grad_norm - 1)     # :632-635
-        return constraint.mean()
+        # per-pixel norm over the colour channels (:623-630), 'LS' (n-1)^2 or hinge (:632-635), mean (:637): one reduction
+        # kernel forward, one elementwise kernel backward (its output is the cotangent of the double backward through D)
+        return ops.gp_penalty(gradients, grad_penalty_Lp_norm, penalty_type)
 
     def gradient_penalty(self, discriminator, real_samples, fake_samples, grad_penalty_Lp_norm='L2', penalty_type='LS'):
         """Same contract as the reference: back-propagates the un-weighted penalty itself and returns it."""
@@ -142,6 +135,9 @@ class SRADSGAN(object):
         mark = getattr(self, "_phase_mark", None) or (lambda name: None)
         mark("start")
         self._repack()
+        # the loader's NCHW fp32 batches -> NHWC fp32 once per iteration (one layout kernel each); VGG, the critic, the L1 loss
+        # and the WGAN-GP interpolation all read these
+        imgs_lr, imgs_hr = ops.to_compute(imgs_lr), ops.to_compute(imgs_hr)
         self.optimizer_G.zero_grad()
         for p in self.optimizer_D.params:
             p.requires_grad_(False)          # skip D's weight gradients in the G step (discarded by the reference, :865)
@@ -176,7 +172,7 @@ class SRADSGAN(object):
         for p in self.optimizer_D.params:
             p.requires_grad_(True)
         return {"loss_G": loss_G.detach(), "pixel": pixel_loss_G.detach(), "content": loss_content.detach(),
-                "adv": loss_gan.detach(), "gen_hr": gen_hr.detach()}
+                "adv": loss_gan.detach(), "gen_hr": gen_hr.detach(), "_hr_nhwc": imgs_hr}
 
     def _repack(self):
         """packed bf16 operands of every G and D convolution weight, refreshed from the fp32 masters by one launch per
@@ -222,7 +218,7 @@ class SRADSGAN(object):
         scale = self.reducer_G.finish()
         self.optimizer_G.step(grad_scale=scale)                                     # :857-858
         mark("adam_G")
-        out.update(self._d_phase(imgs_hr, out["gen_hr"], fuse_gp_backward))
+        out.update(self._d_phase(out["_hr_nhwc"], out["gen_hr"], fuse_gp_backward))
         self.reducer_D.arm()
         scale = self.reducer_D.finish()
         self.optimizer_D.step(grad_scale=scale)                                     # :887 + clamp :891-892 (fused)
@@ -308,7 +304,7 @@ class SRADSGAN(object):
                     out = self._g_phase(st["lr"], st["hr"])
                 with torch.cuda.graph(g2, pool=g1.pool(), capture_error_mode="thread_local"):
                     self.optimizer_G.step(grad_scale=1.0 / world)
-                    out.update(self._d_phase(st["hr"], out["gen_hr"]))
+                    out.update(self._d_phase(out["_hr_nhwc"], out["gen_hr"]))
                 with torch.cuda.graph(g3, pool=g1.pool(), capture_error_mode="thread_local"):
                     self.optimizer_D.step(grad_scale=1.0 / world)
                 st["out"] = out

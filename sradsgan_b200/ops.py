@@ -188,45 +188,68 @@ class PackPlan:
 
     def __init__(self, params):
         self.entries = []          # (param, key, packed tensor)
-        rows, blocks = [], 0
-        self.dtype = None
+        groups = {}                # operand dtype -> [rows, blocks]   (bf16 operands; fp32 ones for the RGB-side thin layers)
+        self.ptrs = []
         for w in params:
             if w.dim() != 4 or w.dtype != torch.float32 or not w.is_contiguous():
                 continue
             for key, hit in w.__dict__.get("_sr_pack", {}).items():
                 mode, dtype, shuffle_r = key
-                if self.dtype is None:
-                    self.dtype = dtype
-                if dtype != self.dtype:
-                    continue
+                grp = groups.setdefault(dtype, [[], 0])
                 cout, cin, kh, kw = w.shape
-                rows.append([w.data_ptr(), hit[1].data_ptr(), cout, cin, kh * kw, mode, int(shuffle_r), blocks])
-                blocks += (w.numel() + 1023) // 1024
+                grp[0].append([w.data_ptr(), hit[1].data_ptr(), cout, cin, kh * kw, mode, int(shuffle_r), grp[1]])
+                grp[1] += (w.numel() + 1023) // 1024
                 self.entries.append((w, key, hit[1]))
-        self.blocks = blocks
-        self.ptrs = [r[0] for r in rows]
-        self.table = torch.tensor(rows, dtype=torch.int64, device=self.entries[0][0].device) if rows else None
+                self.ptrs.append(w.data_ptr())
+        dev = self.entries[0][0].device if self.entries else None
+        # one launch per operand dtype: (dtype, device table, entries, blocks)
+        self.tables = [(dt, torch.tensor(rows, dtype=torch.int64, device=dev), len(rows), blocks) for dt, (rows, blocks) in groups.items()]
+        self.table = self.tables[0][1] if self.tables else None
+        self.dtype = self.tables[0][0] if self.tables else None
+        self.blocks = sum(t[3] for t in self.tables)
 
     def valid(self):
         """master weights still where the table points (FlatAdam views are stable; load_state_dict copies in place)"""
         return all(w.data_ptr() == ptr for (w, _, _), ptr in zip(self.entries, self.ptrs))
 
     def repack(self):
-        if self.table is None:
+        if not self.tables:
             return
-        _lib.backend().pack_weights_batched(self.table, len(self.entries), self.blocks, self.dtype)
+        for dt, table, n, blocks in self.tables:
+            _lib.backend().pack_weights_batched(table, n, blocks, dt)
         for w, key, t in self.entries:
             w.__dict__["_sr_pack"][key] = (_ver(w), t, True)
 
 
 def to_compute(x):
-    """NCHW-shaped tensor in the compute dtype with NHWC memory."""
+    """NCHW-shaped tensor in the compute dtype with NHWC memory.
+    RGB-side tensors (<= 4 channels: the LR / HR batches, the generator output, the WGAN-GP interpolates) are NOT rounded to
+    bf16: the layers that read them are direct FMA kernels (csrc/conv_thin.cu) that take fp32 inputs and fp32-packed weights at
+    no cost, and rounding an 8-bit-mantissa image in front of a train-mode BatchNorm stack costs ~2x in the discriminator's
+    per-layer error (profiles/r02_parity_fullsize.txt)."""
     lp = getattr(x, "_sr_lowp", None)
     if lp is not None and lp.dtype == config.compute_dtype:
         return lp                      # twin written by the producing kernel's epilogue: no cast pass
+    if x.dim() == 4 and x.shape[1] <= 4 and x.dtype == torch.float32:
+        return to_input(x)
     if x.dtype != config.compute_dtype:
         x = x.to(config.compute_dtype)
     return x.contiguous(memory_format=torch.channels_last)
+
+
+def to_input(x):
+    """fp32 (N, C <= 4, H, W) tensor with NHWC memory: one layout kernel for the loader's NCHW batches, a no-op for
+    tensors the library produced"""
+    if x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    if x.is_cuda and x.is_contiguous() and not x.requires_grad:
+        return _lib.backend().nchw_to_nhwc(x, torch.float32)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _out_dtype(x, out_dtype=None):
+    """dtype a convolution writes: the caller's choice, else the compute dtype (fp32 RGB-side inputs feed bf16 feature maps)"""
+    return out_dtype if out_dtype is not None else (config.compute_dtype if x.dtype == torch.float32 else x.dtype)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -242,16 +265,16 @@ class ConvFwd(Function):
         ctx.has_bias = b is not None
         ctx.bias = b                   # only its identity is used (gradient target lookup)
         ctx.save_for_backward(x, w)
-        return _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, impl=config.conv_impl)
+        return _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, out_dtype=_out_dtype(x), impl=config.conv_impl)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         g = ctx.g
-        gy = gy.to(x.dtype)
+        gy = gy.to(_out_dtype(x))
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = ConvDgrad.apply(gy, w, g)
+            gx = ConvDgrad.apply(gy, w, g, x.dtype)
         gw, gb = _wgrad(x, gy, g, w, ctx.bias, ctx.has_bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, None, None
 
@@ -260,22 +283,23 @@ class ConvDgrad(Function):
     """dx = conv_transpose2d(dy, w) for the forward geometry g (linear in dy and in w)."""
 
     @staticmethod
-    def forward(ctx, gy, w, g):
+    def forward(ctx, gy, w, g, x_dtype=None):
         ctx.g = g
         ctx.save_for_backward(gy, w)
-        return _lib.backend().conv_dgrad(gy, packed(w, 1, gy.dtype), g, impl=config.conv_impl)
+        return _lib.backend().conv_dgrad(gy, packed(w, 1, gy.dtype), g, out_dtype=x_dtype, impl=config.conv_impl)
 
     @staticmethod
     def backward(ctx, ggx):
         gy, w = ctx.saved_tensors
         g = ctx.g
-        ggx = ggx.to(gy.dtype)
+        if not (g.Cin <= 4 and ggx.dtype == torch.float32):      # RGB-side cotangents stay fp32 (thin kernels)
+            ggx = ggx.to(gy.dtype)
         d_gy = d_w = None
         if ctx.needs_input_grad[0]:
-            d_gy = ConvFwd.apply(ggx, w, None, g.stride, g.pad)
+            d_gy = ConvFwd.apply(ggx, w, None, g.stride, g.pad).to(gy.dtype)
         if ctx.needs_input_grad[1]:
             d_w, _ = _wgrad(ggx, gy, g, w, None, False, True, False)
-        return d_gy, d_w, None
+        return d_gy, d_w, None, None
 
 
 class ConvWgrad(Function):
@@ -296,10 +320,10 @@ class ConvWgrad(Function):
         g = ctx.g
         d_x = d_gy = None
         if ctx.needs_input_grad[0] and ggw is not None:
-            d_x = ConvDgrad.apply(gy, ggw, g)
+            d_x = ConvDgrad.apply(gy, ggw, g, x.dtype)
         if ctx.needs_input_grad[1]:
             if ggw is not None:
-                d_gy = ConvFwd.apply(x, ggw, ggb, g.stride, g.pad)
+                d_gy = ConvFwd.apply(x, ggw, ggb, g.stride, g.pad).to(gy.dtype)
             elif ggb is not None:
                 d_gy = ggb.to(gy.dtype).view(1, -1, 1, 1).expand_as(gy)
         return d_x, d_gy, None
@@ -326,7 +350,7 @@ class ConvFused(Function):
         if act != ACT_NONE and residual is not None:
             raise NotImplementedError("ConvFused: activation together with a residual is not used by this model")
         y = _lib.backend().conv_fwd(x, packed(w, 0, x.dtype, shuffle_r), b, residual, g, act, slope, shuffle_r,
-                                    out_dtype=out_dtype, impl=config.conv_impl)
+                                    out_dtype=_out_dtype(x, out_dtype), impl=config.conv_impl)
         # the activation derivative is recovered from the sign of the output (slope > 0), which is only
         # possible when no residual was added on top
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
@@ -338,13 +362,16 @@ class ConvFused(Function):
         x, w, y = ctx.saved_tensors
         g = ctx.g
         g_res = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        cd = _out_dtype(x)               # dtype of the gradient operands (the compute dtype; x itself may be an fp32 RGB tensor)
         if ctx.act != ACT_NONE or (ctx.r and ctx.r > 1):
-            gpre = _lib.backend().act_bwd(gy, y if y is not None else gy, ctx.act, ctx.slope, ctx.r, g, x.dtype)
+            gpre = _lib.backend().act_bwd(gy, y if y is not None else gy, ctx.act, ctx.slope, ctx.r, g, cd)
+        elif gy.dtype != cd:
+            gpre = _lib.backend().add_cast(gy.contiguous(memory_format=torch.channels_last), None, cd) if gy.is_cuda else gy.to(cd).contiguous(memory_format=torch.channels_last)
         else:
-            gpre = to_compute(gy) if gy.dtype != x.dtype else gy.contiguous(memory_format=torch.channels_last)
+            gpre = gy.contiguous(memory_format=torch.channels_last)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = _lib.backend().conv_dgrad(gpre, packed(w, 1, gpre.dtype), g, impl=config.conv_impl)
+            gx = _lib.backend().conv_dgrad(gpre, packed(w, 1, gpre.dtype), g, out_dtype=x.dtype, impl=config.conv_impl)
         gw, gb = _wgrad(x, gpre, g, w, ctx.bias, ctx.has_bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, g_res, None, None, None, None, None, None
 
@@ -524,7 +551,7 @@ class ConvActFwd(Function):
         g = conv_geom(x.shape, w.shape, stride, pad)
         ctx.g, ctx.act, ctx.slope, ctx.has_bias = g, act, slope, b is not None
         ctx.bias = b
-        y = _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, act, slope, impl=config.conv_impl)
+        y = _lib.backend().conv_fwd(x, packed(w, 0, x.dtype), b, None, g, act, slope, out_dtype=_out_dtype(x), impl=config.conv_impl)
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -532,10 +559,10 @@ class ConvActFwd(Function):
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         g = ctx.g
-        gpre = ActBwd.apply(gy.to(x.dtype), y, ctx.act, ctx.slope, g)
+        gpre = ActBwd.apply(gy.to(y.dtype), y, ctx.act, ctx.slope, g)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = ConvDgrad.apply(gpre, w, g)
+            gx = ConvDgrad.apply(gpre, w, g, x.dtype)
         gw, gb = _wgrad(x, gpre, g, w, ctx.bias, ctx.has_bias, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, None, None, None, None
 
@@ -591,3 +618,121 @@ def bn_leaky_relu(x, bn, slope):
     with torch.no_grad():
         bn.num_batches_tracked += 1
     return y
+
+
+# ----------------------------------------------------------------------------------------------
+# loss reductions (csrc/losses.cu): scalar losses as fp32 0-dim tensors on the device, first-order
+# ----------------------------------------------------------------------------------------------
+class DiffMeanLoss(Function):
+    """mean |a - b|^p (p = 1: nn.L1Loss, 2: nn.MSELoss; reference model/sradsgan.py:685-688, :834, :838), gradient to `a` only
+    (the target is the HR batch / the detached VGG features)."""
+
+    @staticmethod
+    def forward(ctx, a, b, p):
+        ctx.p = p
+        ctx.save_for_backward(a, b)
+        return _lib.backend().diff_mean(a, b, p)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return _lib.backend().diff_mean_bwd(a, b, ctx.p, g), None, None
+
+
+def diff_mean_loss(a, b, p=1):
+    return DiffMeanLoss.apply(a, b.detach(), p)
+
+
+class MeanLoss(Function):
+    """scale * mean(x): GANLoss('wgan-gp') (reference model/sradsgan.py:46-52)"""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        ctx.save_for_backward(x)
+        return _lib.backend().mean(x, scale)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return _lib.backend().mean_bwd(g, ctx.scale, x), None
+
+
+def mean_loss(x, scale=1.0):
+    return MeanLoss.apply(x, float(scale))
+
+
+GP_NORMS = {"L2": 0, "L1": 1, "Linf": 2}
+GP_PENALTIES = {"LS": 0, "hinge": 1}
+
+
+class GPPenalty(Function):
+    """mean over pixels of (||grad||_p over the colour channels - 1)^2 (or its hinge): reference model/sradsgan.py:623-637.
+    Its backward produces the cotangent that enters the double backward through the discriminator."""
+
+    @staticmethod
+    def forward(ctx, grad, norm, penalty):
+        ctx.norm, ctx.penalty = norm, penalty
+        ctx.save_for_backward(grad)
+        return _lib.backend().gp_penalty(grad, norm, penalty)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return _lib.backend().gp_penalty_bwd(grad, ctx.norm, ctx.penalty, g), None, None
+
+
+def gp_penalty(grad, norm="L2", penalty="LS"):
+    return GPPenalty.apply(grad, GP_NORMS[norm], GP_PENALTIES[penalty])
+
+
+def gp_interpolates(real, fake, alpha):
+    """alpha * real + (1 - alpha) * fake of detached samples (reference :611) as an fp32 NHWC leaf"""
+    return _lib.backend().lerp(real.detach(), fake.detach(), alpha, torch.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# CGAM channel attention (csrc/cgam.cu)
+# ----------------------------------------------------------------------------------------------
+class CGAMAttention(Function):
+    """y = gamma * (softmax(rowmax(X X^T) - X X^T) X) + x (reference model/sradsgan.py:202-213), fp32; optionally also the
+    compute-dtype twin of y for the convolutions that follow."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, lowp):
+        y32, y16, A = _lib.backend().cgam_fwd(x, gamma, config.compute_dtype if lowp else None)
+        ctx.gamma = gamma
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x, A, gamma)
+        return (y32, y16) if lowp else y32
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy32, gy16=None):
+        x, A, gamma = ctx.saved_tensors
+        if gy32 is None and gy16 is None:
+            return None, None, None
+        be = _lib.backend()
+        if gy32 is None:
+            dy = be.add_cast(gy16.contiguous(memory_format=torch.channels_last), None, torch.float32)
+        elif gy16 is None:
+            dy = gy32
+        else:
+            dy = be.add_cast(gy32.contiguous(memory_format=torch.channels_last), gy16.contiguous(memory_format=torch.channels_last), torch.float32)
+        tg = _grad_target(ctx.gamma)
+        dx, dgamma = be.cgam_bwd(dy, x, A, gamma, dgamma_into=tg)
+        return dx, dgamma, None
+
+
+def cgam_attention(x, gamma):
+    x = x.float().contiguous(memory_format=torch.channels_last)
+    lowp = config.compute_dtype != torch.float32
+    out = CGAMAttention.apply(x, gamma, lowp)
+    if lowp:
+        y32, y16 = out
+        y32._sr_lowp = y16
+        return y32
+    return out

@@ -16,19 +16,25 @@ def test_plan_table_layout_and_validity():
         w.__dict__["_sr_pack"] = {(0, torch.bfloat16, 0): (ops._ver(w), torch.empty(kh * kw, co, ci, dtype=torch.bfloat16), False),
                                   (1, torch.bfloat16, 0): (ops._ver(w), torch.empty(kh * kw, ci, co, dtype=torch.bfloat16), False)}
     ws[0].__dict__["_sr_pack"][(0, torch.bfloat16, 2)] = (ops._ver(ws[0]), torch.empty(9, 256, 64, dtype=torch.bfloat16), False)
-    ws[1].__dict__["_sr_pack"][(0, torch.float32, 0)] = (ops._ver(ws[1]), torch.empty(9, 64, 256), False)     # other dtype: not in this plan
+    ws[2].__dict__["_sr_pack"][(0, torch.float32, 0)] = (ops._ver(ws[2]), torch.empty(1, 64, 3), False)     # fp32 operand of an RGB-side thin layer
     plan = ops.PackPlan(ws)
-    assert plan.dtype == torch.bfloat16 and len(plan.entries) == 7 and plan.valid()
-    t = plan.table
-    assert t.shape == (7, 8) and t.dtype == torch.int64
-    first = 0
-    for row, (w, key, out) in zip(t.tolist(), plan.entries):
-        co, ci, kh, kw = w.shape
-        assert row[0] == w.data_ptr() and row[1] == out.data_ptr()
-        assert row[2:7] == [co, ci, kh * kw, key[0], key[2]]
-        assert row[7] == first                                  # every entry owns ceil(numel / 1024) consecutive blocks
-        first += (w.numel() + 1023) // 1024
-    assert plan.blocks == first
+    assert len(plan.entries) == 8 and plan.valid()
+    assert [t[0] for t in plan.tables] == [torch.bfloat16, torch.float32]       # one batched launch per operand dtype
+    total = 0
+    for dt, t, n, blocks in plan.tables:
+        assert t.shape == (n, 8) and t.dtype == torch.int64
+        mine = [(w, key, out) for (w, key, out) in plan.entries if key[1] == dt]
+        assert len(mine) == n == (7 if dt == torch.bfloat16 else 1)
+        first = 0
+        for row, (w, key, out) in zip(t.tolist(), mine):
+            co, ci, kh, kw = w.shape
+            assert row[0] == w.data_ptr() and row[1] == out.data_ptr()
+            assert row[2:7] == [co, ci, kh * kw, key[0], key[2]]
+            assert row[7] == first                              # every entry owns ceil(numel / 1024) consecutive blocks
+            first += (w.numel() + 1023) // 1024
+        assert blocks == first
+        total += blocks
+    assert plan.blocks == total
     ws[0].data = ws[0].data.clone()                             # master moved (e.g. a new flat buffer): the table is stale
     assert not plan.valid()
 
