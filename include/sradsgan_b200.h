@@ -47,6 +47,11 @@ typedef struct sr_conv_desc {
     float   slope;              /* LeakyReLU negative slope */
     int32_t shuffle_r;          /* 0/1: none; r>1: y is written as (N, Ho*r, Wo*r, Cout/r^2) */
     int32_t impl;               /* SR_IMPL_* */
+    /* sr_conv2d_fwd only, nullable: the epilogue also emits the CLAM pooling partials of y (bf16) that the local-attention
+     * chain behind conv2 of a RAB reads (model/sradsgan.py:253 -> :258, avg / max pooling of :117-121) —
+     * [N][sr_conv_pool_rows(desc)][Cout] channel sums and packed keys (see sr_la_chain_args).  Needs a geometry for which
+     * sr_conv_pool_rows() > 0. */
+    float* pool_sum; uint32_t* pool_key;
 } sr_conv_desc;
 
 const char* sr_last_error(void);
@@ -55,6 +60,10 @@ int sr_version(void);
 int sr_device_check(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t sr_launch_count(void);
+
+/* rows per image of the pooling partials sr_conv2d_fwd emits for this geometry when desc.pool_sum / pool_key are set
+ * (0: not available — 3x3 / stride 1 / pad 1, bf16 in and out, Cin % 64 == 0, Cout % 64 == 0, no pixel shuffle, H*W <= 65535). */
+int sr_conv_pool_rows(const sr_conv_desc* d);
 
 /* 1 when sr_conv2d_fwd (kind 0) / sr_conv2d_dgrad (kind 1) / sr_conv2d_wgrad (kind 2) will run this
  * geometry on a tcgen05 kernel, 0 when it takes the SIMT kernel (bench.py attributes time per kernel). */
@@ -118,6 +127,43 @@ int sr_la_chain_bwd(const float* gz32, const void* gz16, const void* x, int x_dt
                     const float* fc1, const float* fc2, const float* w7, const float* W, int N, int H, int Wd, int C, int Cr,
                     void* dx, float* d_fc1, float* d_fc2, float* d_w7, float* dW, float* db, float* dz_out,
                     void* workspace, void* stream);
+
+/* The same chain through ONE parameter block, with the fusions of the band path (csrc/la_band.cu; bf16, H*W <= 65535):
+ *   pool_sum / pool_key [N][pool_rows][64] (nullable): per-(image, channel) partial sums and packed maxima of x that the
+ *       PRODUCER of x emitted in its epilogue (sr_conv2d_fwd with desc.pool_*, or a previous chain's out_pool_*): the CLAM
+ *       pooling then costs no pass over x.  key = (orderable bf16 bits << 16) | (0xFFFF - pixel index in the image).
+ *   acc_in / acc_out (nullable): acc_out = acc_in + z — the dense-sampling sum `out_all += y` (model/sradsgan.py:459).
+ *   out_pool_sum / out_pool_key [N][sr_la_chain_pool_rows(N,H,W)][64] (nullable): the partials of z16 for the chain that
+ *       consumes it (the ResGroup tail reads the last RAB's output, :303-311).
+ * Forward = one kernel (+ one pooling kernel when no partials are given); backward = three (no memset, no side stream).
+ * Shapes outside the band path fall back to sr_la_chain_fwd / _bwd; acc_* / out_pool_* / gacc then fail with
+ * SR_ERR_UNSUPPORTED (query sr_la_chain_band_path first).  tickets: N int32, ZERO before the first use (every launch
+ * re-arms them), one stream at a time; NULL selects the tile kernels. */
+typedef struct sr_la_chain_args {
+    int32_t N, H, W, C, Cr, x_dtype;
+    const void* x; const float* t;
+    const float* fc1; const float* fc2; const float* w7; const float* Wm; const float* bias;
+    const float* pool_sum; const uint32_t* pool_key; int32_t pool_rows;
+    const float* acc_in; float* acc_out;
+    float* z32; void* z16;
+    float* s; float* m; float* avg; float* max; int32_t* pstar; float* q; uint8_t* cstar;
+    float* out_pool_sum; uint32_t* out_pool_key;
+    void* workspace;
+} sr_la_chain_args;
+typedef struct sr_la_chain_grad_args {
+    int32_t N, H, W, C, Cr, x_dtype;
+    const float* gz32; const void* gz16; const float* gacc;      /* dz = gz32 + gz16 + gacc (any may be NULL, not all) */
+    const void* x; const float* s; const float* m; const float* avg; const float* max; const int32_t* pstar; const float* q;
+    const uint8_t* cstar;
+    const float* fc1; const float* fc2; const float* w7; const float* Wm;
+    void* dx; float* d_fc1; float* d_fc2; float* d_w7; float* dW; float* db; float* dz_out;
+    int32_t* tickets;
+    void* workspace;
+} sr_la_chain_grad_args;
+int sr_la_chain_band_path(int N, int H, int W, int x_dtype);     /* 1 when the band kernels take this shape */
+int sr_la_chain_pool_rows(int N, int H, int W);                   /* rows per image of out_pool_sum / out_pool_key */
+int sr_la_chain_forward(const sr_la_chain_args* a, void* stream);
+int sr_la_chain_backward(const sr_la_chain_grad_args* a, void* stream);
 
 /* Backward of the fused conv epilogue: out = PixelUnshuffle_r( gy * act'(y) ), act' recovered from the
  * sign of the stored output y (LeakyReLU / ReLU; nn.LeakyReLU / nn.PixelShuffle of model/sradsgan.py:242,

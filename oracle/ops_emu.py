@@ -35,8 +35,9 @@ def unpack_weights(packed, mode, g_or_shape, shuffle_r=0):
 class EmuBackend:
     name = "emu"
 
-    def __init__(self):
+    def __init__(self, band=False):
         self.launches = 0
+        self.band = band            # emulate the band path's extras (dense-sampling accumulator, pooling partials) of the chain
 
     def launch_count(self):
         return self.launches
@@ -59,7 +60,9 @@ class EmuBackend:
             out = w.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
         return out.contiguous().to(dtype)
 
-    def conv_fwd(self, x, w_packed, bias, residual, g, act=ACT_NONE, slope=0.0, shuffle_r=0, out_dtype=None, impl=0):
+    def conv_fwd(self, x, w_packed, bias, residual, g, act=ACT_NONE, slope=0.0, shuffle_r=0, out_dtype=None, impl=0, want_pool=False):
+        if want_pool:               # the partials only save the chain a pooling pass: the emulation recomputes the pooling from x
+            return self.conv_fwd(x, w_packed, bias, residual, g, act, slope, shuffle_r, out_dtype, impl), None
         self.launches += 1
         out_dtype = x.dtype if out_dtype is None else out_dtype
         w = unpack_weights(w_packed, 0, (g.Cout, g.Cin, g.kh, g.kw), shuffle_r)
@@ -120,6 +123,21 @@ class EmuBackend:
         z32 = z.contiguous(memory_format=torch.channels_last)
         z16 = z32.to(x.dtype) if want_lowp else None
         return z32, z16, {"t_shape": t.shape, "b": b.detach().float()}
+
+    def la_band_path(self, x):
+        return self.band
+
+    def la_chain_forward(self, x, t, fc1, fc2, w7, W, b, want_lowp=True, pool=None, acc=None, want_pool=False):
+        z32, z16, sv = self.la_chain_fwd(x, t, fc1, fc2, w7, W, b, want_lowp)
+        acc_out = (acc.float() + z32).contiguous(memory_format=torch.channels_last) if acc is not None else None
+        n, c = x.shape[0], x.shape[1]
+        out_pool = (torch.zeros(n, 1, c), torch.zeros(n, 1, c, dtype=torch.int32), 1) if want_pool else None
+        return z32, z16, sv, acc_out, out_pool
+
+    def la_chain_backward(self, gz32, gz16, gacc, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
+        if gacc is not None:
+            gz32 = gacc.float() if gz32 is None else gz32.float() + gacc.float()
+        return self.la_chain_bwd(gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz, into)
 
     def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
         self.launches += 6

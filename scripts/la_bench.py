@@ -30,3 +30,14 @@ def timeit(fn, it=20):
 z32, z16, sv = be.la_chain_fwd(x, t, fc1, fc2, w7, Wm, b)
 print("la_chain fwd %.1f us   bwd %.1f us   (ideal traffic fwd 36 MB, bwd ~42 MB)" % (
     timeit(lambda: be.la_chain_fwd(x, t, fc1, fc2, w7, Wm, b)), timeit(lambda: be.la_chain_bwd(gz32, gz16, x, sv, fc1, fc2, w7, Wm))))
+# band path fed by producer partials (what the RAB conv2 epilogue provides) + dense-sampling accumulator
+if be.la_band_path(x):
+    _, _, _, _, pool = be.la_chain_forward(x, t, fc1, fc2, w7, Wm, b, want_pool=True)
+    acc = torch.randn_like(t)
+    gacc = torch.randn_like(t)
+    f1 = timeit(lambda: be.la_chain_forward(x, t, fc1, fc2, w7, Wm, b, pool=pool))
+    f2 = timeit(lambda: be.la_chain_forward(x, t, fc1, fc2, w7, Wm, b, pool=pool, acc=acc, want_pool=True))
+    b2 = timeit(lambda: be.la_chain_backward(gz32, gz16, gacc, x, sv, fc1, fc2, w7, Wm))
+    print("band path: fwd with producer partials %.1f us; + accumulator + out partials %.1f us; bwd with accumulator gradient %.1f us" % (f1, f2, b2))
+    print("  fwd %.0f GB/s, bwd %.0f GB/s of algorithmic traffic (768 / 896 B per pixel)" % (
+        N * H * W * 768 / f1 * 1e-3, N * H * W * 896 / timeit(lambda: be.la_chain_bwd(gz32, gz16, x, sv, fc1, fc2, w7, Wm)) * 1e-3))

@@ -23,6 +23,7 @@ EXPORTS = [
     "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep", "sr_pack_weights_batched", "sr_maxpool2x2_fwd", "sr_maxpool2x2_bwd",
     "sr_reduce_workspace_bytes", "sr_diff_mean_fwd", "sr_diff_mean_bwd", "sr_mean_fwd", "sr_mean_bwd", "sr_gp_penalty_fwd", "sr_gp_penalty_bwd",
     "sr_lerp_nhwc", "sr_nchw_to_nhwc", "sr_add_cast", "sr_cgam_workspace_bytes", "sr_cgam_fwd", "sr_cgam_bwd",
+    "sr_la_chain_band_path", "sr_la_chain_pool_rows", "sr_la_chain_forward", "sr_la_chain_backward", "sr_conv_pool_rows",
 ]
 
 
@@ -30,7 +31,24 @@ class ConvDesc(ctypes.Structure):
     """struct sr_conv_desc"""
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "kh", "kw", "stride", "pad", "in_dtype", "out_dtype", "act")]
-    _fields_ += [("slope", ctypes.c_float), ("shuffle_r", ctypes.c_int32), ("impl", ctypes.c_int32)]
+    _fields_ += [("slope", ctypes.c_float), ("shuffle_r", ctypes.c_int32), ("impl", ctypes.c_int32),
+                 ("pool_sum", ctypes.c_void_p), ("pool_key", ctypes.c_void_p)]
+
+
+class LaChainArgs(ctypes.Structure):
+    """struct sr_la_chain_args"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "H", "W", "C", "Cr", "x_dtype")] + \
+               [(n, ctypes.c_void_p) for n in ("x", "t", "fc1", "fc2", "w7", "Wm", "bias", "pool_sum", "pool_key")] + \
+               [("pool_rows", ctypes.c_int32)] + \
+               [(n, ctypes.c_void_p) for n in ("acc_in", "acc_out", "z32", "z16", "s", "m", "avg", "max", "pstar", "q", "cstar",
+                                               "out_pool_sum", "out_pool_key", "workspace")]
+
+
+class LaChainGradArgs(ctypes.Structure):
+    """struct sr_la_chain_grad_args"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "H", "W", "C", "Cr", "x_dtype")] + \
+               [(n, ctypes.c_void_p) for n in ("gz32", "gz16", "gacc", "x", "s", "m", "avg", "max", "pstar", "q", "cstar", "fc1", "fc2", "w7",
+                                               "Wm", "dx", "d_fc1", "d_fc2", "d_w7", "dW", "db", "dz_out", "tickets", "workspace")]
 
 
 ConvGeom = namedtuple("ConvGeom", "N H W Cin Ho Wo Cout kh kw stride pad")
@@ -65,6 +83,8 @@ def load():
     lib.sr_version.restype = i32
     lib.sr_device_check.restype = i32
     lib.sr_launch_count.restype = i64
+    lib.sr_conv_pool_rows.argtypes = [ctypes.POINTER(ConvDesc)]
+    lib.sr_conv_pool_rows.restype = i32
     lib.sr_conv_uses_tcgen05.argtypes = [ctypes.POINTER(ConvDesc), i32]
     lib.sr_conv_uses_tcgen05.restype = i32
     lib.sr_pack_weights.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
@@ -115,6 +135,14 @@ def load():
     for name in ("sr_diff_mean_fwd", "sr_diff_mean_bwd", "sr_mean_fwd", "sr_mean_bwd", "sr_gp_penalty_fwd", "sr_gp_penalty_bwd", "sr_lerp_nhwc",
                  "sr_nchw_to_nhwc", "sr_add_cast", "sr_cgam_fwd", "sr_cgam_bwd"):
         getattr(lib, name).restype = i32
+    lib.sr_la_chain_band_path.argtypes = [i32, i32, i32, i32]
+    lib.sr_la_chain_band_path.restype = i32
+    lib.sr_la_chain_pool_rows.argtypes = [i32, i32, i32]
+    lib.sr_la_chain_pool_rows.restype = i32
+    lib.sr_la_chain_forward.argtypes = [ctypes.POINTER(LaChainArgs), vp]
+    lib.sr_la_chain_forward.restype = i32
+    lib.sr_la_chain_backward.argtypes = [ctypes.POINTER(LaChainGradArgs), vp]
+    lib.sr_la_chain_backward.restype = i32
     lib.sr_set_workspace.argtypes = [vp, ctypes.c_uint64]
     lib.sr_set_workspace.restype = i32
     lib.sr_debug_umma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
@@ -230,7 +258,8 @@ class CudaBackend:
         return ConvDesc(g.N, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.kh, g.kw, g.stride, g.pad, in_dtype, out_dtype,
                         act, float(slope), int(shuffle_r), int(impl))
 
-    def conv_fwd(self, x, w_packed, bias, residual, g, act=ACT_NONE, slope=0.0, shuffle_r=0, out_dtype=None, impl=IMPL_AUTO):
+    def conv_fwd(self, x, w_packed, bias, residual, g, act=ACT_NONE, slope=0.0, shuffle_r=0, out_dtype=None, impl=IMPL_AUTO, want_pool=False):
+        """want_pool: also return the CLAM pooling partials of y emitted by the epilogue -> (y, (sum, key, rows) | None)"""
         _require_cuda(x, w_packed)
         x = _nhwc(x)
         out_dtype = x.dtype if out_dtype is None else out_dtype
@@ -246,10 +275,17 @@ class CudaBackend:
         if w_packed.dtype != x.dtype:
             raise TypeError("conv_fwd: packed weights must have the activation dtype")
         d = self._desc(g, _dt(x), _dt(y), act, slope, shuffle_r, impl)
+        pool = None
+        if want_pool:
+            rows = int(self.lib.sr_conv_pool_rows(ctypes.byref(d))) if residual is None else 0
+            if rows > 0:
+                pool = (torch.empty((g.N, rows, g.Cout), dtype=torch.float32, device=x.device),
+                        torch.empty((g.N, rows, g.Cout), dtype=torch.int32, device=x.device), rows)
+                d.pool_sum, d.pool_key = pool[0].data_ptr(), pool[1].data_ptr()
         self._timed("fwd", d, False, lambda: _check(
             self.lib.sr_conv2d_fwd(ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(residual), _ptr(y), _stream()),
             "conv2d_fwd"))
-        return y
+        return (y, pool) if want_pool else y
 
     def conv_dgrad(self, dy, w_packed_t, g, out_dtype=None, impl=IMPL_AUTO):
         _require_cuda(dy, w_packed_t)
@@ -309,14 +345,28 @@ class CudaBackend:
             self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 1, _stream()), "conv2d_wgrad"))
 
     # -- fused local-attention chain ---------------------------------------------------------------
-    def la_chain_fwd(self, x, t, fc1, fc2, w7, W, b, want_lowp=True):
-        """z = Conv1x1(SLAM(CLAM(x))) + t  ->  (z32, z16 | None, saved)"""
+    def la_band_path(self, x):
+        n, c, h, w = x.shape
+        return x.is_cuda and bool(self.lib.sr_la_chain_band_path(n, h, w, _dt(x)))
+
+    def _la_tickets(self, device, n):
+        t = getattr(self, "_la_ticket_buf", None)
+        if t is None or t.device != device or t.numel() < n:
+            t = self._la_ticket_buf = torch.zeros(max(n, 256), dtype=torch.int32, device=device)
+        return t
+
+    def la_chain_forward(self, x, t, fc1, fc2, w7, W, b, want_lowp=True, pool=None, acc=None, want_pool=False):
+        """z = Conv1x1(SLAM(CLAM(x))) + t  ->  (z32, z16 | None, saved, acc + z | None, pooling partials of z16 | None).
+        pool = (sum, key, rows): the producer's per-(image, channel) partials of x; acc: the dense-sampling accumulator."""
         _require_cuda(x, t)
         x = _nhwc(x)
         t = _nhwc(t.float())
         n, c, h, w = x.shape
         cr = fc1.shape[0]
         dev = x.device
+        band = self.la_band_path(x) and want_lowp
+        if not band and (acc is not None or want_pool):
+            raise RuntimeError("la_chain_forward: accumulator / pooling outputs need the band path (bf16, H*W <= 65535)")
         f32 = dict(dtype=torch.float32, device=dev)
         z32 = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
         z16 = torch.empty((n, c, h, w), dtype=x.dtype, device=dev, memory_format=torch.channels_last) if want_lowp else None
@@ -324,25 +374,43 @@ class CudaBackend:
               "max": torch.empty((n, c), **f32), "pstar": torch.empty((n, c), dtype=torch.int32, device=dev),
               "q": torch.empty((n, h * w, 2), **f32), "cstar": torch.empty((n, h * w), dtype=torch.uint8, device=dev)}
         ws = torch.empty(self.lib.sr_la_chain_workspace_bytes(n, h, w), dtype=torch.uint8, device=dev)
-        args = [fc1, fc2, w7, W, b]
-        args = [a.detach().float().contiguous() for a in args]
-        nbytes = float(x.numel()) * (x.element_size() + 4 + 4 + (x.element_size() if want_lowp else 0))
-        self._timed_rec("la_chain_fwd", 0.0, nbytes, lambda: _check(
-            self.lib.sr_la_chain_fwd(_ptr(x), _dt(x), _ptr(t), *[_ptr(a) for a in args], n, h, w, c, cr, _ptr(z32), _ptr(z16),
-                                     _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]), _ptr(sv["max"]), _ptr(sv["pstar"]),
-                                     _ptr(sv["q"]), _ptr(sv["cstar"]), _ptr(ws), _stream()), "la_chain_fwd"))
-        return z32, z16, sv
+        wts = [a.detach().float().contiguous() for a in (fc1, fc2, w7, W, b)]
+        acc_out = out_pool = None
+        if acc is not None:
+            acc = _nhwc(acc.float())
+            acc_out = torch.empty_like(z32)
+        if want_pool:
+            rows = int(self.lib.sr_la_chain_pool_rows(n, h, w))
+            out_pool = (torch.empty((n, rows, c), **f32), torch.empty((n, rows, c), dtype=torch.int32, device=dev), rows)
+        if not band:
+            pool = None
+        a = LaChainArgs(n, h, w, c, cr, _dt(x), x.data_ptr(), t.data_ptr(), *[v.data_ptr() for v in wts],
+                        pool[0].data_ptr() if pool else None, pool[1].data_ptr() if pool else None, int(pool[2]) if pool else 0,
+                        acc.data_ptr() if acc is not None else None, acc_out.data_ptr() if acc_out is not None else None,
+                        z32.data_ptr(), z16.data_ptr() if z16 is not None else None, sv["s"].data_ptr(), sv["m"].data_ptr(),
+                        sv["avg"].data_ptr(), sv["max"].data_ptr(), sv["pstar"].data_ptr(), sv["q"].data_ptr(), sv["cstar"].data_ptr(),
+                        out_pool[0].data_ptr() if out_pool else None, out_pool[1].data_ptr() if out_pool else None, ws.data_ptr())
+        nbytes = float(x.numel()) * (x.element_size() + 4 + 4 + (x.element_size() if want_lowp else 0) + (8 if acc is not None else 0))
+        self._timed_rec("la_chain_fwd", 0.0, nbytes, lambda: _check(self.lib.sr_la_chain_forward(ctypes.byref(a), _stream()), "la_chain_forward"))
+        return z32, z16, sv, acc_out, out_pool
 
-    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
-        """-> (dx, d_fc1, d_fc2, d_w7, dW, db, dz); `into` = [d_fc1, d_fc2, d_w7, dW, db] fp32 buffers to accumulate into"""
+    def la_chain_backward(self, gz32, gz16, gacc, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
+        """-> (dx, d_fc1, d_fc2, d_w7, dW, db, dz) for dz = gz32 + gz16 + gacc (any may be None);
+        `into` = [d_fc1, d_fc2, d_w7, dW, db] fp32 buffers to accumulate into"""
         x = _nhwc(x)
         n, c, h, w = x.shape
         cr = fc1.shape[0]
         dev = x.device
+        band = self.la_band_path(x)
         if gz32 is not None:
             gz32 = _nhwc(gz32.float())
         if gz16 is not None:
             gz16 = _nhwc(gz16.to(x.dtype))
+        if gacc is not None:
+            gacc = _nhwc(gacc.float())
+            if not band:                               # tile kernels: fold the accumulator gradient into the fp32 one first
+                gz32 = gacc if gz32 is None else self.add_cast(gz32, gacc, torch.float32)
+                gacc = None
         f32 = dict(dtype=torch.float32, device=dev)
         dx = torch.empty_like(x)
         if into is not None:
@@ -350,23 +418,33 @@ class CudaBackend:
         else:
             d_fc1 = torch.zeros(fc1.shape, **f32); d_fc2 = torch.zeros(fc2.shape, **f32); d_w7 = torch.zeros(w7.shape, **f32)
             dW = torch.zeros(W.shape, **f32); db = torch.zeros((c,), **f32)
-        if want_dz and gz32 is not None and gz16 is None:
-            dz, dz_ptr = gz32, None             # the residual gradient is the incoming gradient itself
+        present = [g for g in (gz32, gz16, gacc) if g is not None]
+        if want_dz and len(present) == 1 and present[0].dtype == torch.float32:
+            dz, dz_buf = present[0], None            # the residual gradient is the incoming gradient itself
         elif want_dz:
-            dz = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
-            dz_ptr = dz
+            dz = dz_buf = torch.empty((n, c, h, w), memory_format=torch.channels_last, **f32)
         else:
-            dz, dz_ptr = None, None
+            dz, dz_buf = None, None
         ws = torch.empty(self.lib.sr_la_chain_workspace_bytes(n, h, w), dtype=torch.uint8, device=dev)
         wts = [a.detach().float().contiguous() for a in (fc1, fc2, w7, W)]
+        tickets = self._la_tickets(dev, n) if band else None
+        a = LaChainGradArgs(n, h, w, c, cr, _dt(x), gz32.data_ptr() if gz32 is not None else None, gz16.data_ptr() if gz16 is not None else None,
+                            gacc.data_ptr() if gacc is not None else None, x.data_ptr(), sv["s"].data_ptr(), sv["m"].data_ptr(),
+                            sv["avg"].data_ptr(), sv["max"].data_ptr(), sv["pstar"].data_ptr(), sv["q"].data_ptr(), sv["cstar"].data_ptr(),
+                            *[v.data_ptr() for v in wts], dx.data_ptr(), d_fc1.data_ptr(), d_fc2.data_ptr(), d_w7.data_ptr(), dW.data_ptr(),
+                            db.data_ptr(), dz_buf.data_ptr() if dz_buf is not None else None,
+                            tickets.data_ptr() if tickets is not None else None, ws.data_ptr())
         es = x.element_size()
-        nbytes = float(x.numel()) * ((4 if gz32 is not None else 0) + (es if gz16 is not None else 0) + es + es + (4 if dz_ptr is not None else 0))
-        self._timed_rec("la_chain_bwd", 0.0, nbytes, lambda: _check(
-            self.lib.sr_la_chain_bwd(_ptr(gz32), _ptr(gz16), _ptr(x), _dt(x), _ptr(sv["s"]), _ptr(sv["m"]), _ptr(sv["avg"]),
-                                     _ptr(sv["max"]), _ptr(sv["pstar"]), _ptr(sv["q"]), _ptr(sv["cstar"]),
-                                     *[_ptr(a) for a in wts], n, h, w, c, cr, _ptr(dx), _ptr(d_fc1), _ptr(d_fc2), _ptr(d_w7),
-                                     _ptr(dW), _ptr(db), _ptr(dz_ptr), _ptr(ws), _stream()), "la_chain_bwd"))
+        nbytes = float(x.numel()) * (sum(g.element_size() for g in present) + es + es + (4 if dz_buf is not None else 0))
+        self._timed_rec("la_chain_bwd", 0.0, nbytes, lambda: _check(self.lib.sr_la_chain_backward(ctypes.byref(a), _stream()), "la_chain_backward"))
         return dx, d_fc1, d_fc2, d_w7, dW, db, dz
+
+    def la_chain_fwd(self, x, t, fc1, fc2, w7, W, b, want_lowp=True):
+        """z = Conv1x1(SLAM(CLAM(x))) + t  ->  (z32, z16 | None, saved)"""
+        return self.la_chain_forward(x, t, fc1, fc2, w7, W, b, want_lowp)[:3]
+
+    def la_chain_bwd(self, gz32, gz16, x, sv, fc1, fc2, w7, W, want_dz=True, into=None):
+        return self.la_chain_backward(gz32, gz16, None, x, sv, fc1, fc2, w7, W, want_dz, into)
 
     def act_bwd(self, gy, y, act, slope, shuffle_r, g, out_dtype):
         """gpre = PixelUnshuffle_r(gy * act'(y)) in out_dtype, shape (N, Cout, Ho, Wo)"""

@@ -36,6 +36,7 @@ bool conv_tc_supported(const sr_conv_desc*, bool dgrad);
 int conv_tc_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 // conv_halo.cu
 bool conv_halo_supported(const sr_conv_desc*, bool dgrad);
+int conv_halo_pool_rows(const sr_conv_desc*);
 int conv_halo_run(const sr_conv_desc*, bool dgrad, const void*, const void*, const float*, const void*, void*, cudaStream_t,
                   const void* mask = nullptr, float mask_slope = 0.f);
 // conv_tc_wgrad.cu
@@ -57,6 +58,10 @@ int la_chain_bwd(const float*, const void*, const void*, int, const float*, cons
                  const float*, const unsigned char*, const float*, const float*, const float*, const float*, int, int, int, int,
                  void*, float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
 int act_bwd(const void*, int, const void*, int, int, float, int, int, int, int, int, void*, int, cudaStream_t);
+bool la_chain_band_path(int, int, int, int);
+int la_band_count(int, int, int);
+int la_chain_forward(const sr_la_chain_args*, cudaStream_t);
+int la_chain_backward(const sr_la_chain_grad_args*, cudaStream_t);
 // bn.cu
 int bn_act_fwd(const void*, int, long long, int, const float*, const float*, float, float, float, float*, float*, void*, float*, float*, cudaStream_t);
 int bn_act_bwd(const void*, const void*, int, long long, int, const float*, float, void*, float*, float*, cudaStream_t);
@@ -139,6 +144,11 @@ int sr_version(void) { return 100; }
 int sr_device_check(void) { return arch_check(); }
 int64_t sr_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int sr_conv_pool_rows(const sr_conv_desc* d) {
+    if (!d || d->impl == SR_IMPL_SIMT || d->impl == SR_IMPL_TCGEN05 || (d->Cout <= 4)) return 0;
+    return conv_halo_pool_rows(d);
+}
+
 int sr_conv_uses_tcgen05(const sr_conv_desc* d, int kind) {
     if (!d || d->impl == SR_IMPL_SIMT) return 0;
     if (kind == 2) return conv_tc_wgrad_supported(d) ? 1 : 0;
@@ -179,6 +189,7 @@ int sr_conv2d_fwd(const sr_conv_desc* d, const void* x, const void* w, const flo
     }
     if (halo_ok && !(d->Cout <= 4 && residual) && (d->impl == SR_IMPL_AUTO || d->impl == SR_IMPL_HALO))
         return conv_halo_run(d, false, x, w, bias, residual, y, (cudaStream_t)stream);
+    if (d->pool_sum || d->pool_key) { set_error("conv2d_fwd: pooling partials are emitted by the halo-tile kernel only (sr_conv_pool_rows() == 0 here)"); return SR_ERR_UNSUPPORTED; }
     if (d->impl == SR_IMPL_TCGEN05 && !tc_ok) {
         set_error("conv2d_fwd: tcgen05 path does not support this shape (Cin=%d Cout=%d k=%d s=%d dtype=%d)", d->Cin, d->Cout, d->kh, d->stride, d->in_dtype);
         return SR_ERR_UNSUPPORTED;
@@ -286,6 +297,33 @@ int sr_la_chain_bwd(const float* gz32, const void* gz16, const void* x, int x_dt
                "la_chain_bwd: NULL pointer");
     return la_chain_bwd(gz32, gz16, x, x_dtype, s, m, avg, mx, pstar, q, cstar, fc1, fc2, w7, W, N, H, Wd, Cr, dx, d_fc1, d_fc2,
                         d_w7, dW, db, dz_out, (float*)workspace, (cudaStream_t)stream);
+}
+
+int sr_la_chain_band_path(int N, int H, int W, int x_dtype) { return (N > 0 && H > 0 && W > 0 && la_chain_band_path(N, H, W, x_dtype)) ? 1 : 0; }
+
+int sr_la_chain_pool_rows(int N, int H, int W) { return (N > 0 && H > 0 && W > 0) ? la_band_count(N, H, W) : 0; }
+
+int sr_la_chain_forward(const sr_la_chain_args* a, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a != nullptr, "la_chain_forward: NULL argument block");
+    SR_REQUIRE(a->C == 64 && a->Cr >= 1 && a->Cr <= 16, "la_chain: C must be 64 and 1 <= Cr <= 16 (got %d, %d)", a->C, a->Cr);
+    SR_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && (a->x_dtype == SR_F32 || a->x_dtype == SR_BF16), "la_chain_forward: bad geometry / dtype");
+    SR_REQUIRE(a->x && a->t && a->fc1 && a->fc2 && a->w7 && a->Wm && a->bias && a->z32 && a->s && a->m && a->avg && a->max && a->pstar && a->q && a->cstar && a->workspace,
+               "la_chain_forward: NULL pointer");
+    SR_REQUIRE((a->acc_in == nullptr) == (a->acc_out == nullptr), "la_chain_forward: acc_in and acc_out must both be given or both NULL");
+    SR_REQUIRE((a->out_pool_sum == nullptr) == (a->out_pool_key == nullptr), "la_chain_forward: out_pool_sum / out_pool_key go together");
+    return la_chain_forward(a, (cudaStream_t)stream);
+}
+
+int sr_la_chain_backward(const sr_la_chain_grad_args* a, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a != nullptr, "la_chain_backward: NULL argument block");
+    SR_REQUIRE(a->C == 64 && a->Cr >= 1 && a->Cr <= 16, "la_chain: C must be 64 and 1 <= Cr <= 16 (got %d, %d)", a->C, a->Cr);
+    SR_REQUIRE((a->gz32 || a->gz16 || a->gacc) && a->x && a->s && a->m && a->avg && a->max && a->pstar && a->q && a->cstar && a->fc1 && a->fc2 && a->w7 && a->Wm &&
+               a->dx && a->d_fc1 && a->d_fc2 && a->d_w7 && a->dW && a->db && a->workspace, "la_chain_backward: NULL pointer");
+    return la_chain_backward(a, (cudaStream_t)stream);
 }
 
 int sr_act_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, int act, float slope, int shuffle_r, int N, int Ho, int Wo,

@@ -40,7 +40,78 @@ struct HaloParams {
     const void* mask;                // nullable bf16 tensor shaped like the output: out *= act'(mask)
     float mask_slope;
     void* out;
+    // CLAM pooling partials of the (bf16) output, emitted by the epilogue for the local-attention chain that follows conv2 of a
+    // RAB (la_band.cu): [N][pool_rows][Cout] channel sums and packed (max, first arg-max pixel) keys, one row per
+    // (pixel tile of the image, 32-row quarter of the tile); nullable
+    float* pool_sum; unsigned int* pool_key; int pool_rows;
 };
+
+__device__ __forceinline__ unsigned int hl_bf16_key(__nv_bfloat16 v) {
+    const unsigned int b = __bfloat16_as_ushort(v);
+    return (b & 0x8000u) ? (~b & 0xFFFFu) : (b | 0x8000u);
+}
+
+// Epilogue of one 32-row x 32-column accumulator chunk (lane = row) for launches that also emit the CLAM pooling partials:
+// bias + activation -> bf16 -> 16-byte stores, then the column maxima (packed with the pixel index) and column sums of the
+// ROUNDED values (what the chain will read back) by a butterfly transpose-reduce — 31 shuffles per quantity, after which lane L
+// holds column L.  Rows that are not output pixels store nothing and contribute nothing.  The value array is reused in place
+// (keys first, then sums) so that the extra live state is one 32-register array.
+template <int ACT>
+__device__ __forceinline__ void hl_store_pool_chunk(const uint32_t (&v)[32], const float* bias_s, float slope, bool valid, __nv_bfloat16* o,
+                                                    unsigned int ptag, int lane, float* psum, unsigned int* pkey) {
+    float f[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float4 b = lds128(bias_s + g * 4);
+        f[g * 4 + 0] = __bfloat162float(__float2bfloat16_rn(tc_act<ACT>(__uint_as_float(v[g * 4 + 0]) + b.x, slope)));
+        f[g * 4 + 1] = __bfloat162float(__float2bfloat16_rn(tc_act<ACT>(__uint_as_float(v[g * 4 + 1]) + b.y, slope)));
+        f[g * 4 + 2] = __bfloat162float(__float2bfloat16_rn(tc_act<ACT>(__uint_as_float(v[g * 4 + 2]) + b.z, slope)));
+        f[g * 4 + 3] = __bfloat162float(__float2bfloat16_rn(tc_act<ACT>(__uint_as_float(v[g * 4 + 3]) + b.w, slope)));
+    }
+    if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint4 w;                                  // f is bf16-representable: its upper 16 bits ARE the bf16 value
+            w.x = (__float_as_uint(f[g * 8 + 0]) >> 16) | (__float_as_uint(f[g * 8 + 1]) & 0xFFFF0000u);
+            w.y = (__float_as_uint(f[g * 8 + 2]) >> 16) | (__float_as_uint(f[g * 8 + 3]) & 0xFFFF0000u);
+            w.z = (__float_as_uint(f[g * 8 + 4]) >> 16) | (__float_as_uint(f[g * 8 + 5]) & 0xFFFF0000u);
+            w.w = (__float_as_uint(f[g * 8 + 6]) >> 16) | (__float_as_uint(f[g * 8 + 7]) & 0xFFFF0000u);
+            reinterpret_cast<uint4*>(o)[g] = w;
+        }
+    }
+    {
+        unsigned int k[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const unsigned int bits = __float_as_uint(f[i]) >> 16;
+            const unsigned int key = (bits & 0x8000u) ? (~bits & 0xFFFFu) : (bits | 0x8000u);       // orderable bf16 key
+            k[i] = valid ? ((key << 16) | ptag) : 0u;
+        }
+#pragma unroll
+        for (int half = 16; half >= 1; half >>= 1) {
+            const bool up = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const unsigned int recv = __shfl_xor_sync(0xffffffffu, up ? k[i] : k[i + half], half);
+                const unsigned int keep = up ? k[i + half] : k[i];
+                k[i] = keep > recv ? keep : recv;
+            }
+        }
+        pkey[lane] = k[0];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = valid ? f[i] : 0.f;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, up ? f[i] : f[i + half], half);
+            f[i] = (up ? f[i + half] : f[i]) + recv;
+        }
+    }
+    psum[lane] = f[0];
+}
 
 constexpr int HL_EPI_WARPS = 8;
 constexpr int HL_THREADS = 96 + 32 * HL_EPI_WARPS;   // warp 0 TMA, warps 1-2 MMA issuers, warps 3..10 epilogue
@@ -79,7 +150,7 @@ __device__ __forceinline__ void hl_tile_origin(const HaloParams& p, int p_tile, 
 // split (dual, a single tile whose channel blocks were divided between the two issuers): both groups wait for BOTH
 // accumulators, group g sums and stores the chunks of parity g, and after a barrier among the eight epilogue warps group g
 // releases issuer g's buffer.  Every warp tracks both issuers' buffer indices so the three item kinds can interleave.
-template <typename OutT, int ACT>
+template <typename OutT, int ACT, bool POOL>
 __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
                                             const float* bias_s, int quarter, int grp, int lane) {
     const int j = quarter * 32 + lane;           // MMA row
@@ -105,7 +176,17 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
             const int oy = y0 + tr, ox = x0 + cp - 1;
             const bool valid = tr < p.TR && cp >= 1 && cp <= p.TW && oy < p.H && ox < p.W;
             const long long row_idx = (((long long)n * p.H + oy) * p.W + ox) * p.Cout;
+            const int tile_in_img = p_tile - n * (p.tiles_y * p.tiles_x);
             auto emit = [&](const uint32_t (&v)[32], int c) {
+                if (POOL) {                      // (bf16 output, no residual / mask / shuffle: checked on the host) every lane takes part
+                    if (sizeof(OutT) == 2) {
+                        const int col = nb * p.block_n + c * 32;
+                        const long long prow = ((long long)n * p.pool_rows + tile_in_img * 4 + quarter) * p.Cout + col;
+                        hl_store_pool_chunk<ACT>(v, bias_s + col, p.slope, valid, reinterpret_cast<__nv_bfloat16*>(out) + row_idx + col,
+                                                 (unsigned int)(0xFFFF - (oy * p.W + ox)) & 0xFFFFu, lane, p.pool_sum + prow, p.pool_key + prow);
+                    }
+                    return;
+                }
                 if (!valid) return;
                 if (p.narrow) {              // thin output (RGB / 1-channel critic map): only the first Cout accumulator columns are real
                     if (c == 0) {
@@ -178,7 +259,9 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
     }
 }
 
-template <typename OutT>
+// POOL: the instantiation whose epilogue also emits the CLAM pooling partials (RAB conv2 launches only) — a separate
+// kernel so that its extra register pressure (spills) never touches the other convolutions
+template <typename OutT, bool POOL>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -359,10 +442,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int e = warp - 3;                    // 0..7
         const int quarter = warp & 3, grp = e >> 2;
         switch (p.act) {
-            case SR_ACT_LRELU: hl_epilogue<OutT, SR_ACT_LRELU>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
-            case SR_ACT_RELU: hl_epilogue<OutT, SR_ACT_RELU>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
-            case SR_ACT_SIGMOID: hl_epilogue<OutT, SR_ACT_SIGMOID>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
-            default: hl_epilogue<OutT, SR_ACT_NONE>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            case SR_ACT_LRELU: hl_epilogue<OutT, SR_ACT_LRELU, POOL>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            case SR_ACT_RELU: hl_epilogue<OutT, SR_ACT_RELU, POOL>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            case SR_ACT_SIGMOID: hl_epilogue<OutT, SR_ACT_SIGMOID, false>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            default: hl_epilogue<OutT, SR_ACT_NONE, POOL>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
         }
     }
     tc_fence_before();
@@ -389,6 +472,24 @@ bool conv_halo_supported(const sr_conv_desc* d, bool dgrad) {
     return true;
 }
 
+// geometry of the pixel tiling (depends on the map size only)
+static void hl_tiling(int H, int W, int& tiles_x, int& TW, int& TR, int& tiles_y) {
+    tiles_x = (int)cdiv(W, 62);
+    TW = (int)cdiv(W, tiles_x);
+    TR = 129 / (TW + 2);
+    if (TR > H) TR = H;
+    tiles_y = (int)cdiv(H, TR);
+}
+
+// rows per image of the pooling partials a forward launch emits (0: this convolution cannot emit them)
+int conv_halo_pool_rows(const sr_conv_desc* d) {
+    if (!conv_halo_supported(d, false) || d->Cout % 64 != 0 || d->shuffle_r > 1 || d->out_dtype != SR_BF16) return 0;
+    if ((long long)d->H * d->W > 65535) return 0;
+    int tx, TW, TR, ty;
+    hl_tiling(d->H, d->W, tx, TW, TR, ty);
+    return tx * ty * 4;
+}
+
 int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* w, const float* bias,
                   const void* residual, void* dst, cudaStream_t st, const void* mask, float mask_slope) {
     int rc = load_driver_fns();
@@ -404,10 +505,8 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = Cd;
     // tile = TR rows x TW columns of one image with TR * (TW + 2) <= 129 MMA rows; column strips of <= 62 pixels keep
     // the halo tile (and its shared-memory stage) small for every map width
-    p.tiles_x = (int)cdiv(d->W, 62);
-    p.TW = (int)cdiv(d->W, p.tiles_x); p.TWp = p.TW + 2; p.TR = 129 / p.TWp;
-    if (p.TR > d->H) p.TR = d->H;
-    p.tiles_y = (int)cdiv(d->H, p.TR);
+    hl_tiling(d->H, d->W, p.tiles_x, p.TW, p.TR, p.tiles_y);
+    p.TWp = p.TW + 2;
     p.p_tiles = d->N * p.tiles_y * p.tiles_x;
     p.c_blocks = Cs / 64;
     p.flip = dgrad ? 1 : 0;
@@ -415,6 +514,11 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.shuffle_r = dgrad ? 0 : d->shuffle_r;
     p.bias = bias; p.residual = residual; p.out = dst;
     p.mask = mask; p.mask_slope = mask_slope;
+    if (!dgrad && d->pool_sum && d->pool_key) {
+        const int rows = conv_halo_pool_rows(d);
+        if (!rows || residual || mask) { set_error("conv_halo: pooling partials need a plain bf16 forward convolution with Cout %% 64 == 0"); return SR_ERR_UNSUPPORTED; }
+        p.pool_sum = (float*)d->pool_sum; p.pool_key = (unsigned int*)d->pool_key; p.pool_rows = rows;
+    }
     p.a_box_bytes = (p.TR + 2) * p.TWp * 128;
     // the tap views of junk rows reach up to pixel row 129 + 2*TWp of the stage: keep that inside the stage
     const int rows_needed = 130 + 2 * p.TWp, rows_loaded = (p.TR + 2) * p.TWp;
@@ -491,13 +595,16 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     if (rc != SR_OK) return rc;
     const size_t smem = 1024 + tile_bytes + 1024 + HL_BIAS_MAX * 4;
     const bool out_bf16 = d->out_dtype == SR_BF16;
-    static bool attr_set[2] = {false, false};
-    if (out_bf16) {
-        if (!attr_set[0]) { cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[0] = true; }
-        conv_halo_kernel<__nv_bfloat16><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
+    static bool attr_set[3] = {false, false, false};
+    if (p.pool_sum) {
+        if (!attr_set[2]) { cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[2] = true; }
+        conv_halo_kernel<__nv_bfloat16, true><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
+    } else if (out_bf16) {
+        if (!attr_set[0]) { cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[0] = true; }
+        conv_halo_kernel<__nv_bfloat16, false><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
     } else {
-        if (!attr_set[1]) { cudaFuncSetAttribute(conv_halo_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[1] = true; }
-        conv_halo_kernel<float><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
+        if (!attr_set[1]) { cudaFuncSetAttribute(conv_halo_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[1] = true; }
+        conv_halo_kernel<float, false><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
     }
     count_launch();
     return check_launch("conv_halo_kernel");

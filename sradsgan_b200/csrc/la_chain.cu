@@ -12,14 +12,13 @@
 // All reductions are warp-shuffle / shared-memory based with fp32 accumulation; every kernel is HBM/L2
 // bound.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "la_common.cuh"
 
 namespace sr {
-
-constexpr int LA_C = 64;
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -376,45 +375,6 @@ la_bwd_apply_kernel(const float* __restrict__ gz32, const T* __restrict__ gz16, 
 // memory as bf16 rows of 72 elements (144 B pitch: ldmatrix rows and fragment loads hit 32 distinct banks).
 // fp32 mode keeps the SIMT kernels (<=1e-4 parity).
 // ------------------------------------------------------------------------------------------------
-constexpr int LA_LD = LA_C + 8;
-
-__device__ __forceinline__ uint32_t la_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(la_smem_u32(p)));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(la_smem_u32(p)));
-}
-// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col)
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-    uint2 v;
-    v.x = *reinterpret_cast<uint32_t*>(&lo); v.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(p) = v;
-}
-
-// v -> (hi, lo) bf16 pair with hi + lo = v to 16 mantissa bits: operands that are fp32 in the reference chain (the trunk
-// gradient, the gate products, the 1x1 weights) enter the tensor-core products as hi*hi + lo*hi + hi*lo, so the chain keeps
-// fp32-class accuracy (the dropped lo*lo term is 2^-18 relative) at three MMAs per product.
-__device__ __forceinline__ void st_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float a, float b, float c, float d) {
-    const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
-    const float ch = __bfloat162float(__float2bfloat16_rn(c)), dh = __bfloat162float(__float2bfloat16_rn(d));
-    st_bf16x4(hi, ah, bh, ch, dh);
-    st_bf16x4(lo, a - ah, b - bh, c - ch, d - dh);
-}
-__device__ __forceinline__ void st_split1(__nv_bfloat16* hi, __nv_bfloat16* lo, float a) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(a);
-    *hi = h;
-    *lo = __float2bfloat16_rn(a - __bfloat162float(h));
-}
-
 // z = W.(m*s*x) + b + t, persistent over 64-pixel tiles.  warp = (16-pixel row tile mt, 32-channel half nh).
 __global__ void __launch_bounds__(256)
 la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s, const float* __restrict__ q,
@@ -501,10 +461,11 @@ la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 //   g = m*dv = W^T e (GEMM 1, stored fp32),  dm = (sum_ci g*u) / m,  dW += e^T u (GEMM 2, K = pixels, both operands
 //   read transposed through ldmatrix.trans),  db += sum dz (fp32, from the loaded values),  dz_out = dz.
 __global__ void __launch_bounds__(256)
-la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __restrict__ gz16, const __nv_bfloat16* __restrict__ x,
+la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __restrict__ gz16, const float* __restrict__ gacc,
+                        const __nv_bfloat16* __restrict__ x,
                         const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ Wm, int P, long long NP,
                         int tiles, float* __restrict__ g_out, float* __restrict__ dm, float* __restrict__ dW, float* __restrict__ db,
-                        float* __restrict__ dz_out) {
+                        float* __restrict__ dz_out, float* __restrict__ wpart) {
     extern __shared__ __align__(16) unsigned char la_mma_smem[];
     __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(la_mma_smem);      // [co][ci] hi
     __nv_bfloat16* Wl = Ws + LA_C * LA_LD;                                   //          lo
@@ -543,6 +504,7 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
                     load4<__nv_bfloat16>(x + pix * LA_C + c, xv);
                     if (gz32) { const float4 a = *reinterpret_cast<const float4*>(gz32 + pix * LA_C + c); d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; }
                     if (gz16) { float b[4]; load4<__nv_bfloat16>(gz16 + pix * LA_C + c, b); d[0] += b[0]; d[1] += b[1]; d[2] += b[2]; d[3] += b[3]; }
+                    if (gacc) { const float4 a = *reinterpret_cast<const float4*>(gacc + pix * LA_C + c); d[0] += a.x; d[1] += a.y; d[2] += a.z; d[3] += a.w; }
                     if (dz_out) *reinterpret_cast<float4*>(dz_out + pix * LA_C + c) = make_float4(d[0], d[1], d[2], d[3]);
                     const float4 sv = *reinterpret_cast<const float4*>(s + n * LA_C + c);
                     st_split4(Es + pl * LA_LD + c, El + pl * LA_LD + c, mp * d[0], mp * d[1], mp * d[2], mp * d[3]);
@@ -626,13 +588,16 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
             if (pix < NP) dm[pix] = mp > 0.f ? (dm_part[0][t] + dm_part[1][t]) / mp : 0.f;     // m = 0: de = dm*m*(1-m) = 0 anyway
         }
     }
+    // per-block results: either added to dW / db with fp32 atomics, or (band path) written as ONE partial row per block that
+    // la_bwd_band_kernel sums in a fixed order — 4160 plain stores instead of 4160 contended atomics per block
+    float* wrow = wpart ? wpart + (long long)blockIdx.x * (LA_C * LA_C + LA_C) : nullptr;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            float* o = dW + (mt * 16 + g + rr * 8) * LA_C + nh * 32 + nt * 8 + 2 * tq;
-            atomicAdd(o, wacc[nt][rr * 2]);
-            atomicAdd(o + 1, wacc[nt][rr * 2 + 1]);
+            const int e = (mt * 16 + g + rr * 8) * LA_C + nh * 32 + nt * 8 + 2 * tq;
+            if (wrow) *reinterpret_cast<float2*>(wrow + e) = make_float2(wacc[nt][rr * 2], wacc[nt][rr * 2 + 1]);
+            else { atomicAdd(dW + e, wacc[nt][rr * 2]); atomicAdd(dW + e + 1, wacc[nt][rr * 2 + 1]); }
         }
     {
         const int cb = (t & 3) * 4;
@@ -642,7 +607,10 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
             for (int k = 0; k < 4; ++k) atomicAdd(&bsum[cb + 16 * jj + k], bacc[jj * 4 + k]);
     }
     __syncthreads();
-    if (t < LA_C) atomicAdd(db + t, bsum[t]);
+    if (t < LA_C) {
+        if (wrow) wrow[LA_C * LA_C + t] = bsum[t];
+        else atomicAdd(db + t, bsum[t]);
+    }
 }
 
 static int la_mma_enabled() {
@@ -727,39 +695,6 @@ la_conv7_wgrad_kernel(const float* __restrict__ dm, const float* __restrict__ m,
     }
     __syncthreads();
     if (threadIdx.x < 98) atomicAdd(dw7 + threadIdx.x, red[threadIdx.x] + red[98 + threadIdx.x]);
-}
-
-// gate backward (tiny, per image): d(sigmoid) -> MLP backward; weight gradients via fp32 atomics.  Called by ALL threads of a
-// block (block-uniform), the first LA_C of which do the work.  `ds` is read through L2 (it was produced by other blocks' atomics).
-__device__ __forceinline__ void la_gate_bwd_body(int n, const float* __restrict__ ds, const float* __restrict__ s, const float* __restrict__ avg,
-                                                 const float* __restrict__ mx, const float* __restrict__ fc1, const float* __restrict__ fc2, int Cr,
-                                                 float* __restrict__ d_fc1, float* __restrict__ d_fc2, float* __restrict__ da, float* __restrict__ dmx) {
-    const int c = threadIdx.x;
-    __shared__ float a[LA_C], m[LA_C], dov[LA_C], pa[16], pm[16], dha[16], dhm[16];
-    if (c < LA_C) {
-        a[c] = avg[n * LA_C + c]; m[c] = mx[n * LA_C + c];
-        const float sv = s[n * LA_C + c];
-        dov[c] = __ldcg(ds + n * LA_C + c) * sv * (1.f - sv);
-    }
-    __syncthreads();
-    if (c < Cr) {
-        float u = 0.f, v = 0.f, d = 0.f;
-        for (int k = 0; k < LA_C; ++k) { u += fc1[c * LA_C + k] * a[k]; v += fc1[c * LA_C + k] * m[k]; d += fc2[k * Cr + c] * dov[k]; }
-        pa[c] = u; pm[c] = v;
-        dha[c] = u > 0.f ? d : 0.f;
-        dhm[c] = v > 0.f ? d : 0.f;
-    }
-    __syncthreads();
-    if (c < LA_C) {
-        float dav = 0.f, dmv = 0.f;
-        for (int j = 0; j < Cr; ++j) {
-            atomicAdd(d_fc2 + c * Cr + j, dov[c] * (fmaxf(pa[j], 0.f) + fmaxf(pm[j], 0.f)));
-            atomicAdd(d_fc1 + j * LA_C + c, dha[j] * a[c] + dhm[j] * m[c]);
-            dav += fc1[j * LA_C + c] * dha[j];
-            dmv += fc1[j * LA_C + c] * dhm[j];
-        }
-        da[n * LA_C + c] = dav; dmx[n * LA_C + c] = dmv;
-    }
 }
 
 __global__ void __launch_bounds__(LA_C)
@@ -856,6 +791,10 @@ size_t la_workspace_bytes(int N, int H, int W) {
     // fwd: psum, pmax, pidx ; bwd: g, dm, dq, ds, da, dmx
     size_t fwd = (size_t)N * (S > 32 ? S : 32) * LA_C * 12 + (size_t)N * 16 + 64;   // + the fused kernel's partials / barrier counters
     size_t bwd = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + ((size_t)N * P + 4) * 8 + (size_t)N * LA_C * 12 + ((size_t)N + 4) * 4;
+    // band path: g, dm, <= 296 rows of dW | db partials, per-band ds partials, ds / da / dmx
+    const size_t band = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + (size_t)296 * (LA_C * LA_C + LA_C) * 4 +
+                        (size_t)N * 64 * LA_C * 4 + (size_t)N * LA_C * 12 + 64;
+    if (band > bwd) bwd = band;
     return (fwd > bwd ? fwd : bwd) + 256;
 }
 
@@ -910,8 +849,8 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
         const size_t mma_smem = (size_t)6 * LA_C * LA_LD * sizeof(__nv_bfloat16);
         static bool mma_attr = false;
         if (!mma_attr) { cudaFuncSetAttribute(la_bwd_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem); mma_attr = true; }
-        la_bwd_apply_mma_kernel<<<grid, 256, mma_smem, st>>>(gz32, (const __nv_bfloat16*)gz16, (const __nv_bfloat16*)x, s, m, Wm, P, NP, tiles, g, dm, dW,
-                                                     db, dz_out);
+        la_bwd_apply_mma_kernel<<<grid, 256, mma_smem, st>>>(gz32, (const __nv_bfloat16*)gz16, nullptr, (const __nv_bfloat16*)x, s, m, Wm, P, NP, tiles, g, dm, dW,
+                                                     db, dz_out, nullptr);
     } else
         la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
     // The 7x7 weight gradient only feeds the optimiser: it runs on an internal side stream (forked / joined with events, so
@@ -947,22 +886,9 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
     return check_launch("la_chain_bwd");
 }
 
-int la_fused_fwd(const void*, int, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
-                 float*, void*, float*, float*, float*, float*, int*, float*, unsigned char*, float*, cudaStream_t);
-
 int la_chain_fwd(const void* x, int dtype, const float* t_res, const float* fc1, const float* fc2, const float* w7, const float* Wm,
                  const float* bias, int N, int H, int W, int Cr, float* z32, void* z16, float* s_out, float* m_out, float* avg_out,
                  float* max_out, int* pstar, float* q, unsigned char* cstar, float* ws, cudaStream_t st) {
-    // Experimental (SR_LA_FUSED=1): one co-resident wave with per-image barriers (la_fused.cu).  Measured 36.9 us vs
-    // 39.1 us for the five kernels at the x4 B=16 shape — the chain is latency-, not bandwidth-bound at 54^2 — so the
-    // default stays the multi-kernel path, which needs no co-residency guarantee.
-    static int fused_on = -1;
-    if (fused_on < 0) { const char* e = getenv("SR_LA_FUSED"); fused_on = (e && atoi(e)) ? 1 : 0; }
-    if (fused_on) {
-        const int r = la_fused_fwd(x, dtype, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q,
-                                   cstar, ws, st);
-        if (r != 0) return r < 0 ? r : SR_OK;
-    }
     if (dtype == SR_F32) return la_fwd_t<float>(x, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q, cstar, ws, st);
     return la_fwd_t<__nv_bfloat16>(x, t_res, fc1, fc2, w7, Wm, bias, N, H, W, Cr, z32, z16, s_out, m_out, avg_out, max_out, pstar, q, cstar, ws, st);
 }
@@ -973,6 +899,89 @@ int la_chain_bwd(const float* gz32, const void* gz16, const void* x, int dtype, 
                  float* dW, float* db, float* dz_out, float* ws, cudaStream_t st) {
     if (dtype == SR_F32) return la_bwd_t<float>(gz32, gz16, x, s, m, avg, mx, pstar, q, cstar, fc1, fc2, w7, Wm, N, H, W, Cr, dx, d_fc1, d_fc2, d_w7, dW, db, dz_out, ws, st);
     return la_bwd_t<__nv_bfloat16>(gz32, gz16, x, s, m, avg, mx, pstar, q, cstar, fc1, fc2, w7, Wm, N, H, W, Cr, dx, d_fc1, d_fc2, d_w7, dW, db, dz_out, ws, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// struct-based entry points: band path (la_band.cu) when it applies, else the tile kernels above
+// ------------------------------------------------------------------------------------------------
+bool la_band_supported(int N, int H, int W);
+int la_band_count(int N, int H, int W);
+int la_pool_pack(const void* x, int N, int P, int S, float* psum, unsigned int* pkey, cudaStream_t st);
+int la_band_fwd(LaBandFwd p, cudaStream_t st);
+int la_band_bwd(LaBandBwd p, cudaStream_t st);
+
+static int la_band_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SR_LA_BAND"); on = e ? atoi(e) : 1; }
+    return on;
+}
+
+bool la_chain_band_path(int N, int H, int W, int dtype) { return dtype == SR_BF16 && la_band_enabled() && la_band_supported(N, H, W); }
+
+int la_chain_forward(const sr_la_chain_args* a, cudaStream_t st) {
+    const bool band = la_chain_band_path(a->N, a->H, a->W, a->x_dtype) && a->z16;
+    if (!band) {
+        if (a->acc_out || a->out_pool_sum) { set_error("la_chain_forward: accumulator / pooling outputs need the band path (bf16, H*W <= 65535)"); return SR_ERR_UNSUPPORTED; }
+        return la_chain_fwd(a->x, a->x_dtype, a->t, a->fc1, a->fc2, a->w7, a->Wm, a->bias, a->N, a->H, a->W, a->Cr, a->z32, a->z16, a->s, a->m,
+                            a->avg, a->max, a->pstar, a->q, a->cstar, (float*)a->workspace, st);
+    }
+    LaBandFwd p;
+    memset(&p, 0, sizeof(p));
+    p.x = (const __nv_bfloat16*)a->x; p.t = a->t; p.acc_in = a->acc_in; p.acc_out = a->acc_out;
+    p.fc1 = a->fc1; p.fc2 = a->fc2; p.w7 = a->w7; p.Wm = a->Wm; p.bias = a->bias;
+    p.N = a->N; p.H = a->H; p.W = a->W; p.Cr = a->Cr;
+    p.z32 = a->z32; p.z16 = (__nv_bfloat16*)a->z16;
+    p.s_out = a->s; p.m_out = a->m; p.avg_out = a->avg; p.max_out = a->max; p.pstar = a->pstar; p.q = a->q; p.cstar = a->cstar;
+    p.out_psum = a->out_pool_sum; p.out_pkey = a->out_pool_key;
+    if (a->pool_sum && a->pool_key && a->pool_rows > 0) {
+        p.psum = a->pool_sum; p.pkey = a->pool_key; p.T = a->pool_rows;
+    } else {                                   // no producer-side partials: one pooling kernel first
+        const int P = a->H * a->W, S = la_slices(P);
+        float* psum = (float*)a->workspace;
+        unsigned int* pkey = reinterpret_cast<unsigned int*>(psum + (size_t)a->N * S * LA_C);
+        int rc = la_pool_pack(a->x, a->N, P, S, psum, pkey, st);
+        if (rc) return rc;
+        p.psum = psum; p.pkey = pkey; p.T = S;
+    }
+    return la_band_fwd(p, st);
+}
+
+int la_chain_backward(const sr_la_chain_grad_args* a, cudaStream_t st) {
+    const bool band = la_chain_band_path(a->N, a->H, a->W, a->x_dtype) && a->tickets;
+    if (!band) {
+        if (a->gacc) { set_error("la_chain_backward: the accumulator gradient needs the band path"); return SR_ERR_UNSUPPORTED; }
+        return la_chain_bwd(a->gz32, a->gz16, a->x, a->x_dtype, a->s, a->m, a->avg, a->max, a->pstar, a->q, a->cstar, a->fc1, a->fc2, a->w7,
+                            a->Wm, a->N, a->H, a->W, a->Cr, a->dx, a->d_fc1, a->d_fc2, a->d_w7, a->dW, a->db, a->dz_out, (float*)a->workspace, st);
+    }
+    const int N = a->N, P = a->H * a->W;
+    const long long NP = (long long)N * P;
+    const size_t npa = ((size_t)NP + 3) & ~(size_t)3;
+    const int bands = la_band_count(N, a->H, a->W);
+    float* ws = (float*)a->workspace;
+    float* g = ws; float* dm = g + (size_t)NP * LA_C; float* wpart = dm + npa;
+    const int tiles = (int)cdiv(NP, 64);
+    const int grid = tiles < 296 ? tiles : 296;
+    float* dspart = wpart + (size_t)grid * (LA_C * LA_C + LA_C);
+    float* ds = dspart + (size_t)N * bands * LA_C; float* da = ds + (size_t)N * LA_C; float* dmx = da + (size_t)N * LA_C;
+    const size_t mma_smem = (size_t)6 * LA_C * LA_LD * sizeof(__nv_bfloat16);
+    static bool mma_attr = false;
+    if (!mma_attr) { cudaFuncSetAttribute(la_bwd_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem); mma_attr = true; }
+    la_bwd_apply_mma_kernel<<<grid, 256, mma_smem, st>>>(a->gz32, (const __nv_bfloat16*)a->gz16, a->gacc, (const __nv_bfloat16*)a->x, a->s, a->m, a->Wm,
+                                                         P, NP, tiles, g, dm, a->dW, a->db, a->dz_out, wpart);
+    count_launch();
+    LaBandBwd p;
+    memset(&p, 0, sizeof(p));
+    p.g = g; p.dm = dm; p.m = a->m; p.q = a->q; p.cstar = a->cstar; p.x = (const __nv_bfloat16*)a->x; p.s = a->s; p.avg = a->avg; p.mx = a->max;
+    p.fc1 = a->fc1; p.fc2 = a->fc2; p.w7 = a->w7; p.wpart = wpart; p.nparts = grid;
+    p.N = N; p.H = a->H; p.W = a->W; p.Cr = a->Cr;
+    p.dx = (__nv_bfloat16*)a->dx; p.d_w7 = a->d_w7; p.dW = a->dW; p.db = a->db; p.d_fc1 = a->d_fc1; p.d_fc2 = a->d_fc2;
+    p.dspart = dspart; p.ds = ds; p.da = da; p.dmx = dmx; p.tickets = a->tickets;
+    int rc = la_band_bwd(p, st);
+    if (rc) return rc;
+    la_fix_kernel<__nv_bfloat16><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((__nv_bfloat16*)a->dx, da, dmx, a->pstar, P, NP * LA_C);
+    count_launch();
+    return check_launch("la_chain_backward");
 }
 
 }  // namespace sr

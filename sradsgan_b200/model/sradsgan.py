@@ -200,7 +200,13 @@ def _la_init(mod, planes, la_mode, pool_mode, addconv):
         mod.last_conv = Conv2d(64, 64, 1, bias=True)
 
 
-def _la_forward(mod, out, x):
+def _fused_la(mod):
+    """the default local-attention configuration, the one the fused chain kernels implement"""
+    return (mod.la_mode == 'CA-SA' and mod.addconv and mod.ca.pool_mode == 'Avg|Max' and mod.sa.pool_mode == 'Avg|Max'
+            and mod.sa.conv1.kernel_size == 7 and mod.ca.fc1.out_channels <= 16)
+
+
+def _la_forward(mod, out, x, acc=None, want_pool=False):
     """local-attention tail shared by RAB (:254-274) and ResGroup (:303-323), ending with `out += x`
     (fused into the closing 1x1 conv as a residual epilogue when there is one).  The residual stream `x`
     and the block output stay in fp32: only the branch runs in the compute dtype, so rounding errors do not
@@ -212,9 +218,8 @@ def _la_forward(mod, out, x):
         return mod.ca(out).float() + x
     if m == 'SA':
         return mod.sa(out).float() + x
-    if (m == 'CA-SA' and mod.addconv and out.shape[1] == 64 and mod.ca.pool_mode == 'Avg|Max' and mod.sa.pool_mode == 'Avg|Max'
-            and mod.sa.conv1.kernel_size == 7 and mod.ca.fc1.out_channels <= 16):
-        return ops.local_attn_chain(out, x, mod.ca, mod.sa, mod.conv)      # the default configuration: one fused chain
+    if out.shape[1] == 64 and _fused_la(mod):
+        return ops.local_attn_chain(out, x, mod.ca, mod.sa, mod.conv, acc=acc, want_pool=want_pool)      # the default configuration: one fused chain
     if m in ('CA-SA', 'SA-CA'):
         out = mod.sa(mod.ca(out)) if m == 'CA-SA' else mod.ca(mod.sa(out))
         return mod.conv.fused(out, residual=x, out_dtype=f32) if mod.addconv else out.float() + x
@@ -241,14 +246,16 @@ class RAB(nn.Module):
         elif act_type in ('tanh', 'sigmoid'):
             self.act = nn.Tanh() if act_type == 'tanh' else nn.Sigmoid()
 
-    def forward(self, x):
+    def forward(self, x, want_pool=False):
+        """want_pool (new, internal): also emit the CLAM pooling partials of the output for the ResGroup tail that reads it"""
         xc = ops.to_compute(x)
         c1, c2 = self.conv1, self.conv2
         if (self.act_type in ('lrelu', 'relu') and c1.kernel_size == 3 and c1.stride == 1 and c1.padding == 1 and c1.bias is not None
                 and c2.bias is not None):
-            # the default block: both convolutions in one autograd node (activation derivative fused into conv2's dgrad)
-            out = ops.conv_act_conv(xc, c1, c2, ACT_LRELU if self.act_type == 'lrelu' else ACT_RELU, 0.2)
-            return _la_forward(self, out, x)
+            # the default block: both convolutions in one autograd node (activation derivative fused into conv2's dgrad); conv2's
+            # epilogue emits the pooling partials the chain's CLAM needs
+            out = ops.conv_act_conv(xc, c1, c2, ACT_LRELU if self.act_type == 'lrelu' else ACT_RELU, 0.2, want_pool=_fused_la(self))
+            return _la_forward(self, out, x, want_pool=want_pool)
         if self.act_type == 'lrelu':
             out = self.conv1.fused(xc, ACT_LRELU, 0.2)
         elif self.act_type == 'relu':
@@ -273,8 +280,18 @@ class ResGroup(nn.Module):
                                   for _ in range(n_blocks)])
         _la_init(self, nc, rla_mode, pool_mode, addconv)
 
-    def forward(self, x):
-        return _la_forward(self, ops.to_compute(self.RG(x)), x)
+    def forward(self, x, acc=None):
+        """acc (new, internal): the generator's dense-sampling accumulator; when given, returns (y, acc + y) with the sum
+        `out_all += y` (reference :459) done in the epilogue of the chain kernel"""
+        fused = _fused_la(self)
+        t = x
+        for i, blk in enumerate(self.RG):
+            last = i == len(self.RG) - 1
+            t = blk(t, want_pool=True) if (last and fused and isinstance(blk, RAB)) else blk(t)
+        if acc is not None and not fused:
+            y = _la_forward(self, ops.to_compute(t), x)
+            return y, acc + y
+        return _la_forward(self, ops.to_compute(t), x, acc=acc)
 
 
 class MSB(nn.Module):
@@ -376,8 +393,11 @@ class GeneratorResNet(nn.Module):
         out = self.conv1[0].fused(x, ACT_LRELU, self.conv1[1].negative_slope, out_dtype=torch.float32)
         out_all = msb.float() + out
         for res_group in self.res_groups:
-            y = res_group(out)            # fp32 residual stream
-            out_all = out_all + y
+            if isinstance(res_group, ResGroup):
+                y, out_all = res_group(out, acc=out_all)      # fp32 residual stream; out_all += y inside the chain kernel
+            else:
+                y = res_group(out)
+                out_all = out_all + y
             out = y
         out_all = self.GAB_UP(out_all)
         return self.conv3[0].fused(out_all, out_dtype=torch.float32)
@@ -422,25 +442,26 @@ class Discriminator(nn.Module):
         # eval mode take the unfused module-by-module path.
         if ops.config.double_backward or not self.training:
             return self.model(x)
-        mods = list(self.model)
         taps = self.block_taps
-        i = 0
-        while i < len(mods):
-            m = mods[i]
-            nxt = mods[i + 1] if i + 1 < len(mods) else None
-            nxt2 = mods[i + 2] if i + 2 < len(mods) else None
-            if isinstance(m, Conv2d) and isinstance(nxt, BatchNorm2d) and isinstance(nxt2, LeakyReLU):
-                x = ops.bn_leaky_relu(m(x), nxt, nxt2.negative_slope)             # conv -> fused BN+LReLU
-                i += 3
-            elif isinstance(m, Conv2d) and isinstance(nxt, LeakyReLU):
-                x = ops.conv2d_act(x, m.weight, m.bias, m.stride, m.padding, ACT_LRELU, nxt.negative_slope)   # conv + LReLU epilogue
-                i += 2
-            else:
-                x = m(x)
-                i += 1
+        i, n = 0, len(self.model)
+        while i < n:
+            x, i = self.run_block(i, x)
             if taps is not None:
                 taps[i - 1] = x.detach()
         return x
+
+    def run_block(self, i, x):
+        """one fused block of the training path starting at Sequential index i: conv -> BatchNorm(train) + LeakyReLU,
+        conv + LeakyReLU (epilogue), or a single module.  Returns (output, index of the next block)."""
+        mods = self.model
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        nxt2 = mods[i + 2] if i + 2 < len(mods) else None
+        if isinstance(m, Conv2d) and isinstance(nxt, BatchNorm2d) and isinstance(nxt2, LeakyReLU):
+            return ops.bn_leaky_relu(m(x), nxt, nxt2.negative_slope), i + 3             # conv -> fused BN+LReLU
+        if isinstance(m, Conv2d) and isinstance(nxt, LeakyReLU):
+            return ops.conv2d_act(x, m.weight, m.bias, m.stride, m.padding, ACT_LRELU, nxt.negative_slope), i + 2   # conv + LReLU epilogue
+        return m(x), i + 1
 
 
 from .trainer import SRADSGAN  # noqa: E402,F401  (reference: class SRADSGAN lives in this module, :510)

@@ -391,21 +391,29 @@ class ConvActConv(Function):
     tensor-core dgrad kernel (sr_conv2d_dgrad_act) instead of a separate pass over the wide tensor."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, act, slope, residual=None, out_dtype=None):
+    def forward(ctx, x, w1, b1, w2, b2, act, slope, residual=None, out_dtype=None, want_pool=False):
         g1 = conv_geom(x.shape, w1.shape, 1, 1)
         be = _lib.backend()
         y1 = be.conv_fwd(x, packed(w1, 0, x.dtype), b1, None, g1, act, slope, impl=config.conv_impl)
         g2 = conv_geom(y1.shape, w2.shape, 1, 1)
-        y2 = be.conv_fwd(y1, packed(w2, 0, x.dtype), b2, residual, g2, out_dtype=out_dtype, impl=config.conv_impl)
+        pool = None
+        if want_pool:                  # conv2's epilogue also emits the CLAM pooling partials of y2 for the chain behind it
+            y2, pool = be.conv_fwd(y1, packed(w2, 0, x.dtype), b2, residual, g2, out_dtype=out_dtype, impl=config.conv_impl, want_pool=True)
+        else:
+            y2 = be.conv_fwd(y1, packed(w2, 0, x.dtype), b2, residual, g2, out_dtype=out_dtype, impl=config.conv_impl)
         ctx.g1, ctx.g2, ctx.act, ctx.slope = g1, g2, act, slope
         ctx.params = (w1, b1, w2, b2)
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, y1, w1, w2)
+        if pool is not None:
+            ctx.mark_non_differentiable(pool[0], pool[1])
+            ctx.pool_rows = pool[2]
+            return y2, pool[0], pool[1]
         return y2
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gy2_in):
+    def backward(ctx, gy2_in, *_unused):
         x, y1, w1, w2 = ctx.saved_tensors
         _, b1, _, b2 = ctx.params
         be = _lib.backend()
@@ -415,7 +423,7 @@ class ConvActConv(Function):
         gw2, gb2 = _wgrad(y1, gy2, ctx.g2, w2, b2, True, ctx.needs_input_grad[3], ctx.needs_input_grad[4])
         gx = be.conv_dgrad(g1, packed(w1, 1, x.dtype), ctx.g1, impl=config.conv_impl) if ctx.needs_input_grad[0] else None
         gw1, gb1 = _wgrad(x, g1, ctx.g1, w1, b1, True, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        return gx, gw1, gb1, gw2, gb2, None, None, g_res, None
+        return gx, gw1, gb1, gw2, gb2, None, None, g_res, None, None
 
 
 class MaxPool2x2(Function):
@@ -437,59 +445,97 @@ def maxpool2x2(x):
     return MaxPool2x2.apply(to_compute(x))
 
 
-def conv_act_conv(x, conv1, conv2, act, slope, residual=None, out_dtype=None):
-    """conv1 -> activation -> conv2 (+ residual) for two 3x3 / stride 1 / pad 1 Conv2d modules with biases"""
+def conv_act_conv(x, conv1, conv2, act, slope, residual=None, out_dtype=None, want_pool=False):
+    """conv1 -> activation -> conv2 (+ residual) for two 3x3 / stride 1 / pad 1 Conv2d modules with biases.
+    want_pool: conv2's epilogue also emits the CLAM pooling partials of its output (attached as `._sr_pool`)."""
     if residual is not None:
         od = out_dtype or config.compute_dtype
         residual = residual.to(od).contiguous(memory_format=torch.channels_last)
-    return ConvActConv.apply(to_compute(x), conv1.weight, conv1.bias, conv2.weight, conv2.bias, act, slope, residual, out_dtype)
+    x = to_compute(x)
+    want_pool = bool(want_pool and residual is None and x.is_cuda and x.dtype == torch.bfloat16)
+    out = ConvActConv.apply(x, conv1.weight, conv1.bias, conv2.weight, conv2.bias, act, slope, residual, out_dtype, want_pool)
+    if isinstance(out, tuple):
+        y2, ps, pk = out
+        y2._sr_pool = (ps, pk, ps.shape[1])
+        return y2
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
 # fused local-attention chain (CLAM -> SLAM -> 1x1 conv -> + residual), C = 64
 # ----------------------------------------------------------------------------------------------
 class LocalAttnChain(Function):
-    """(z32, z16) = Conv1x1(SLAM(CLAM(x))) + t.  z32 continues the fp32 residual trunk, z16 (same values in
-    the compute dtype) feeds the next 3x3 convolution; their gradients are summed inside the backward kernel.
-    In fp32 mode only z32 is produced."""
+    """(z32, z16[, acc + z][, pooling partials of z16]) = Conv1x1(SLAM(CLAM(x))) + t.  z32 continues the fp32 residual trunk,
+    z16 (same values in the compute dtype) feeds the next 3x3 convolution; their gradients — and the gradient of the
+    dense-sampling accumulator, when the chain adds its output to one (reference model/sradsgan.py:459) — are summed inside the
+    backward kernel.  In fp32 mode only z32 is produced."""
 
     @staticmethod
-    def forward(ctx, x, t, fc1, fc2, w7, W, b, lowp):
-        z32, z16, sv = _lib.backend().la_chain_fwd(x, t, fc1, fc2, w7, W, b, want_lowp=lowp)
+    def forward(ctx, x, t, acc, fc1, fc2, w7, W, b, lowp, pool, want_pool):
+        z32, z16, sv, acc_out, out_pool = _lib.backend().la_chain_forward(x, t, fc1, fc2, w7, W, b, want_lowp=lowp, pool=pool, acc=acc,
+                                                                            want_pool=want_pool)
         ctx.sv = sv
-        ctx.lowp = lowp
+        ctx.layout = (lowp, acc is not None, out_pool is not None)
         ctx.params = (fc1, fc2, w7, W, b)
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, fc1, fc2, w7, W)
-        return (z32, z16) if lowp else z32
+        outs = [z32]
+        if lowp:
+            outs.append(z16)
+        if acc is not None:
+            outs.append(acc_out)
+        if out_pool is not None:
+            ctx.mark_non_differentiable(out_pool[0], out_pool[1])
+            outs += [out_pool[0], out_pool[1]]
+        return tuple(outs) if len(outs) > 1 else z32
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gz32, gz16=None):
+    def backward(ctx, gz32, *rest):
         x, fc1, fc2, w7, W = ctx.saved_tensors
-        if gz32 is None and gz16 is None:
-            return (None,) * 8
+        lowp, has_acc, _ = ctx.layout
+        rest = list(rest)
+        gz16 = rest.pop(0) if lowp else None
+        gacc = rest.pop(0) if has_acc else None
+        if gz32 is None and gz16 is None and gacc is None:
+            return (None,) * 11
         targets = [_grad_target(p) for p in ctx.params]
         into = targets if all(t is not None for t in targets) else None
-        dx, d_fc1, d_fc2, d_w7, dW, db, dz = _lib.backend().la_chain_bwd(gz32, gz16, x, ctx.sv, fc1, fc2, w7, W,
-                                                                          want_dz=ctx.needs_input_grad[1], into=into)
+        dx, d_fc1, d_fc2, d_w7, dW, db, dz = _lib.backend().la_chain_backward(gz32, gz16, gacc, x, ctx.sv, fc1, fc2, w7, W,
+                                                                              want_dz=ctx.needs_input_grad[1], into=into)
+        dacc = gacc if ctx.needs_input_grad[2] else None       # d(acc + z)/d(acc) = identity: the gradient passes through untouched
         if into is not None:
-            return dx, dz, None, None, None, None, None, None
-        return dx, dz, d_fc1, d_fc2, d_w7, dW, db, None
+            return dx, dz, dacc, None, None, None, None, None, None, None, None
+        return dx, dz, dacc, d_fc1, d_fc2, d_w7, dW, db, None, None, None
 
 
-def local_attn_chain(x, t, ca, sa, conv):
-    """x: conv output (compute dtype), t: residual (fp32 trunk); ca/sa/conv: CLAM, SLAM, 1x1 Conv2d modules.
-    Returns the fp32 trunk tensor; its compute-dtype twin rides along as `._sr_lowp` (picked up by to_compute)."""
+def local_attn_chain(x, t, ca, sa, conv, acc=None, want_pool=False):
+    """x: conv output (compute dtype; its `._sr_pool` partials are used when present), t: residual (fp32 trunk); ca/sa/conv:
+    CLAM, SLAM, 1x1 Conv2d modules.  Returns the fp32 trunk tensor — its compute-dtype twin rides along as `._sr_lowp` (picked up
+    by to_compute), the pooling partials of the twin as `._sr_pool` when want_pool — or (trunk, acc + trunk) when the
+    dense-sampling accumulator `acc` is given."""
+    pool = getattr(x, "_sr_pool", None)
     x = to_compute(x)
     t = t.float().contiguous(memory_format=torch.channels_last)
     lowp = config.compute_dtype != torch.float32
-    out = LocalAttnChain.apply(x, t, ca.fc1.weight, ca.fc2.weight, sa.conv1.weight, conv.weight, conv.bias, lowp)
+    band = lowp and _lib.backend().la_band_path(x)
+    if acc is not None and not band:                       # tile kernels (fp32 mode, very large maps): the sum stays an elementwise add
+        z = local_attn_chain(x, t, ca, sa, conv)
+        return z, acc + z
+    out = LocalAttnChain.apply(x, t, acc, ca.fc1.weight, ca.fc2.weight, sa.conv1.weight, conv.weight, conv.bias, lowp,
+                               pool if band else None, bool(want_pool and band))
+    if not isinstance(out, tuple):
+        return out
+    out = list(out)
+    z32 = out.pop(0)
     if lowp:
-        z32, z16 = out
-        z32._sr_lowp = z16
-        return z32
-    return out
+        z32._sr_lowp = out.pop(0)
+    new_acc = out.pop(0) if acc is not None else None
+    if out:
+        z32._sr_pool = (out[0], out[1], out[0].shape[1])
+        if lowp:
+            z32._sr_lowp._sr_pool = z32._sr_pool
+    return (z32, new_acc) if acc is not None else z32
 
 
 # ----------------------------------------------------------------------------------------------

@@ -215,3 +215,84 @@ def test_maxpool2x2_forward_backward(be, shape, dtype):
     (dx_ref,) = torch.autograd.grad(y_ref, xr, gy.float())
     dx = be.maxpool2x2_bwd(gy.cuda(), xc)
     assert dx.shape == x.shape and torch.equal(dx.float().cpu(), dx_ref)
+
+
+def _decode_pool(psum, pkey, P):
+    """reduce the per-row pooling partials like the chain kernel does -> (avg, max, first arg-max pixel) per (image, channel)"""
+    s = psum.double().sum(dim=1) / P
+    k = pkey.long() & 0xFFFFFFFF                     # stored as int32 bit patterns
+    kmax = k.max(dim=1)[0]
+    bits = (kmax >> 16) & 0xFFFF
+    raw = torch.where((bits & 0x8000) != 0, bits & 0x7FFF, (~bits) & 0xFFFF).to(torch.int32)
+    val = raw.to(torch.int16).view(torch.bfloat16).float()
+    return s, val, (0xFFFF - (kmax & 0xFFFF))
+
+
+@pytest.mark.parametrize("shape", [(2, 54, 54), (1, 13, 17), (3, 24, 24), (1, 72, 72)])
+def test_conv_epilogue_emits_clam_pooling_partials(be, shape):
+    """RAB conv2 (256 -> 64, 3x3) with desc.pool_*: the tensor-core kernel's epilogue emits the per-(image, channel) sums and
+    packed (max, first arg-max) keys of its bf16 output that the chain's CLAM pooling needs (reference model/sradsgan.py:117-121)."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(h + w)
+    x = torch.randn(n, 256, h, w, generator=g).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(64, 256, 3, 3, generator=g) * 0.03).cuda()
+    b = (torch.randn(64, generator=g) * 0.1).cuda()
+    geom = conv_geom(x.shape, wt.shape, 1, 1)
+    wp = be.pack_weights(wt, 0, torch.bfloat16)
+    y_plain = be.conv_fwd(x, wp, b, None, geom)
+    y, pool = be.conv_fwd(x, wp, b, None, geom, want_pool=True)
+    assert pool is not None and pool[0].shape == (n, pool[2], 64)
+    assert torch.equal(y, y_plain)                                   # the pooling instantiation stores the same values
+    avg, mx, pstar = _decode_pool(pool[0], pool[1], h * w)
+    yf = y.float().permute(0, 2, 3, 1).reshape(n, h * w, 64)
+    assert rel(avg, yf.double().mean(1)) < 1e-5
+    assert torch.equal(mx.cpu(), yf.max(1)[0].cpu())
+    first = (yf == yf.max(1, keepdim=True)[0]).float().argmax(1)     # first pixel attaining the maximum
+    assert torch.equal(pstar.cpu(), first.cpu().long())
+
+
+@pytest.mark.parametrize("shape", [(2, 54, 54), (1, 13, 17), (2, 108, 108)])
+def test_la_chain_band_path_with_producer_partials_and_accumulator(be, shape):
+    """the band path fed by a producer's pooling partials, adding its output to the dense-sampling accumulator and emitting the
+    partials of its own output == the plain chain (partials recomputed from x) + an explicit add; backward with the
+    accumulator's gradient == backward with that gradient folded into the fp32 one."""
+    n, h, w = shape
+    x, t, fc1, fc2, w7, W, b = _chain_inputs(n, h, w, torch.bfloat16, seed=h)
+    cu = [v.cuda() for v in (x, t, fc1, fc2, w7, W, b)]
+    cu[0] = cu[0].contiguous(memory_format=torch.channels_last)
+    assert be.la_band_path(cu[0])
+    z32, z16, sv, _, _ = be.la_chain_forward(*cu, want_lowp=True)
+    # "producer" partials in a different row split than the chain's own pooling kernel uses: 7 rows per image
+    xf = cu[0].float().permute(0, 2, 3, 1).reshape(n, h * w, 64)
+    rows = 7
+    psum = torch.zeros(n, rows, 64, device="cuda")
+    pkey = torch.zeros(n, rows, 64, dtype=torch.int64, device="cuda")
+    bits = cu[0].permute(0, 2, 3, 1).reshape(n, h * w, 64).contiguous().view(torch.int16).long() & 0xFFFF
+    key = torch.where((bits & 0x8000) != 0, (~bits) & 0xFFFF, bits | 0x8000)
+    packed = (key << 16) | (0xFFFF - torch.arange(h * w, device="cuda").view(1, -1, 1))
+    for r in range(rows):
+        sl = slice(r * (h * w) // rows, (r + 1) * (h * w) // rows)
+        psum[:, r] = xf[:, sl].sum(1)
+        pkey[:, r] = packed[:, sl].max(1)[0]
+    pk32 = torch.where(pkey >= 2 ** 31, pkey - 2 ** 32, pkey).to(torch.int32)
+    acc = torch.randn(n, 64, h, w, generator=torch.Generator().manual_seed(1)).cuda().contiguous(memory_format=torch.channels_last)
+    z32b, z16b, svb, acc_out, out_pool = be.la_chain_forward(*cu, want_lowp=True, pool=(psum, pk32, rows), acc=acc, want_pool=True)
+    assert rel(z32b, z32) < 1e-6 and torch.equal(z16b, z32b.bfloat16())
+    assert torch.equal(svb["pstar"], sv["pstar"]) and rel(svb["avg"], sv["avg"]) < 1e-6 and torch.equal(svb["max"], sv["max"])
+    assert rel(acc_out, acc + z32b) < 1e-7
+    avg, mx, pstar = _decode_pool(out_pool[0], out_pool[1], h * w)
+    zf = z16b.float().permute(0, 2, 3, 1).reshape(n, h * w, 64)
+    assert rel(avg, zf.double().mean(1)) < 1e-5 and torch.equal(mx.cpu(), zf.max(1)[0].cpu())
+    assert torch.equal(pstar.cpu(), (zf == zf.max(1, keepdim=True)[0]).float().argmax(1).cpu().long())
+    # backward: dz = gz32 + gz16 + gacc inside the kernel
+    gg = torch.Generator().manual_seed(3)
+    gz32 = torch.randn(n, 64, h, w, generator=gg).cuda()
+    gz16 = torch.randn(n, 64, h, w, generator=gg).bfloat16().cuda()
+    gacc = torch.randn(n, 64, h, w, generator=gg).cuda()
+    a = be.la_chain_backward(gz32, gz16, gacc, cu[0], svb, cu[2], cu[3], cu[4], cu[5])
+    r = be.la_chain_backward(gz32 + gacc, gz16, None, cu[0], svb, cu[2], cu[3], cu[4], cu[5])
+    for nm, u, v in zip(["dx", "d_fc1", "d_fc2", "d_w7", "dW", "db", "dz"], a, r):
+        assert rel(u, v) < (4e-3 if nm == "dx" else 2e-5), (nm, rel(u, v))
+    # twice the same launch: deterministic (fixed-order partial sums; only the tiny MLP / 7x7 weight gradients use atomics)
+    a2 = be.la_chain_backward(gz32, gz16, gacc, cu[0], svb, cu[2], cu[3], cu[4], cu[5])
+    assert torch.equal(a2[0], a[0]) and torch.equal(a2[4], a[4]) and torch.equal(a2[5], a[5])

