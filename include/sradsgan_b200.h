@@ -62,7 +62,7 @@ int sr_device_check(void);
 int64_t sr_launch_count(void);
 
 /* rows per image of the pooling partials sr_conv2d_fwd emits for this geometry when desc.pool_sum / pool_key are set
- * (0: not available — 3x3 / stride 1 / pad 1, bf16 in and out, Cin % 64 == 0, Cout % 64 == 0, no pixel shuffle, H*W <= 65535). */
+ * (0: not available — 3x3 / stride 1 / pad 1, bf16 in and out, Cin % 64 == 0, Cout == 64, no pixel shuffle, H*W <= 65535). */
 int sr_conv_pool_rows(const sr_conv_desc* d);
 
 /* 1 when sr_conv2d_fwd (kind 0) / sr_conv2d_dgrad (kind 1) / sr_conv2d_wgrad (kind 2) will run this

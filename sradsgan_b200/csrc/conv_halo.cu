@@ -41,8 +41,8 @@ struct HaloParams {
     float mask_slope;
     void* out;
     // CLAM pooling partials of the (bf16) output, emitted by the epilogue for the local-attention chain that follows conv2 of a
-    // RAB (la_band.cu): [N][pool_rows][Cout] channel sums and packed (max, first arg-max pixel) keys, one row per
-    // (pixel tile of the image, 32-row quarter of the tile); nullable
+    // RAB (la_band.cu): [N][pool_rows][64] channel sums and packed (max, first arg-max pixel) keys, one row per pixel tile of
+    // the image; nullable
     float* pool_sum; unsigned int* pool_key; int pool_rows;
 };
 
@@ -58,7 +58,7 @@ __device__ __forceinline__ unsigned int hl_bf16_key(__nv_bfloat16 v) {
 // (keys first, then sums) so that the extra live state is one 32-register array.
 template <int ACT>
 __device__ __forceinline__ void hl_store_pool_chunk(const uint32_t (&v)[32], const float* bias_s, float slope, bool valid, __nv_bfloat16* o,
-                                                    unsigned int ptag, int lane, float* psum, unsigned int* pkey) {
+                                                    unsigned int ptag, int lane, float& col_sum, unsigned int& col_key) {
     float f[32];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -97,7 +97,7 @@ __device__ __forceinline__ void hl_store_pool_chunk(const uint32_t (&v)[32], con
                 k[i] = keep > recv ? keep : recv;
             }
         }
-        pkey[lane] = k[0];
+        col_key = k[0];
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = valid ? f[i] : 0.f;
@@ -110,7 +110,7 @@ __device__ __forceinline__ void hl_store_pool_chunk(const uint32_t (&v)[32], con
             f[i] = (up ? f[i + half] : f[i]) + recv;
         }
     }
-    psum[lane] = f[0];
+    col_sum = f[0];
 }
 
 constexpr int HL_EPI_WARPS = 8;
@@ -177,13 +177,45 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
             const bool valid = tr < p.TR && cp >= 1 && cp <= p.TW && oy < p.H && ox < p.W;
             const long long row_idx = (((long long)n * p.H + oy) * p.W + ox) * p.Cout;
             const int tile_in_img = p_tile - n * (p.tiles_y * p.tiles_x);
+            float pool_s[2] = {0.f, 0.f};
+            unsigned int pool_k[2] = {0u, 0u};
+            // POOL: the four quarter warps of this group (32 tile rows each) combine their column results through shared memory
+            // (fixed order) and quarter 0 writes ONE partial row per tile: [N][tiles per image][64]
+            auto pool_flush = [&](int cmask) {
+                float* sc_s = const_cast<float*>(bias_s) + 64 + grp * 384;                 // [3 quarters][2 chunks][32 lanes] sums, then keys
+                unsigned int* sc_k = reinterpret_cast<unsigned int*>(sc_s + 192);
+                if (quarter > 0) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if ((cmask >> c) & 1) { sc_s[((quarter - 1) * 2 + c) * 32 + lane] = pool_s[c]; sc_k[((quarter - 1) * 2 + c) * 32 + lane] = pool_k[c]; }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                if (quarter == 0) {
+                    const long long prow = ((long long)n * p.pool_rows + tile_in_img) * p.Cout;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if ((cmask >> c) & 1) {
+                            float sv = pool_s[c]; unsigned int kv = pool_k[c];
+#pragma unroll
+                            for (int qq = 0; qq < 3; ++qq) {
+                                sv += sc_s[(qq * 2 + c) * 32 + lane];
+                                const unsigned int ko = sc_k[(qq * 2 + c) * 32 + lane];
+                                kv = kv > ko ? kv : ko;
+                            }
+                            p.pool_sum[prow + c * 32 + lane] = sv;
+                            p.pool_key[prow + c * 32 + lane] = kv;
+                        }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+            };
             auto emit = [&](const uint32_t (&v)[32], int c) {
-                if (POOL) {                      // (bf16 output, no residual / mask / shuffle: checked on the host) every lane takes part
+                if (POOL) {                      // (bf16 output, Cout = 64, no residual / mask / shuffle: checked on the host) every lane takes part
                     if (sizeof(OutT) == 2) {
-                        const int col = nb * p.block_n + c * 32;
-                        const long long prow = ((long long)n * p.pool_rows + tile_in_img * 4 + quarter) * p.Cout + col;
+                        const int col = c * 32;
+                        float cs; unsigned int ck;
                         hl_store_pool_chunk<ACT>(v, bias_s + col, p.slope, valid, reinterpret_cast<__nv_bfloat16*>(out) + row_idx + col,
-                                                 (unsigned int)(0xFFFF - (oy * p.W + ox)) & 0xFFFFu, lane, p.pool_sum + prow, p.pool_key + prow);
+                                                 (unsigned int)(0xFFFF - (oy * p.W + ox)) & 0xFFFFu, lane, cs, ck);
+                        if (c == 0) { pool_s[0] = cs; pool_k[0] = ck; } else { pool_s[1] = cs; pool_k[1] = ck; }
                     }
                     return;
                 }
@@ -225,6 +257,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                     for (int k = 0; k < 32; ++k) va[k] = __float_as_uint(__uint_as_float(va[k]) + __uint_as_float(vb[k]));
                     emit(va, c);
                 }
+                if (POOL) pool_flush(1 << grp);                         // split: this group produced the chunks of parity grp
                 tc_fence_before();
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // both groups are done reading both buffers
                 if (lane == 0) mbar_arrive(acc_empty + grp * 2 + accs[grp]);
@@ -247,6 +280,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                     emit(vb, c);
                     c += c_step;
                 }
+                if (POOL) pool_flush(3);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + buf);
@@ -483,11 +517,11 @@ static void hl_tiling(int H, int W, int& tiles_x, int& TW, int& TR, int& tiles_y
 
 // rows per image of the pooling partials a forward launch emits (0: this convolution cannot emit them)
 int conv_halo_pool_rows(const sr_conv_desc* d) {
-    if (!conv_halo_supported(d, false) || d->Cout % 64 != 0 || d->shuffle_r > 1 || d->out_dtype != SR_BF16) return 0;
+    if (!conv_halo_supported(d, false) || d->Cout != 64 || d->shuffle_r > 1 || d->out_dtype != SR_BF16) return 0;
     if ((long long)d->H * d->W > 65535) return 0;
     int tx, TW, TR, ty;
     hl_tiling(d->H, d->W, tx, TW, TR, ty);
-    return tx * ty * 4;
+    return tx * ty;
 }
 
 int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* w, const float* bias,
@@ -516,7 +550,7 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.mask = mask; p.mask_slope = mask_slope;
     if (!dgrad && d->pool_sum && d->pool_key) {
         const int rows = conv_halo_pool_rows(d);
-        if (!rows || residual || mask) { set_error("conv_halo: pooling partials need a plain bf16 forward convolution with Cout %% 64 == 0"); return SR_ERR_UNSUPPORTED; }
+        if (!rows || residual || mask) { set_error("conv_halo: pooling partials need a plain bf16 forward convolution with 64 output channels"); return SR_ERR_UNSUPPORTED; }
         p.pool_sum = (float*)d->pool_sum; p.pool_key = (unsigned int*)d->pool_key; p.pool_rows = rows;
     }
     p.a_box_bytes = (p.TR + 2) * p.TWp * 128;

@@ -54,7 +54,7 @@ la_pool_pack_kernel(const __nv_bfloat16* __restrict__ x, int P, int S, float* __
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 la_fwd_band_kernel(const LaBandFwd p) {
     extern __shared__ __align__(16) unsigned char lb_smem[];
     __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(lb_smem);            // [co][ci] hi
@@ -129,41 +129,57 @@ la_fwd_band_kernel(const LaBandFwd p) {
         float sv[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) sv[k] = s_s[sub * 16 + k];
-        for (int base = 0; base < qn; base += 64) {
-            const int pi = base + (t >> 2);
-            const bool inside = pi < qn;
-            const int qr = inside ? pi / W : 0, xx = pi - qr * W;
-            const int yy = y0 - 3 + qr;
-            const bool valid = inside && yy >= 0 && yy < H;
-            float sum = 0.f, mv = -INFINITY; int mi = 0;
-            if (valid) {
-                const __nv_bfloat16* xp = p.x + ((long long)n * P + (long long)yy * W + xx) * LA_C + sub * 16;
-                const uint4 a = *reinterpret_cast<const uint4*>(xp), b = *reinterpret_cast<const uint4*>(xp + 8);
-                const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+        for (int base = 0; base < qn; base += 128) {
+            // two 64-pixel passes per iteration, all four 16-byte loads issued before any of them is consumed
+            int pi_[2], yy_[2], xx_[2]; bool inside_[2], valid_[2];
+            uint4 a_[2], b_[2];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const __nv_bfloat162 v = k < 4 ? a2[k] : b2[k - 4];
-                    const float u0 = __low2float(v) * sv[2 * k], u1 = __high2float(v) * sv[2 * k + 1];
-                    sum += u0 + u1;
-                    if (u0 > mv) { mv = u0; mi = sub * 16 + 2 * k; }
-                    if (u1 > mv) { mv = u1; mi = sub * 16 + 2 * k + 1; }
+            for (int u = 0; u < 2; ++u) {
+                pi_[u] = base + u * 64 + (t >> 2);
+                inside_[u] = pi_[u] < qn;
+                const int qr = inside_[u] ? pi_[u] / W : 0;
+                xx_[u] = pi_[u] - qr * W;
+                yy_[u] = y0 - 3 + qr;
+                valid_[u] = inside_[u] && yy_[u] >= 0 && yy_[u] < H;
+                a_[u] = make_uint4(0u, 0u, 0u, 0u); b_[u] = a_[u];
+                if (valid_[u]) {
+                    const __nv_bfloat16* xp = p.x + ((long long)n * P + (long long)yy_[u] * W + xx_[u]) * LA_C + sub * 16;
+                    a_[u] = *reinterpret_cast<const uint4*>(xp); b_[u] = *reinterpret_cast<const uint4*>(xp + 8);
                 }
             }
 #pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-                if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
-            }
-            if (inside && sub == 0) {
-                const float mean = valid ? sum * (1.f / LA_C) : 0.f, mx = valid ? mv : 0.f;
-                qs[pi * 2] = mean; qs[pi * 2 + 1] = mx;
-                if (valid && qr >= 3 && qr < 3 + rows) {                       // a pixel of the band itself: saved for the backward
-                    const long long pix = (long long)n * P + (long long)yy * W + xx;
-                    *reinterpret_cast<float2*>(p.q + pix * 2) = make_float2(mean, mx);
-                    p.cstar[pix] = (unsigned char)mi;
+            for (int u = 0; u < 2; ++u) {
+                const int pi = pi_[u], yy = yy_[u], xx = xx_[u];
+                const bool inside = inside_[u], valid = valid_[u];
+                float sum = 0.f, mv = -INFINITY; int mi = 0;
+                if (valid) {
+                    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a_[u]);
+                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b_[u]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const __nv_bfloat162 v = k < 4 ? a2[k] : b2[k - 4];
+                        const float u0 = __low2float(v) * sv[2 * k], u1 = __high2float(v) * sv[2 * k + 1];
+                        sum += u0 + u1;
+                        if (u0 > mv) { mv = u0; mi = sub * 16 + 2 * k; }
+                        if (u1 > mv) { mv = u1; mi = sub * 16 + 2 * k + 1; }
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                    if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
+                }
+                if (inside && sub == 0) {
+                    const float mean = valid ? sum * (1.f / LA_C) : 0.f, mx = valid ? mv : 0.f;
+                    qs[pi * 2] = mean; qs[pi * 2 + 1] = mx;
+                    const int qr = pi / W;
+                    if (valid && qr >= 3 && qr < 3 + rows) {                   // a pixel of the band itself: saved for the backward
+                        const long long pix = (long long)n * P + (long long)yy * W + xx;
+                        *reinterpret_cast<float2*>(p.q + pix * 2) = make_float2(mean, mx);
+                        p.cstar[pix] = (unsigned char)mi;
+                    }
                 }
             }
         }
@@ -221,6 +237,18 @@ la_fwd_band_kernel(const LaBandFwd p) {
             }
         }
         __syncthreads();
+        // the epilogue's operands (residual trunk, dense-sampling accumulator) are requested BEFORE the tensor-core products
+        float2 tres[2][4];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int li = l0 + mt * 16 + g + rr * 8;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int co = nh * 32 + nt * 8 + 2 * tq;
+                tres[rr][nt] = make_float2(0.f, 0.f);
+                if (li < npx) tres[rr][nt] = *reinterpret_cast<const float2*>(p.t + (pix0 + li) * LA_C + co);
+            }
+        }
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -253,8 +281,7 @@ la_fwd_band_kernel(const LaBandFwd p) {
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int co = nh * 32 + nt * 8 + 2 * tq;
-                const float2 r = *reinterpret_cast<const float2*>(p.t + pix * LA_C + co);
-                const float o0 = acc[nt][rr * 2] + bias_s[co] + r.x, o1 = acc[nt][rr * 2 + 1] + bias_s[co + 1] + r.y;
+                const float o0 = acc[nt][rr * 2] + bias_s[co] + tres[rr][nt].x, o1 = acc[nt][rr * 2 + 1] + bias_s[co + 1] + tres[rr][nt].y;
                 *reinterpret_cast<float2*>(p.z32 + pix * LA_C + co) = make_float2(o0, o1);
                 const __nv_bfloat162 o16 = __floats2bfloat162_rn(o0, o1);
                 *reinterpret_cast<__nv_bfloat162*>(p.z16 + pix * LA_C + co) = o16;
@@ -366,16 +393,29 @@ la_bwd_band_kernel(const LaBandBwd p) {
     {
         const float s0 = p.s[n * LA_C + lane * 2], s1 = p.s[n * LA_C + lane * 2 + 1];
         float a0 = 0.f, a1 = 0.f;
-        for (int li = warp; li < npx; li += 8) {
-            const long long pix = pix0 + li;
-            const float2 gv = *reinterpret_cast<const float2*>(p.g + pix * LA_C + lane * 2);
-            const float dqa = dqs[li * 2] * (1.f / LA_C), dqm = dqs[li * 2 + 1];
-            const int cs = p.cstar[pix];
-            const float du0 = gv.x + dqa + (cs == lane * 2 ? dqm : 0.f);
-            const float du1 = gv.y + dqa + (cs == lane * 2 + 1 ? dqm : 0.f);
-            const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(p.x + pix * LA_C + lane * 2);
-            a0 += du0 * __low2float(xv); a1 += du1 * __high2float(xv);
-            *reinterpret_cast<__nv_bfloat162*>(p.dx + pix * LA_C + lane * 2) = __floats2bfloat162_rn(s0 * du0, s1 * du1);
+        for (int l0 = warp; l0 < npx; l0 += 32) {
+            float2 gv[4]; __nv_bfloat162 xv[4]; int cs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int li = l0 + 8 * u;
+                gv[u] = make_float2(0.f, 0.f); xv[u] = __floats2bfloat162_rn(0.f, 0.f); cs[u] = 0;
+                if (li < npx) {
+                    const long long pix = pix0 + li;
+                    gv[u] = *reinterpret_cast<const float2*>(p.g + pix * LA_C + lane * 2);
+                    xv[u] = *reinterpret_cast<const __nv_bfloat162*>(p.x + pix * LA_C + lane * 2);
+                    cs[u] = p.cstar[pix];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int li = l0 + 8 * u;
+                if (li >= npx) continue;
+                const float dqa = dqs[li * 2] * (1.f / LA_C), dqm = dqs[li * 2 + 1];
+                const float du0 = gv[u].x + dqa + (cs[u] == lane * 2 ? dqm : 0.f);
+                const float du1 = gv[u].y + dqa + (cs[u] == lane * 2 + 1 ? dqm : 0.f);
+                a0 += du0 * __low2float(xv[u]); a1 += du1 * __high2float(xv[u]);
+                *reinterpret_cast<__nv_bfloat162*>(p.dx + (pix0 + li) * LA_C + lane * 2) = __floats2bfloat162_rn(s0 * du0, s1 * du1);
+            }
         }
         red[warp * LA_C + lane * 2] = a0; red[warp * LA_C + lane * 2 + 1] = a1;
     }
@@ -393,8 +433,14 @@ la_bwd_band_kernel(const LaBandBwd p) {
         const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
         const int e1 = min(total, ((int)blockIdx.x + 1) * per);
         for (int e = blockIdx.x * per + t; e < e1; e += 256) {
-            float v = 0.f;
-            for (int k = 0; k < p.nparts; ++k) v += p.wpart[(long long)k * total + e];
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            int k = 0;
+            for (; k + 4 <= p.nparts; k += 4) {
+                v0 += p.wpart[(long long)k * total + e]; v1 += p.wpart[(long long)(k + 1) * total + e];
+                v2 += p.wpart[(long long)(k + 2) * total + e]; v3 += p.wpart[(long long)(k + 3) * total + e];
+            }
+            for (; k < p.nparts; ++k) v0 += p.wpart[(long long)k * total + e];
+            const float v = (v0 + v1) + (v2 + v3);
             if (e < LA_C * LA_C) p.dW[e] += v; else p.db[e - LA_C * LA_C] += v;
         }
     }
@@ -427,20 +473,23 @@ static int lb_sms() {
     return g_lb_sms;
 }
 
-// rows per band: the band height that minimises (waves of N * bands blocks) x (rows + 6 halo rows) — e.g. 16 x 54^2 maps:
-// R = 6 -> 9 bands per image, 144 blocks = one wave of the 148 SMs
+// rows per band.  A block is a short chain of dependent phases (pooled gate -> q -> 7x7 -> GEMM tiles), so the SMs want several
+// blocks resident (LB_OCC) rather than one tall band each: cost = waves of (N * bands) blocks over sms * LB_OCC slots, times the
+// work of a block — (R + 6) rows of cheap per-pixel statistics + R rows of GEMM / stencil work (weighted 4x).  16 x 54^2 maps:
+// R = 2 -> 27 bands per image, 432 blocks = one wave at 3 blocks per SM (80 registers x 256 threads).
+constexpr int LB_OCC = 3;
 int la_band_rows(int N, int H, int W) {
     const int sms = lb_sms();
     int best = 0; long long best_cost = 0;
-    for (int R = 3; R <= 16; ++R) {
+    for (int R = 1; R <= 16; ++R) {
         if (R > H && best) break;
         const int r = R > H ? H : R;
         if ((long long)r * W > 2048) break;
         const long long blocks = (long long)N * cdiv(H, r);
-        const long long cost = cdiv(blocks, sms) * (long long)(r + 6) * W;
+        const long long cost = cdiv(blocks, (long long)sms * LB_OCC) * ((long long)(r + 6) * W + 4LL * r * W);
         if (!best || cost < best_cost) { best = r; best_cost = cost; }
     }
-    return best ? best : (H < 3 ? H : 3);
+    return best ? best : 1;
 }
 
 int la_band_count(int N, int H, int W) { return (int)cdiv(H, la_band_rows(N, H, W)); }

@@ -792,8 +792,8 @@ size_t la_workspace_bytes(int N, int H, int W) {
     size_t fwd = (size_t)N * (S > 32 ? S : 32) * LA_C * 12 + (size_t)N * 16 + 64;   // + the fused kernel's partials / barrier counters
     size_t bwd = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + ((size_t)N * P + 4) * 8 + (size_t)N * LA_C * 12 + ((size_t)N + 4) * 4;
     // band path: g, dm, <= 296 rows of dW | db partials, per-band ds partials, ds / da / dmx
-    const size_t band = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + (size_t)296 * (LA_C * LA_C + LA_C) * 4 +
-                        (size_t)N * 64 * LA_C * 4 + (size_t)N * LA_C * 12 + 64;
+    const size_t band = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + (size_t)444 * (LA_C * LA_C + LA_C) * 4 +
+                        (size_t)N * (size_t)H * LA_C * 4 + (size_t)N * LA_C * 12 + 64;
     if (band > bwd) bwd = band;
     return (fwd > bwd ? fwd : bwd) + 256;
 }
@@ -961,7 +961,7 @@ int la_chain_backward(const sr_la_chain_grad_args* a, cudaStream_t st) {
     float* ws = (float*)a->workspace;
     float* g = ws; float* dm = g + (size_t)NP * LA_C; float* wpart = dm + npa;
     const int tiles = (int)cdiv(NP, 64);
-    const int grid = tiles < 296 ? tiles : 296;
+    const int grid = tiles < 296 ? tiles : 296;            // 2 resident blocks per SM (102 registers x 256 threads)
     float* dspart = wpart + (size_t)grid * (LA_C * LA_C + LA_C);
     float* ds = dspart + (size_t)N * bands * LA_C; float* da = ds + (size_t)N * LA_C; float* dmx = da + (size_t)N * LA_C;
     const size_t mma_smem = (size_t)6 * LA_C * LA_LD * sizeof(__nv_bfloat16);

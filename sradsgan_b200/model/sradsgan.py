@@ -281,17 +281,23 @@ class ResGroup(nn.Module):
         _la_init(self, nc, rla_mode, pool_mode, addconv)
 
     def forward(self, x, acc=None):
-        """acc (new, internal): the generator's dense-sampling accumulator; when given, returns (y, acc + y) with the sum
-        `out_all += y` (reference :459) done in the epilogue of the chain kernel"""
+        """acc (new, internal): the generator's dense-sampling accumulator; when given, the sum `out_all += y` (reference :459)
+        is done in the epilogue of the chain kernel and rides along as `y._sr_acc` (the module still returns y alone, so
+        forward hooks and callers see the reference's output)"""
         fused = _fused_la(self)
         t = x
         for i, blk in enumerate(self.RG):
             last = i == len(self.RG) - 1
             t = blk(t, want_pool=True) if (last and fused and isinstance(blk, RAB)) else blk(t)
-        if acc is not None and not fused:
+        if acc is None:
+            return _la_forward(self, ops.to_compute(t), x)
+        if fused:
+            y, new_acc = _la_forward(self, ops.to_compute(t), x, acc=acc)
+        else:
             y = _la_forward(self, ops.to_compute(t), x)
-            return y, acc + y
-        return _la_forward(self, ops.to_compute(t), x, acc=acc)
+            new_acc = acc + y
+        y._sr_acc = new_acc
+        return y
 
 
 class MSB(nn.Module):
@@ -394,7 +400,8 @@ class GeneratorResNet(nn.Module):
         out_all = msb.float() + out
         for res_group in self.res_groups:
             if isinstance(res_group, ResGroup):
-                y, out_all = res_group(out, acc=out_all)      # fp32 residual stream; out_all += y inside the chain kernel
+                y = res_group(out, acc=out_all)               # fp32 residual stream; out_all += y inside the chain kernel
+                out_all = y._sr_acc if getattr(y, "_sr_acc", None) is not None else out_all + y
             else:
                 y = res_group(out)
                 out_all = out_all + y

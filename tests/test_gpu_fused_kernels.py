@@ -293,6 +293,7 @@ def test_la_chain_band_path_with_producer_partials_and_accumulator(be, shape):
     r = be.la_chain_backward(gz32 + gacc, gz16, None, cu[0], svb, cu[2], cu[3], cu[4], cu[5])
     for nm, u, v in zip(["dx", "d_fc1", "d_fc2", "d_w7", "dW", "db", "dz"], a, r):
         assert rel(u, v) < (4e-3 if nm == "dx" else 2e-5), (nm, rel(u, v))
-    # twice the same launch: deterministic (fixed-order partial sums; only the tiny MLP / 7x7 weight gradients use atomics)
+    # twice the same launch: dx and the 1x1 weight gradient are bit-identical (fixed-order partial sums; the bias / MLP / 7x7
+    # weight gradients still combine through shared-memory / global fp32 atomics)
     a2 = be.la_chain_backward(gz32, gz16, gacc, cu[0], svb, cu[2], cu[3], cu[4], cu[5])
-    assert torch.equal(a2[0], a[0]) and torch.equal(a2[4], a[4]) and torch.equal(a2[5], a[5])
+    assert torch.equal(a2[0], a[0]) and torch.equal(a2[4], a[4]) and rel(a2[5], a[5]) < 1e-6

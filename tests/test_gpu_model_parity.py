@@ -111,6 +111,11 @@ def test_generator_backward_parity(precision):
     from sradsgan_b200.model.sradsgan import GeneratorResNet, ResGroup
     scale, ng, nb = 4, 2, 1
     sd = O.tie_upsampling(O.make_state(O.generator_spec(scale, ng, nb), seed=5, init="fan"))
+    # O(1) trunk activations make CGAM's softmax(rowmax(E) - E) over a gram of magnitude ~H*W one-hot on the row minimum:
+    # discontinuous in its input, i.e. an ill-posed comparison.  A 0.1x stem keeps the attention soft (logits O(1)).
+    for k in sd:
+        if k.startswith(("conv1.0.", "MSB.")):
+            sd[k] = sd[k] * 0.1
     G = GeneratorResNet(ResGroup, n_residual_blocks=ng, n_basic_blocks=nb, upscale_factor=scale)
     G.load_state_dict(sd, strict=True)
     G.cuda()
