@@ -98,15 +98,24 @@ int sr_conv2d_dgrad_act(const sr_conv_desc* d, const void* dy, const void* w_pac
                         void* dx, void* stream);
 /* dw (OIHW fp32) (+)= sum_pixels dy (x) x ; dbias (fp32, may be NULL) (+)= sum_pixels dy.
  * accumulate=0 overwrites (the library zero-fills first), 1 adds (tied upsampler weights, GP double
- * backward).  x and dy have dtype d->in_dtype. */
+ * backward).  x and dy have dtype d->in_dtype.
+ * workspace (nullable, 16-byte aligned DEVICE scratch owned by the caller, >= sr_conv2d_wgrad_workspace_bytes(d), used by
+ * this call only — one buffer per stream makes concurrent weight gradients re-entrant): with it the split-K partial tiles
+ * are combined by plain stores + one reduce kernel instead of fp32 atomics (3x faster, and deterministic). */
+size_t sr_conv2d_wgrad_workspace_bytes(const sr_conv_desc* d);
 int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float* dw_oihw, float* dbias,
-                    int accumulate, void* stream);
+                    int accumulate, void* workspace, uint64_t workspace_bytes, void* stream);
 
-/* Registers a caller-owned DEVICE scratch buffer that stays valid until replaced (NULL, 0 removes it).  With it,
- * sr_conv2d_wgrad combines its split-K partial tiles through plain stores + one reduce kernel instead of fp32
- * atomics (3x faster, and deterministic); without it (or when it is too small) the atomic path is used.
- * The library still never allocates.  64 MiB covers every layer of the x4 B=16 training step. */
-int sr_set_workspace(void* ptr, uint64_t bytes);
+/* Tuning / experiment options by name (e.g. "SR_LA_BAND" 0: tile kernels for the local-attention chain; "SR_HALO_SPLITK",
+ * "SR_WG_RMULT", ...; DESIGN.md §3 lists them).  The library never reads the environment: whoever wants a knob sets it here. */
+int sr_set_option(const char* name, int value);
+
+/* Up to 3 auxiliary streams with one fork event and one join event per stream, all created and owned by the CALLER (the
+ * library creates no streams or events).  Calls whose work splits into independent launches — the four parity classes of a
+ * stride-2 input gradient, the 7x7 weight gradient of the tile-path attention chain — fork them onto these streams and
+ * re-join before returning, so every call stays stream-ordered for the caller and capturable.  n = 0 (default): everything
+ * runs on the caller's stream.  The set is shared by all calls: issue such calls from one stream at a time. */
+int sr_set_aux_streams(void* const* streams, void* fork_event, void* const* join_events, int n);
 
 /* Fused local-attention tail of RAB / ResGroup (C = 64): z = Conv1x1(SLAM(CLAM(x))) + t, i.e.
  * nn modules CLAM (model/sradsgan.py:101-127), SLAM (:129-151), the 1x1 `conv` (:233/:297) and the
@@ -275,7 +284,8 @@ int sr_nchw_to_nhwc(const float* x, int64_t N, int C, int64_t HW, void* out, int
 /* out = a + b elementwise (b may be NULL: a cast), independent dtypes — sums of gradient branches of different precision. */
 int sr_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, void* out, int out_dtype, void* stream);
 
-/* Diagnostics (not on the product path): D[128][64] (fp32) = A_view * B^T on tcgen05, where A is a
+#ifdef SR_WITH_PROBES
+/* Diagnostics, compiled only with -DSR_WITH_PROBES (csrc/debug_probe.cu; not part of the product build): D[128][64] (fp32) = A_view * B^T on tcgen05, where A is a
  * [rows_a][64] bf16 matrix staged by TMA with the 128-byte swizzle and A_view row r is smem row
  * shift_rows + (r/8)*(sbo_bytes/128) + r%8 — probes which shared-memory operand descriptors the tensor core
  * accepts (shifted start address, non-1024 B group stride, descriptor base_offset field). */
@@ -286,6 +296,7 @@ int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows
  * issues iters x num_acc x k_steps instructions, k_steps consecutive ones into the same of num_acc TMEM accumulators;
  * cycles[cta] = SM clock ticks from first issue to completion. */
 int sr_debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, int64_t* cycles, void* stream);
+#endif
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_HALO = 0, 1, 2, 3
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_device_check", "sr_launch_count", "sr_conv_uses_tcgen05", "sr_pack_weights",
     "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step",
-    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_debug_umma_shift", "sr_debug_umma_rate", "sr_set_workspace",
+    "sr_la_chain_workspace_bytes", "sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd", "sr_bn_act_bwd_bwd", "sr_set_option", "sr_set_aux_streams", "sr_conv2d_wgrad_workspace_bytes",
     "sr_sgam_stats", "sr_sgam_pv", "sr_sgam_ds", "sr_sgam_bwd_prep", "sr_pack_weights_batched", "sr_maxpool2x2_fwd", "sr_maxpool2x2_bwd",
     "sr_reduce_workspace_bytes", "sr_diff_mean_fwd", "sr_diff_mean_bwd", "sr_mean_fwd", "sr_mean_bwd", "sr_gp_penalty_fwd", "sr_gp_penalty_bwd",
     "sr_lerp_nhwc", "sr_nchw_to_nhwc", "sr_add_cast", "sr_cgam_workspace_bytes", "sr_cgam_fwd", "sr_cgam_bwd",
@@ -97,7 +97,13 @@ def load():
     lib.sr_conv2d_dgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp]
     lib.sr_conv2d_dgrad_act.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, i32, f32, vp, vp]
     lib.sr_conv2d_dgrad_act.restype = i32
-    lib.sr_conv2d_wgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, i32, vp]
+    lib.sr_conv2d_wgrad.argtypes = [ctypes.POINTER(ConvDesc), vp, vp, vp, vp, i32, vp, ctypes.c_uint64, vp]
+    lib.sr_conv2d_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(ConvDesc)]
+    lib.sr_conv2d_wgrad_workspace_bytes.restype = ctypes.c_size_t
+    lib.sr_set_option.argtypes = [ctypes.c_char_p, i32]
+    lib.sr_set_option.restype = i32
+    lib.sr_set_aux_streams.argtypes = [ctypes.POINTER(vp), vp, ctypes.POINTER(vp), i32]
+    lib.sr_set_aux_streams.restype = i32
     lib.sr_colsum.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp]
     lib.sr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, f32, f32, vp]
     lib.sr_la_chain_workspace_bytes.argtypes = [i32, i32, i32]
@@ -109,8 +115,11 @@ def load():
     lib.sr_bn_act_bwd.argtypes = [vp, vp, i32, i64, i32, vp, f32, vp, vp, vp, vp]
     lib.sr_bn_act_bwd_bwd.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
     lib.sr_bn_act_bwd_bwd.restype = i32
-    lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
-    lib.sr_debug_umma_shift.restype = i32
+    if hasattr(lib, "sr_debug_umma_shift"):             # diagnostics build only (-DSR_WITH_PROBES)
+        lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
+        lib.sr_debug_umma_shift.restype = i32
+        lib.sr_debug_umma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
+        lib.sr_debug_umma_rate.restype = i32
     lib.sr_sgam_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.sr_sgam_pv.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.sr_sgam_ds.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
@@ -143,10 +152,13 @@ def load():
     lib.sr_la_chain_forward.restype = i32
     lib.sr_la_chain_backward.argtypes = [ctypes.POINTER(LaChainGradArgs), vp]
     lib.sr_la_chain_backward.restype = i32
-    lib.sr_set_workspace.argtypes = [vp, ctypes.c_uint64]
-    lib.sr_set_workspace.restype = i32
-    lib.sr_debug_umma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
-    lib.sr_debug_umma_rate.restype = i32
+    # experiment knobs: the library never reads the environment; SR_* variables of THIS process are forwarded explicitly
+    for k, v in os.environ.items():
+        if k.startswith(("SR_LA_", "SR_HALO_", "SR_WG_", "SR_S2_")):
+            try:
+                lib.sr_set_option(k.encode(), int(v))
+            except ValueError:
+                pass
     for name in ("sr_la_chain_fwd", "sr_la_chain_bwd", "sr_act_bwd", "sr_bn_act_fwd", "sr_bn_act_bwd"):
         getattr(lib, name).restype = i32
     for name in ("sr_pack_weights", "sr_pack_weights_batched", "sr_conv2d_fwd", "sr_conv2d_dgrad", "sr_conv2d_dgrad_act", "sr_conv2d_wgrad", "sr_colsum", "sr_adam_step"):
@@ -201,13 +213,36 @@ class CudaBackend:
     def __init__(self):
         self.lib = load()
         self.prof = None      # bench.py: list of (kernel class, flops, bytes, start event, end event)
-        self._workspace = None
+        self._workspaces = {}
+        self._aux = None
 
-    def ensure_workspace(self, device, nbytes=64 << 20):
-        """persistent scratch for the split-K weight-gradient reduction (owned here, registered with the library)"""
-        if self._workspace is None or self._workspace.device != device:
-            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            _check(self.lib.sr_set_workspace(ctypes.c_void_p(self._workspace.data_ptr()), nbytes), "set_workspace")
+    def wgrad_workspace(self, d, device):
+        """split-K scratch of the weight-gradient kernels: one persistent buffer PER STREAM (so weight gradients running on
+        different streams never share one), handed to the library with every call"""
+        need = int(self.lib.sr_conv2d_wgrad_workspace_bytes(ctypes.byref(d)))
+        if need == 0:
+            return None, 0
+        key = (device, torch.cuda.current_stream().cuda_stream)
+        ws = self._workspaces.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._workspaces[key] = torch.empty(need, dtype=torch.uint8, device=device)
+        return ws, ws.numel()
+
+    def ensure_aux_streams(self, device):
+        """three side streams + fork / join events owned here and handed to the library (sr_set_aux_streams): the parity
+        classes of stride-2 input gradients run next to each other on them"""
+        if self._aux is not None and self._aux["device"] == device:
+            return
+        streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+        events = [torch.cuda.Event() for _ in range(4)]
+        cur = torch.cuda.current_stream(device)
+        for e in events:
+            e.record(cur)                               # materialises the CUDA event handle
+        vp = ctypes.c_void_p
+        sarr = (vp * 3)(*[s.cuda_stream for s in streams])
+        jarr = (vp * 3)(*[e.cuda_event for e in events[1:]])
+        _check(self.lib.sr_set_aux_streams(sarr, vp(events[0].cuda_event), jarr, 3), "set_aux_streams")
+        self._aux = {"device": device, "streams": streams, "events": events}
 
     def _timed(self, kind, d, dgrad, call):
         """optional per-launch CUDA-event timing on the launching stream (bench.py roofline attribution)"""
@@ -295,6 +330,8 @@ class CudaBackend:
         if w_packed_t.dtype != dy.dtype:
             raise TypeError("conv_dgrad: packed weights must have the gradient dtype")
         d = self._desc(g, _dt(dy), _dt(dx), impl=impl)
+        if g.stride == 2:
+            self.ensure_aux_streams(dy.device)
         self._timed("dgrad", d, True, lambda: _check(
             self.lib.sr_conv2d_dgrad(ctypes.byref(d), _ptr(dy), _ptr(w_packed_t), _ptr(dx), _stream()), "conv2d_dgrad"))
         return dx
@@ -328,9 +365,9 @@ class CudaBackend:
         dw = torch.empty((g.Cout, g.Cin, g.kh, g.kw), dtype=torch.float32, device=x.device)
         db = torch.empty((g.Cout,), dtype=torch.float32, device=x.device) if want_bias else None
         d = self._desc(g, _dt(x), SR_F32, impl=impl)
-        self.ensure_workspace(x.device)
+        ws, nws = self.wgrad_workspace(d, x.device)
         self._timed("wgrad", d, False, lambda: _check(
-            self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 0, _stream()), "conv2d_wgrad"))
+            self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 0, _ptr(ws), nws, _stream()), "conv2d_wgrad"))
         return dw, db
 
     def conv_wgrad_into(self, x, dy, g, dw, db, impl=IMPL_AUTO):
@@ -340,9 +377,9 @@ class CudaBackend:
         if dw.dtype != torch.float32 or not dw.is_contiguous() or (db is not None and (db.dtype != torch.float32 or not db.is_contiguous())):
             raise ValueError("conv_wgrad_into: contiguous fp32 gradient buffers required")
         d = self._desc(g, _dt(x), SR_F32, impl=impl)
-        self.ensure_workspace(x.device)
+        ws, nws = self.wgrad_workspace(d, x.device)
         self._timed("wgrad", d, False, lambda: _check(
-            self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 1, _stream()), "conv2d_wgrad"))
+            self.lib.sr_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), 1, _ptr(ws), nws, _stream()), "conv2d_wgrad"))
 
     # -- fused local-attention chain ---------------------------------------------------------------
     def la_band_path(self, x):

@@ -18,6 +18,17 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+struct Option { char name[32]; int value; };
+static Option g_options[64];
+static int g_num_options = 0;
+int option(const char* name, int dflt) {
+    for (int i = 0; i < g_num_options; ++i)
+        if (strcmp(g_options[i].name, name) == 0) return g_options[i].value;
+    return dflt;
+}
+static AuxStreams g_aux = {{nullptr, nullptr, nullptr}, nullptr, {nullptr, nullptr, nullptr}, 0};
+const AuxStreams& aux_streams() { return g_aux; }
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -41,10 +52,10 @@ int conv_halo_run(const sr_conv_desc*, bool dgrad, const void*, const void*, con
                   const void* mask = nullptr, float mask_slope = 0.f);
 // conv_tc_wgrad.cu
 bool conv_tc_wgrad_supported(const sr_conv_desc*);
-int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, cudaStream_t);
-void conv_tc_wgrad_set_workspace(void*, size_t);
+int conv_tc_wgrad_run(const sr_conv_desc*, const void*, const void*, float*, float*, size_t, cudaStream_t);
+size_t conv_tc_wgrad_workspace_bytes(const sr_conv_desc*);
 bool conv_wgrad_halo_supported(const sr_conv_desc*);
-int conv_wgrad_halo_run(const sr_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
+int conv_wgrad_halo_run(const sr_conv_desc*, const void*, const void*, float*, float*, float*, size_t, cudaStream_t);
 // conv_thin.cu
 bool thin_fwd_supported(const sr_conv_desc*, bool dgrad);
 bool thin_wgrad_supported(const sr_conv_desc*);
@@ -101,9 +112,11 @@ int sgam_stats(const void*, const void*, int, int, int, float*, float*, cudaStre
 int sgam_pv(const SgCommon&, const void*, __nv_bfloat16*, float*, const float*, const float*, cudaStream_t);
 int sgam_ds(const SgCommon&, const void*, const void*, float*, cudaStream_t);
 int sgam_bwd_prep(const float*, const void*, const float*, long long, void*, float*, float*, cudaStream_t);
-// debug_probe.cu
+#ifdef SR_WITH_PROBES
+// debug_probe.cu (diagnostics: built only with -DSR_WITH_PROBES, see __graft_entry__.build(probes=True))
 int debug_umma_shift(const void*, int, const void*, int, int, int, float*, cudaStream_t);
 int debug_umma_rate(int, int, int, int, int, long long*, cudaStream_t);
+#endif
 
 static int g_arch_ok = -1;
 static int arch_check() {
@@ -238,13 +251,20 @@ int sr_conv2d_dgrad_act(const sr_conv_desc* d, const void* dy, const void* wt, c
     return act_bwd(dx, d->out_dtype, y_prev, d->out_dtype, act, slope, 0, d->N, d->H, d->W, d->Cin, dx, d->out_dtype, (cudaStream_t)stream);
 }
 
+size_t sr_conv2d_wgrad_workspace_bytes(const sr_conv_desc* d) {
+    if (!d || d->impl == SR_IMPL_SIMT || !conv_tc_wgrad_supported(d)) return 0;
+    return conv_tc_wgrad_workspace_bytes(d);
+}
+
 int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, int accumulate,
-                    void* stream) {
+                    void* workspace, uint64_t workspace_bytes, void* stream) {
     int rc = arch_check();
     if (rc) return rc;
     rc = check_desc(d);
     if (rc) return rc;
     SR_REQUIRE(x && dy && dw, "conv2d_wgrad: NULL pointer");
+    SR_REQUIRE((workspace == nullptr) == (workspace_bytes == 0) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "conv2d_wgrad: workspace pointer (16-byte aligned) and size must both be given or both be zero");
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * d->kh * d->kw, st);
     const bool tc_ok = conv_tc_wgrad_supported(d);
@@ -255,9 +275,9 @@ int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float*
     if (tc_ok && d->impl != SR_IMPL_SIMT && conv_wgrad_halo_supported(d)) {
         // 3x3 / stride 1: shifted-view kernel, bias gradient accumulated inside it
         if (dbias && !accumulate) cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)d->Cout, st);
-        return conv_wgrad_halo_run(d, x, dy, dw, dbias, st);
+        return conv_wgrad_halo_run(d, x, dy, dw, dbias, (float*)workspace, (size_t)workspace_bytes, st);
     }
-    if (tc_ok && d->impl != SR_IMPL_SIMT) rc = conv_tc_wgrad_run(d, x, dy, dw, st);
+    if (tc_ok && d->impl != SR_IMPL_SIMT) rc = conv_tc_wgrad_run(d, x, dy, dw, (float*)workspace, (size_t)workspace_bytes, st);
     else if (d->impl == SR_IMPL_AUTO && thin_wgrad_supported(d)) rc = thin_wgrad_run(d, x, dy, dw, st);
     else rc = conv_wgrad_simt(d, x, dy, dw, st);
     if (rc) return rc;
@@ -265,10 +285,25 @@ int sr_conv2d_wgrad(const sr_conv_desc* d, const void* x, const void* dy, float*
     return rc;
 }
 
-int sr_set_workspace(void* ptr, uint64_t bytes) {
-    SR_REQUIRE((ptr == nullptr) == (bytes == 0), "set_workspace: pointer and size must both be given or both be zero");
-    SR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "set_workspace: pointer must be 16-byte aligned");
-    conv_tc_wgrad_set_workspace(ptr, (size_t)bytes);
+int sr_set_option(const char* name, int value) {
+    SR_REQUIRE(name && strlen(name) > 0 && strlen(name) < 32, "set_option: name must have 1..31 characters");
+    for (int i = 0; i < g_num_options; ++i)
+        if (strcmp(g_options[i].name, name) == 0) { g_options[i].value = value; return SR_OK; }
+    SR_REQUIRE(g_num_options < 64, "set_option: table full");
+    strcpy(g_options[g_num_options].name, name);
+    g_options[g_num_options++].value = value;
+    return SR_OK;
+}
+
+int sr_set_aux_streams(void* const* streams, void* fork_event, void* const* join_events, int n) {
+    SR_REQUIRE(n >= 0 && n <= 3 && (n == 0 || (streams && fork_event && join_events)), "set_aux_streams: 0..3 streams with their events");
+    for (int i = 0; i < 3; ++i) { g_aux.stream[i] = nullptr; g_aux.join[i] = nullptr; }
+    for (int i = 0; i < n; ++i) {
+        SR_REQUIRE(streams[i] && join_events[i], "set_aux_streams: NULL stream / event");
+        g_aux.stream[i] = (cudaStream_t)streams[i]; g_aux.join[i] = (cudaEvent_t)join_events[i];
+    }
+    g_aux.fork = n ? (cudaEvent_t)fork_event : nullptr;
+    g_aux.n = n;
     return SR_OK;
 }
 
@@ -531,6 +566,7 @@ int sr_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, int64_t 
     return add_cast(a, a_dtype, b, b ? b_dtype : a_dtype, n, out, out_dtype, (cudaStream_t)stream);
 }
 
+#ifdef SR_WITH_PROBES
 int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows, int sbo_bytes, int base_offset, float* out,
                         void* stream) {
     int rc = arch_check();
@@ -545,5 +581,6 @@ int sr_debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, int
     SR_REQUIRE(cycles != nullptr, "debug_umma_rate: NULL output");
     return debug_umma_rate(n, num_acc, iters, k_steps, grid, (long long*)cycles, (cudaStream_t)stream);
 }
+#endif  // SR_WITH_PROBES
 
 }  // extern "C"

@@ -12,6 +12,13 @@ namespace sr {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);   // cudaGetLastError -> SR_OK / SR_ERR_CUDA
+// Tuning / experiment options set EXPLICITLY by the caller through sr_set_option() (api.cu); the library never reads the
+// environment.  Unknown names return `dflt`.
+int option(const char* name, int dflt);
+// Side streams + events handed in by the caller through sr_set_aux_streams() (the library creates none): used to run
+// independent launches of ONE call next to each other (fork / join with events: stream-ordered for the caller, capturable).
+struct AuxStreams { cudaStream_t stream[3]; cudaEvent_t fork; cudaEvent_t join[3]; int n; };
+const AuxStreams& aux_streams();
 
 #define SR_REQUIRE(cond, ...)                \
     do {                                     \

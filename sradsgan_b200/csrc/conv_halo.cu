@@ -585,9 +585,8 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     }
     p.resident = resident ? 1 : 0;
     p.dual = (bn <= 128 && (resident || p.n_blocks == 1)) ? 1 : 0;
-    static int nodual_res = -1;             // experiment knob: resident-weights layers on ONE issuer with a two-deep activation ring
-    if (nodual_res < 0) { const char* e = getenv("SR_HALO_NODUAL_RES"); nodual_res = e ? atoi(e) : 0; }
-    if (nodual_res && resident) p.dual = 0;
+    // experiment option: resident-weights layers on ONE issuer with a two-deep activation ring
+    if (option("SR_HALO_NODUAL_RES", 0) && resident) p.dual = 0;
     const int lane_ctas = resident ? grid / p.n_blocks : grid;
     if (p.dual) {
         const int pairs_total = p.p_tiles / 2;
@@ -599,9 +598,7 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
         p.n_pair_items = 0;
         p.n_items = resident ? p.p_tiles : p.p_tiles * p.n_blocks;
     }
-    static int splitk = -1;
-    if (splitk < 0) { const char* e = getenv("SR_HALO_SPLITK"); splitk = e ? atoi(e) : 1; }
-    p.split_ok = (splitk && p.dual && !resident && p.c_blocks >= 2) ? 1 : 0;
+    p.split_ok = (option("SR_HALO_SPLITK", 1) && p.dual && !resident && p.c_blocks >= 2) ? 1 : 0;
     const int total_items = resident ? p.n_items * p.n_blocks : p.n_items;
     if (total_items < grid) { grid = total_items; if (resident) grid -= grid % p.n_blocks; }
     if (grid < 1) grid = p.n_blocks;

@@ -359,19 +359,13 @@ int conv_tc_run(const sr_conv_desc* d, bool dgrad, const void* src, const void* 
     // class is a stride-1 convolution of dy with the subset of taps whose (iy + pad - ky) is even, written
     // to every second pixel of dx (the transposed-convolution analogue of the PixelShuffle epilogue).
     // The four class launches are independent (disjoint output pixels) and, on the small maps of the deeper layers, far
-    // too small to fill the GPU one at a time (D.8: 7 tiles per class) — classes 1..3 are forked onto internal side streams
-    // (event fork / join: stream-ordered for the caller, capturable) and run next to class 0.  SR_S2_STREAMS=0: one stream.
-    static cudaStream_t cls_stream[3] = {nullptr, nullptr, nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-    static int fork_on = -1;
-    if (fork_on < 0) { const char* e = getenv("SR_S2_STREAMS"); fork_on = e ? atoi(e) : 1; }
-    if (fork_on && !ev_fork) {
-        bool ok = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; i < 3 && ok; ++i)
-            ok = cudaStreamCreateWithFlags(&cls_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) { fork_on = 0; cudaGetLastError(); }
-    }
+    // too small to fill the GPU one at a time (D.8: 7 tiles per class) — classes 1..3 are forked onto the caller's auxiliary
+    // streams (event fork / join: stream-ordered for the caller, capturable) and run next to class 0.
+    const AuxStreams& aux = aux_streams();                 // handed in by the caller (sr_set_aux_streams); none: one stream
+    const bool fork_on = aux.n >= 3 && option("SR_S2_STREAMS", 1);
+    cudaStream_t const* cls_stream = aux.stream;
+    cudaEvent_t ev_fork = aux.fork;
+    cudaEvent_t const* ev_join = aux.join;
     if (fork_on) cudaEventRecord(ev_fork, st);
     int cls = 0;
     bool forked[3] = {false, false, false};

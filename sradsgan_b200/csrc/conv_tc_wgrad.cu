@@ -416,10 +416,7 @@ wgrad_reduce_rows_kernel(const float* __restrict__ partial, WgParams p, int tile
 }
 
 static int g_wg_sms = 0;
-static float* g_wg_workspace = nullptr;
-static size_t g_wg_workspace_bytes = 0;
 
-void conv_tc_wgrad_set_workspace(void* ptr, size_t bytes) { g_wg_workspace = (float*)ptr; g_wg_workspace_bytes = bytes; }
 
 bool conv_tc_wgrad_supported(const sr_conv_desc* d) {
     if (d->in_dtype != SR_BF16) return false;
@@ -431,7 +428,11 @@ bool conv_tc_wgrad_supported(const sr_conv_desc* d) {
 }
 
 // dw must have been zero-filled (or hold the value to accumulate onto).
-int conv_tc_wgrad_run(const sr_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+// upper bound of the split-K scratch of either weight-gradient kernel: one [mt <= 128] x [tg * nt <= 256] fp32 tile per work item,
+// at most one item per SM
+size_t conv_tc_wgrad_workspace_bytes(const sr_conv_desc*) { return (size_t)160 * 128 * 256 * sizeof(float); }
+
+int conv_tc_wgrad_run(const sr_conv_desc* d, const void* x, const void* dy, float* dw, float* ws, size_t ws_bytes, cudaStream_t st) {
     int rc = load_driver_fns();
     if (rc != SR_OK) return rc;
     if (!g_wg_sms) {
@@ -450,8 +451,7 @@ int conv_tc_wgrad_run(const sr_conv_desc* d, const void* x, const void* dy, floa
     p.tg = 256 / p.nt;                                              // taps stacked along N (N = tg * nt <= 256)
     if (p.tg > taps_total) p.tg = taps_total;
     if (taps_total == 9 && p.tg >= 3) p.tg = 3;                     // one filter row per group: 3 equal groups
-    static int tg_override = -1, bk_override = -1;                  // tuning knobs (environment, read once)
-    if (tg_override < 0) { const char* e = getenv("SR_WG_TG"); tg_override = e ? atoi(e) : 0; e = getenv("SR_WG_BK"); bk_override = e ? atoi(e) : 0; }
+    const int tg_override = option("SR_WG_TG", 0), bk_override = option("SR_WG_BK", 0);      // tuning options (sr_set_option)
     if (tg_override > 0 && tg_override < p.tg) p.tg = tg_override;
     p.tap_groups = (int)cdiv(taps_total, p.tg);
     const int panels = p.mt / 64 + p.tg * (p.nt / 64);
@@ -484,12 +484,10 @@ int conv_tc_wgrad_run(const sr_conv_desc* d, const void* x, const void* dy, floa
 
     const int items = p.splits * tiles;
     const int grid = items < g_wg_sms ? items : g_wg_sms;
-    // split-K partials go to the registered workspace (plain 16-byte stores + one reduce kernel) when it is large
+    // split-K partials go to the caller's workspace (plain 16-byte stores + one reduce kernel) when it is large
     // enough; otherwise they are combined with fp32 atomics straight into dW
     const size_t need = (size_t)items * p.mt * (p.tg * p.nt) * sizeof(float);
-    static int ws_off = -1;
-    if (ws_off < 0) { const char* e = getenv("SR_WG_NOWS"); ws_off = (e && atoi(e)) ? 1 : 0; }
-    p.partial = (!ws_off && g_wg_workspace && need <= g_wg_workspace_bytes && p.splits > 1) ? g_wg_workspace : nullptr;
+    p.partial = (!option("SR_WG_NOWS", 0) && ws && need <= ws_bytes && p.splits > 1) ? ws : nullptr;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + 256;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
@@ -504,12 +502,8 @@ int conv_tc_wgrad_run(const sr_conv_desc* d, const void* x, const void* dy, floa
 }
 
 // ---- halo variant: host side ----
-static int wg_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-
 bool conv_wgrad_halo_supported(const sr_conv_desc* d) {
-    static int enabled = -1;
-    if (enabled < 0) enabled = wg_env("SR_WG_HALO", 1);
-    if (!enabled) return false;
+    if (!option("SR_WG_HALO", 1)) return false;
     if (d->in_dtype != SR_BF16) return false;
     if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1) return false;
     if (d->Cin % 64 != 0 || d->Cout % 64 != 0) return false;
@@ -519,7 +513,7 @@ bool conv_wgrad_halo_supported(const sr_conv_desc* d) {
 }
 
 // dw (and dbias, when given) must have been zero-filled or hold the value to accumulate onto.
-int conv_wgrad_halo_run(const sr_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, cudaStream_t st) {
+int conv_wgrad_halo_run(const sr_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, float* ws, size_t ws_bytes, cudaStream_t st) {
     int rc = load_driver_fns();
     if (rc != SR_OK) return rc;
     if (!g_wg_sms) {
@@ -536,8 +530,7 @@ int conv_wgrad_halo_run(const sr_conv_desc* d, const void* x, const void* dy, fl
     p.ci_blocks = d->Cin / 64;
     p.P = (int)cdiv(d->W + 2, 8) * 8;
     // rows per tile: R * P must be a multiple of 16 pixels (one K step); aim at ~128-pixel stages (few, large TMA boxes)
-    static int r_mult = -1;
-    if (r_mult < 0) r_mult = wg_env("SR_WG_RMULT", 2);      // measured: 2 (224-pixel stages at 54^2) beats 1 on every layer but D.7
+    const int r_mult = option("SR_WG_RMULT", 2);            // measured: 2 (224-pixel stages at 54^2) beats 1 on every layer but D.7
     const int r0 = (p.P % 16 == 0) ? 1 : 2;
     int m = 128 / (r0 * p.P); if (m < 1) m = 1;
     p.R = r0 * m * (r_mult > 0 ? r_mult : 1);
@@ -571,9 +564,7 @@ int conv_wgrad_halo_run(const sr_conv_desc* d, const void* x, const void* dy, fl
     const int items = p.splits * tiles;
     const int grid = items < g_wg_sms ? items : g_wg_sms;
     const size_t need = (size_t)items * p.mt * (p.tg * p.nt) * sizeof(float);
-    static int ws_off = -1;
-    if (ws_off < 0) ws_off = wg_env("SR_WG_NOWS", 0) ? 1 : 0;
-    p.partial = (!ws_off && g_wg_workspace && need <= g_wg_workspace_bytes && p.splits > 1) ? g_wg_workspace : nullptr;
+    p.partial = (!option("SR_WG_NOWS", 0) && ws && need <= ws_bytes && p.splits > 1) ? ws : nullptr;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + 256;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }

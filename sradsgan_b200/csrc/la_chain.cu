@@ -614,9 +614,7 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
 }
 
 static int la_mma_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("SR_LA_MMA"); on = e ? atoi(e) : 1; }
-    return on;
+    return option("SR_LA_MMA", 1);
 }
 
 // dq[p][ch] = sum_taps w7[ch][tap] * de[p - off],  de = dm * m * (1 - m)
@@ -780,8 +778,8 @@ la_fix_kernel(T* __restrict__ dx, const float* __restrict__ da, const float* __r
 // pixel slices per image of the two per-image reductions (pool partials, ds): their kernels walk a slice with one warp per
 // pixel and dependent global loads, so they want MANY blocks (measured, SR_LA_SLICE_PX = pixels per slice)
 static int la_slices(int P) {
-    static int px = -1;
-    if (px < 0) { const char* e = getenv("SR_LA_SLICE_PX"); px = e ? atoi(e) : 96; if (px < 8) px = 8; }
+    int px = option("SR_LA_SLICE_PX", 96);
+    if (px < 8) px = 8;
     int s = (P + px - 1) / px;
     return s < 1 ? 1 : (s > 32 ? 32 : s);
 }
@@ -853,17 +851,12 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
                                                      db, dz_out, nullptr);
     } else
         la_bwd_apply_kernel<T><<<grid, 256, smem, st>>>(gz32, (const T*)gz16, (const T*)x, s, m, Wm, P, NP, tiles, g, dm, dW, db, dz_out);
-    // The 7x7 weight gradient only feeds the optimiser: it runs on an internal side stream (forked / joined with events, so
-    // the call stays stream-ordered for the caller and capturable) next to the rest of the chain.  SR_LA_SIDE=0: same stream.
-    static cudaStream_t side = nullptr;
-    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    static int side_on = -1;
-    if (side_on < 0) { const char* e = getenv("SR_LA_SIDE"); side_on = e ? atoi(e) : 1; }
-    if (side_on && !side) {
-        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) { side = nullptr; side_on = 0; cudaGetLastError(); }
-    }
+    // The 7x7 weight gradient only feeds the optimiser: it runs on the caller's auxiliary stream (forked / joined with events, so
+    // the call stays stream-ordered for the caller and capturable) next to the rest of the chain.
+    const AuxStreams& aux = aux_streams();                 // the caller's auxiliary stream 0 (sr_set_aux_streams), if any
+    const bool side_on = aux.n >= 1 && option("SR_LA_SIDE", 1);
+    cudaStream_t side = side_on ? aux.stream[0] : nullptr;
+    cudaEvent_t ev_fork = aux.fork, ev_join = aux.join[0];
     {
         const int bands = (H + LA_WG_ROWS - 1) / LA_WG_ROWS;
         const size_t wg_smem = sizeof(float) * ((size_t)(LA_WG_ROWS + 6) * (W + 6) * 2 + (size_t)LA_WG_ROWS * W + 2 * 98);
@@ -875,8 +868,7 @@ static int la_bwd_t(const float* gz32, const void* gz16, const void* x, const fl
         if (side_on) cudaEventRecord(ev_join, side);
     }
     la_conv7_dgrad_kernel<<<(unsigned)cdiv(NP, 256), 256, 0, st>>>(dm, m, w7, N, H, W, dq);
-    static int gate_tail = -1;
-    if (gate_tail < 0) { const char* e = getenv("SR_LA_GATE_TAIL"); gate_tail = e ? atoi(e) : 1; }
+    const int gate_tail = option("SR_LA_GATE_TAIL", 1);
     la_bwd_stats_kernel<T><<<dim3(S, N), 256, 0, st>>>(g, dq, cstar, (const T*)x, s, P, S, (T*)dx, ds, gate_tail ? done : nullptr, avg, mx, fc1, fc2,
                                                        Cr, d_fc1, d_fc2, da, dmx);
     if (!gate_tail) la_gate_bwd_kernel<<<N, LA_C, 0, st>>>(ds, s, avg, mx, fc1, fc2, Cr, d_fc1, d_fc2, da, dmx);
@@ -912,9 +904,7 @@ int la_band_fwd(LaBandFwd p, cudaStream_t st);
 int la_band_bwd(LaBandBwd p, cudaStream_t st);
 
 static int la_band_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("SR_LA_BAND"); on = e ? atoi(e) : 1; }
-    return on;
+    return option("SR_LA_BAND", 1);
 }
 
 bool la_chain_band_path(int N, int H, int W, int dtype) { return dtype == SR_BF16 && la_band_enabled() && la_band_supported(N, H, W); }
