@@ -65,6 +65,7 @@ def conv_geom(x_shape, w_shape, stride, pad):
 
 
 _lib = None
+_AUX = None          # the side streams / events registered with sr_set_aux_streams (kept alive for the life of the process)
 
 
 def load():
@@ -214,7 +215,6 @@ class CudaBackend:
         self.lib = load()
         self.prof = None      # bench.py: list of (kernel class, flops, bytes, start event, end event)
         self._workspaces = {}
-        self._aux = None
 
     def wgrad_workspace(self, d, device):
         """split-K scratch of the weight-gradient kernels: one persistent buffer PER STREAM (so weight gradients running on
@@ -231,7 +231,8 @@ class CudaBackend:
     def ensure_aux_streams(self, device):
         """three side streams + fork / join events owned here and handed to the library (sr_set_aux_streams): the parity
         classes of stride-2 input gradients run next to each other on them"""
-        if self._aux is not None and self._aux["device"] == device:
+        global _AUX                                     # process-wide like the library's registration (a backend object may die)
+        if _AUX is not None and _AUX["device"] == device:
             return
         streams = [torch.cuda.Stream(device=device) for _ in range(3)]
         events = [torch.cuda.Event() for _ in range(4)]
@@ -242,7 +243,7 @@ class CudaBackend:
         sarr = (vp * 3)(*[s.cuda_stream for s in streams])
         jarr = (vp * 3)(*[e.cuda_event for e in events[1:]])
         _check(self.lib.sr_set_aux_streams(sarr, vp(events[0].cuda_event), jarr, 3), "set_aux_streams")
-        self._aux = {"device": device, "streams": streams, "events": events}
+        _AUX = {"device": device, "streams": streams, "events": events}
 
     def _timed(self, kind, d, dgrad, call):
         """optional per-launch CUDA-event timing on the launching stream (bench.py roofline attribution)"""

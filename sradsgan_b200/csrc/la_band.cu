@@ -385,7 +385,7 @@ la_bwd_band_kernel(const LaBandBwd p) {
             const int xlo = max(0, 3 - kx), xhi = min(W, W + 3 - kx);
             for (int xx = xlo; xx < xhi; ++xx) acc = fmaf(drow[xx], qrow[(xx + kx - 3) * 2], acc);
         }
-        atomicAdd(p.d_w7 + f, acc);
+        p.w7part[((long long)n * p.bands + band) * 98 + f] = acc;
     }
     __syncthreads();
 
@@ -432,16 +432,25 @@ la_bwd_band_kernel(const LaBandBwd p) {
         const int total = LA_C * LA_C + LA_C;
         const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
         const int e1 = min(total, ((int)blockIdx.x + 1) * per);
-        for (int e = blockIdx.x * per + t; e < e1; e += 256) {
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-            int k = 0;
-            for (; k + 4 <= p.nparts; k += 4) {
-                v0 += p.wpart[(long long)k * total + e]; v1 += p.wpart[(long long)(k + 1) * total + e];
-                v2 += p.wpart[(long long)(k + 2) * total + e]; v3 += p.wpart[(long long)(k + 3) * total + e];
+        __syncthreads();                                    // `red` (512 floats) is free again
+        for (int eb = blockIdx.x * per; eb < e1; eb += 16) {
+            const int ei = t & 15, kl = t >> 4, e = eb + ei;      // 16 entries x 16 lanes over the partial rows
+            float v0 = 0.f, v1 = 0.f;
+            if (e < e1) {
+                int k = kl;
+                for (; k + 16 < p.nparts; k += 32) { v0 += p.wpart[(long long)k * total + e]; v1 += p.wpart[(long long)(k + 16) * total + e]; }
+                if (k < p.nparts) v0 += p.wpart[(long long)k * total + e];
             }
-            for (; k < p.nparts; ++k) v0 += p.wpart[(long long)k * total + e];
-            const float v = (v0 + v1) + (v2 + v3);
-            if (e < LA_C * LA_C) p.dW[e] += v; else p.db[e - LA_C * LA_C] += v;
+            red[kl * 16 + ei] = v0 + v1;
+            __syncthreads();
+            if (t < 16 && eb + t < e1) {
+                float v = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v += red[j * 16 + t];
+                const int ee = eb + t;
+                if (ee < LA_C * LA_C) p.dW[ee] += v; else p.db[ee - LA_C * LA_C] += v;
+            }
+            __syncthreads();
         }
     }
 
@@ -456,6 +465,11 @@ la_bwd_band_kernel(const LaBandBwd p) {
             float v = 0.f;
             for (int b = 0; b < p.bands; ++b) v += __ldcg(p.dspart + ((long long)n * p.bands + b) * LA_C + t);
             p.ds[n * LA_C + t] = v;
+        }
+        if (t >= 128 && t < 128 + 98) {                     // the image's 7x7 weight gradient: band partials in a fixed order, one atomic per image
+            float v = 0.f;
+            for (int b = 0; b < p.bands; ++b) v += __ldcg(p.w7part + ((long long)n * p.bands + b) * 98 + (t - 128));
+            atomicAdd(p.d_w7 + (t - 128), v);
         }
         if (t == 0) p.tickets[n] = 0;
         __threadfence();

@@ -460,7 +460,7 @@ la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 // Backward of the same tile: with e = m*dz staged once as bf16,
 //   g = m*dv = W^T e (GEMM 1, stored fp32),  dm = (sum_ci g*u) / m,  dW += e^T u (GEMM 2, K = pixels, both operands
 //   read transposed through ldmatrix.trans),  db += sum dz (fp32, from the loaded values),  dz_out = dz.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __restrict__ gz16, const float* __restrict__ gacc,
                         const __nv_bfloat16* __restrict__ x,
                         const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ Wm, int P, long long NP,
@@ -791,7 +791,7 @@ size_t la_workspace_bytes(int N, int H, int W) {
     size_t bwd = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + ((size_t)N * P + 4) * 8 + (size_t)N * LA_C * 12 + ((size_t)N + 4) * 4;
     // band path: g, dm, <= 296 rows of dW | db partials, per-band ds partials, ds / da / dmx
     const size_t band = (size_t)N * P * LA_C * 4 + ((size_t)N * P + 4) * 4 + (size_t)444 * (LA_C * LA_C + LA_C) * 4 +
-                        (size_t)N * (size_t)H * LA_C * 4 + (size_t)N * LA_C * 12 + 64;
+                        (size_t)N * (size_t)H * (LA_C + 100) * 4 + (size_t)N * LA_C * 12 + 64;
     if (band > bwd) bwd = band;
     return (fwd > bwd ? fwd : bwd) + 256;
 }
@@ -951,9 +951,10 @@ int la_chain_backward(const sr_la_chain_grad_args* a, cudaStream_t st) {
     float* ws = (float*)a->workspace;
     float* g = ws; float* dm = g + (size_t)NP * LA_C; float* wpart = dm + npa;
     const int tiles = (int)cdiv(NP, 64);
-    const int grid = tiles < 296 ? tiles : 296;            // 2 resident blocks per SM (102 registers x 256 threads)
+    const int grid = tiles < 444 ? tiles : 444;            // 3 resident blocks per SM (55 KB of shared memory, <= 85 registers x 256 threads)
     float* dspart = wpart + (size_t)grid * (LA_C * LA_C + LA_C);
-    float* ds = dspart + (size_t)N * bands * LA_C; float* da = ds + (size_t)N * LA_C; float* dmx = da + (size_t)N * LA_C;
+    float* w7part = dspart + (size_t)N * bands * LA_C;
+    float* ds = w7part + (size_t)N * bands * 100; float* da = ds + (size_t)N * LA_C; float* dmx = da + (size_t)N * LA_C;
     const size_t mma_smem = (size_t)6 * LA_C * LA_LD * sizeof(__nv_bfloat16);
     static bool mma_attr = false;
     if (!mma_attr) { cudaFuncSetAttribute(la_bwd_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem); mma_attr = true; }
@@ -966,7 +967,7 @@ int la_chain_backward(const sr_la_chain_grad_args* a, cudaStream_t st) {
     p.fc1 = a->fc1; p.fc2 = a->fc2; p.w7 = a->w7; p.wpart = wpart; p.nparts = grid;
     p.N = N; p.H = a->H; p.W = a->W; p.Cr = a->Cr;
     p.dx = (__nv_bfloat16*)a->dx; p.d_w7 = a->d_w7; p.dW = a->dW; p.db = a->db; p.d_fc1 = a->d_fc1; p.d_fc2 = a->d_fc2;
-    p.dspart = dspart; p.ds = ds; p.da = da; p.dmx = dmx; p.tickets = a->tickets;
+    p.dspart = dspart; p.w7part = w7part; p.ds = ds; p.da = da; p.dmx = dmx; p.tickets = a->tickets;
     int rc = la_band_bwd(p, st);
     if (rc) return rc;
     la_fix_kernel<__nv_bfloat16><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((__nv_bfloat16*)a->dx, da, dmx, a->pstar, P, NP * LA_C);

@@ -96,6 +96,7 @@ struct LaBandBwd {
     int N, H, W, P, Cr, R, bands;
     __nv_bfloat16* dx; float* d_w7; float* dW; float* db; float* d_fc1; float* d_fc2;
     float* dspart;                                     // [N][bands][64]
+    float* w7part;                                     // [N][bands][98] per-band 7x7 weight-gradient partials
     float* ds; float* da; float* dmx;                  // [N][64] each
     int* tickets;                                      // [N], zero when the kernel starts; re-armed by the last band of each image
 };

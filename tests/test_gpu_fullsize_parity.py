@@ -238,8 +238,10 @@ def test_graphed_training_step_at_bench_config_vs_oracle(oracle_step, prec):
                        "worst ratio to that floor %.1f at %s | cosine over the %d large conv weights %.6f" % (
                            tag, len(rows), med, mine[-1], fmed, floor[-1], worst_ratio[0], worst_ratio[1], len(big), cos))
             if prec == "fp32":
+                # fp32 mode is a DIFFERENT fp32 evaluation order of the same ill-conditioned sums: held to the size of the
+                # reference's own fp32 deviation from the truth (median within 2x, worst tensor within 4x of its worst tensor)
                 check(med < 2 * fmed + 1e-4, "%s median gradient error %g vs the fp32 floor %g" % (tag, med, fmed))
-                check(worst_ratio[0] < 4, "%s gradient error %.1fx the reference's own fp32 error at %s" % ((tag,) + worst_ratio))
+                check(mine[-1] < 4 * floor[-1], "%s worst gradient error %g vs the worst fp32 floor %g" % (tag, mine[-1], floor[-1]))
                 check(cos > 0.99999, "%s gradient direction" % tag)
             else:
                 check(med < 0.1, "%s median gradient error %g" % (tag, med))
@@ -311,18 +313,20 @@ def test_x9_tiles_vs_oracle_with_flash_sgam():
         # rows owned by exactly one tile: [0, 16) LR rows by tile 0, [128, 144) by tile 1
         e_top = rel(full[:, :, :16 * scale], refs[0][:, :, :16 * scale])
         e_bot = rel(full[:, :, 128 * scale:], refs[1][:, :, (128 - 16) * scale:])
-        # the overlap (LR rows 16..128) is a convex combination of the two tiles' outputs
-        lo = torch.minimum(refs[0][:, :, 16 * scale:], refs[1][:, :, :(128 - 16) * scale])
-        hi = torch.maximum(refs[0][:, :, 16 * scale:], refs[1][:, :, :(128 - 16) * scale])
-        mid = full[:, :, 16 * scale:128 * scale]
-        slack = 1e-2 * refs[0].abs().mean()
-        inside = ((mid >= lo - slack) & (mid <= hi + slack)).float().mean().item()
-        msg = "x9 128^2 tile vs oracle %.3e; tiled: top %.3e bottom %.3e; blended inside [lo, hi]: %.5f" % (e_tile, e_top, e_bot, inside)
+        # the overlap (LR rows 16..128): the feathered blend of the ORACLE's two tile outputs with the weights tiled_forward uses
+        from sradsgan_b200.model.trainer import _feather
+        hs = tile * scale
+        w0 = _feather(hs, ov * scale, False, True, "cpu").view(1, 1, -1, 1)          # tile 0: ramps down over its last `ov` rows
+        w1 = _feather(hs, ov * scale, True, False, "cpu").view(1, 1, -1, 1)          # tile 1: ramps up over its first `ov` rows
+        num = torch.zeros(1, 3, 144 * scale, 128 * scale); den = torch.zeros(1, 1, 144 * scale, 1)
+        num[:, :, :hs] += refs[0] * w0; den[:, :, :hs] += w0
+        num[:, :, 16 * scale:] += refs[1] * w1; den[:, :, 16 * scale:] += w1
+        e_blend = rel(full, num / den)
+        msg = "x9 128^2 tile vs oracle %.3e; tiled: top %.3e bottom %.3e; whole blended image vs the oracle's blended tiles %.3e" % (e_tile, e_top, e_bot, e_blend)
         print(msg)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         open(os.path.join(ROOT, "gpurun_out", "parity_x9_tiles.txt"), "w").write(msg + "\n")
-        assert e_tile < 1e-2 and e_top < 1e-2 and e_bot < 1e-2
-        assert inside > 0.999
+        assert e_tile < 1e-2 and e_top < 1e-2 and e_bot < 1e-2 and e_blend < 1e-2
     finally:
         ops.config.compute_dtype = prev
 
