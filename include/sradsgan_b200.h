@@ -296,6 +296,15 @@ int sr_debug_umma_shift(const void* a, int rows_a, const void* b, int shift_rows
  * issues iters x num_acc x k_steps instructions, k_steps consecutive ones into the same of num_acc TMEM accumulators;
  * cycles[cta] = SM clock ticks from first issue to completion. */
 int sr_debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, int64_t* cycles, void* stream);
+
+/* Diagnostics: role timeline of the halo convolution kernel.  While `buf` (device, [CTAs][128] int64, zeroed by the caller) is
+ * set, every conv_halo launch stamps the SM clock at its milestones (slot map: csrc/conv_halo.cu); NULL switches it off.
+ * dbg: experiment bits for the epilogue (1: no global stores, 2: no accumulator reads either; results are then garbage). */
+int sr_debug_halo_trace(int64_t* buf, int dbg);
+
+/* Diagnostics: writes a [rows][row_bytes] buffer once with the store pattern of a convolution epilogue (0: lane = row, 16 B per
+ * lane and instruction; 1: lane quads share a row; 2: lane octets; 3: fully contiguous) — L2 write bandwidth vs LSU line rate. */
+int sr_debug_store_pattern(void* out, int rows, int row_bytes, int pattern, int grid, void* stream);
 #endif
 
 #ifdef __cplusplus

@@ -10,7 +10,9 @@ from collections import namedtuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsradsgan_b200.so")
+# SR_LIB_PATH: a DIAGNOSTICS build of the same library (python __graft_entry__.py --probes writes build/probes/...); the product
+# always loads the in-tree file
+LIB_PATH = os.environ.get("SR_LIB_PATH") or os.path.join(_HERE, "libsradsgan_b200.so")
 
 SR_F32, SR_BF16 = 0, 1
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
@@ -121,6 +123,12 @@ def load():
         lib.sr_debug_umma_shift.restype = i32
         lib.sr_debug_umma_rate.argtypes = [i32, i32, i32, i32, i32, vp, vp]
         lib.sr_debug_umma_rate.restype = i32
+    if hasattr(lib, "sr_debug_store_pattern"):
+        lib.sr_debug_store_pattern.argtypes = [vp, i32, i32, i32, i32, vp]
+        lib.sr_debug_store_pattern.restype = i32
+    if hasattr(lib, "sr_debug_halo_trace"):
+        lib.sr_debug_halo_trace.argtypes = [vp, i32]
+        lib.sr_debug_halo_trace.restype = i32
     lib.sr_sgam_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.sr_sgam_pv.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.sr_sgam_ds.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]

@@ -116,6 +116,9 @@ int sgam_bwd_prep(const float*, const void*, const float*, long long, void*, flo
 // debug_probe.cu (diagnostics: built only with -DSR_WITH_PROBES, see __graft_entry__.build(probes=True))
 int debug_umma_shift(const void*, int, const void*, int, int, int, float*, cudaStream_t);
 int debug_umma_rate(int, int, int, int, int, long long*, cudaStream_t);
+int debug_store_pattern(void*, int, int, int, int, cudaStream_t);
+extern int g_hl_dbg;
+extern long long* g_hl_trace;          // conv_halo.cu: role timeline of the halo convolution ([grid][128] SM clock stamps)
 #endif
 
 static int g_arch_ok = -1;
@@ -581,6 +584,12 @@ int sr_debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, int
     SR_REQUIRE(cycles != nullptr, "debug_umma_rate: NULL output");
     return debug_umma_rate(n, num_acc, iters, k_steps, grid, (long long*)cycles, (cudaStream_t)stream);
 }
+
+int sr_debug_store_pattern(void* out, int rows, int row_bytes, int pattern, int grid, void* stream) {
+    return debug_store_pattern(out, rows, row_bytes, pattern, grid, (cudaStream_t)stream);
+}
+
+int sr_debug_halo_trace(int64_t* buf, int dbg) { g_hl_trace = (long long*)buf; g_hl_dbg = dbg; return SR_OK; }
 #endif  // SR_WITH_PROBES
 
 }  // extern "C"

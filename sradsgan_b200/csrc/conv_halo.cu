@@ -13,6 +13,13 @@
 //     accumulator rows that are never stored: ~84 % of the MMA rows are useful, for 4.5x less L2->SMEM traffic;
 //   * weights: resident in shared memory for the whole kernel when the [9*Cin] x block_n slab fits (Cin = 64),
 //     else streamed tap by tap through their own TMA ring.
+//   * 64 output channels (RAB conv2, the input gradient of conv1): an N = 64 instruction keeps the tensor core busy for 32
+//     cycles but cannot be issued faster than every ~50 (profiles/r01_umma_issue_rate.txt) — the kernel was issue-bound at
+//     ~70 cycles per instruction (profiles/r02_halo_trace.txt).  `stack` mode: the weight stage of a filter ROW holds its three
+//     kx taps as 192 consecutive B rows, ONE N = 192 instruction per k-step multiplies the row-shifted (ky only) view with
+//     all three, and the column shift moves to the epilogue: out[j] = R_0[j] + R_1[j + 1] + R_2[j + 2] (accumulator rows are
+//     TMEM lanes = threads of the epilogue warp: two shuffles per value, the two rows past a warp's quarter come from the
+//     next warp through shared memory).  3x fewer instructions, each long enough for a single issuer.
 // Warp roles, TMEM double buffering and the epilogue are those of conv_tc.cu.
 // Reference call sites: the 3x3 stride-1 nn.Conv2d layers of model/sradsgan.py (RAB :222-223, GAB_UP :381,
 // Discriminator :476 odd blocks, VGG19 features) and their input gradients.
@@ -35,6 +42,9 @@ struct HaloParams {
     int dual;                        // 1: two MMA-issuer warps work on two pixel tiles at once (shared weights)
     int n_pair_items, n_items;       // per CTA lane: items [0, n_pair_items) are tile pairs, the rest single tiles
     int split_ok;                    // dual + streamed weights + >= 2 channel blocks: a SINGLE tile is split along K between the two issuers
+    int stack;                       // Cout = 64: the three kx taps of a filter row stacked along N (one N = 192 instruction instead of three N = 64
+                                     // ones, which are issue-bound); accumulator = [R_kx0 | R_kx1 | R_kx2], out[j] = sum_kx R_kx[j + shift(kx)] in the
+                                     // epilogue.  Tile pairs (dual = 1) on ONE issuer, single-buffered accumulators (2 x 192 TMEM columns)
     const float* bias;
     const void* residual;
     const void* mask;                // nullable bf16 tensor shaped like the output: out *= act'(mask)
@@ -44,7 +54,22 @@ struct HaloParams {
     // RAB (la_band.cu): [N][pool_rows][64] channel sums and packed (max, first arg-max pixel) keys, one row per pixel tile of
     // the image; nullable
     float* pool_sum; unsigned int* pool_key; int pool_rows;
+#ifdef SR_WITH_PROBES
+    int dbg;                         // diagnostics build: 1 = epilogue issues no global stores, 2 = epilogue reads no accumulators either
+    long long* trace;                // diagnostics build: [grid][HL_TRACE_SLOTS] SM clock stamps of the roles' milestones (scripts/halo_trace.py)
+#endif
 };
+
+#ifdef SR_WITH_PROBES
+constexpr int HL_TRACE_SLOTS = 128;
+long long* g_hl_trace = nullptr;
+int g_hl_dbg = 0;
+// slots: 0 start, 1 setup done, 2 end; producer 8+it*2+w = A load issued; issuer w: 32+w*24+it*3+{0 accumulator free, 1 A landed,
+// 2 MMAs committed}; epilogue group g (quarter 0): 80+g*16+it*2+{0 accumulator full, 1 stores issued}
+#define HL_TRACE(slot) do { if (p.trace && (slot) < HL_TRACE_SLOTS) p.trace[(long long)blockIdx.x * HL_TRACE_SLOTS + (slot)] = clock64(); } while (0)
+#else
+#define HL_TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ unsigned int hl_bf16_key(__nv_bfloat16 v) {
     const unsigned int b = __bfloat16_as_ushort(v);
@@ -150,9 +175,9 @@ __device__ __forceinline__ void hl_tile_origin(const HaloParams& p, int p_tile, 
 // split (dual, a single tile whose channel blocks were divided between the two issuers): both groups wait for BOTH
 // accumulators, group g sums and stores the chunks of parity g, and after a barrier among the eight epilogue warps group g
 // releases issuer g's buffer.  Every warp tracks both issuers' buffer indices so the three item kinds can interleave.
-template <typename OutT, int ACT, bool POOL>
+template <typename OutT, int ACT, bool POOL, bool STACK>
 __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
-                                            const float* bias_s, int quarter, int grp, int lane) {
+                                            const float* bias_s, float* xch_s, int quarter, int grp, int lane) {
     const int j = quarter * 32 + lane;           // MMA row
     const int q = j + 1;                         // padded-linear position inside the tile
     const int tr = q / p.TWp, cp = q - tr * p.TWp;
@@ -164,7 +189,8 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
     const OutT* res = reinterpret_cast<const OutT*>(p.residual);
     const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(p.mask);
     int accs[2] = {0, 0}; uint32_t phs[2] = {0, 0};
-    auto advance = [&](int w) { if (++accs[w] == 2) { accs[w] = 0; phs[w] ^= 1; } };
+    const int nbuf = p.stack ? 1 : 2;            // accumulator buffers per issuer / tile slot
+    auto advance = [&](int w) { if (++accs[w] == nbuf) { accs[w] = 0; phs[w] ^= 1; } };
     int t0, t1, nb;
     for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
         const bool split = p.split_ok && t1 < 0;
@@ -208,7 +234,21 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
             };
+            // bf16 outputs: row-coalesced stores (tc_store_chunk_quads) — the row bases of the lane's quad, fetched once per tile
+            const bool quads = sizeof(OutT) == 2 && !POOL && !p.narrow;
+            const long long row_base = r > 1 ? ((((long long)n * p.H * r + (long long)oy * r) * ((long long)p.W * r)) + (long long)ox * r) * cq : row_idx;
+            long long q_base[4] = {0, 0, 0, 0};
+            unsigned q_ok = 0;
+            if (quads) {
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                q_ok = (vm >> (lane & ~3)) & 0xFu;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q_base[i] = __shfl_sync(0xffffffffu, row_base, (lane & ~3) + i) + (lane & 3) * 8;
+            }
             auto emit = [&](const uint32_t (&v)[32], int c) {
+#ifdef SR_WITH_PROBES
+                if (p.dbg & 1) return;
+#endif
                 if (POOL) {                      // (bf16 output, Cout = 64, no residual / mask / shuffle: checked on the host) every lane takes part
                     if (sizeof(OutT) == 2) {
                         const int col = c * 32;
@@ -219,9 +259,8 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                     }
                     return;
                 }
-                if (!valid) return;
                 if (p.narrow) {              // thin output (RGB / 1-channel critic map): only the first Cout accumulator columns are real
-                    if (c == 0) {
+                    if (valid && c == 0) {
                         OutT* o = out + ((((long long)n * p.H + oy) * p.W) + ox) * p.Cout;
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj)
@@ -230,14 +269,22 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                     return;
                 }
                 const int col = nb * p.block_n + c * 32;
-                long long idx;
+                int chunk_off = col;             // offset of this chunk's first column from the row base (the same for every row)
                 if (r > 1) {
                     const int sub = col / cq, ch0 = col - sub * cq;
                     const int si = sub / r, sj = sub - si * r;
-                    idx = ((((long long)n * p.H * r + (oy * r + si)) * ((long long)p.W * r)) + (ox * r + sj)) * cq + ch0;
-                } else {
-                    idx = row_idx + col;
+                    chunk_off = (si * p.W * r + sj) * cq + ch0;
                 }
+                if (sizeof(OutT) == 2) {
+                    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
+                    __nv_bfloat16* const qp[4] = {ob + q_base[0] + chunk_off, ob + q_base[1] + chunk_off, ob + q_base[2] + chunk_off, ob + q_base[3] + chunk_off};
+                    const long long idx = row_base + chunk_off;
+                    tc_store_chunk_quads<ACT>(v, bias_s + col, p.slope, (res && valid) ? reinterpret_cast<const __nv_bfloat16*>(res) + idx : nullptr,
+                                              (mask && valid) ? mask + idx : nullptr, p.mask_slope, qp, q_ok, lane);
+                    return;
+                }
+                if (!valid) return;
+                const long long idx = row_base + chunk_off;
                 tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx,
                                           mask ? mask + idx : nullptr, p.mask_slope);
             };
@@ -266,8 +313,66 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                 const int buf = own * 2 + accs[own];
                 mbar_wait(acc_full + buf, phs[own]);
                 tc_fence_after();
-                const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * acc_stride);
+                if (quarter == 0 && lane == 0) HL_TRACE(80 + grp * 16 + it * 2);
+                const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(STACK ? own * 192 : buf * acc_stride);
                 int c = c_first;
+                if (STACK) {
+                    // out[j] = S0[j] + S1[j + 1] + S2[j + 2], S_s = the 64-column block whose taps sit s pixels to the right (flip mirrors
+                    // the order).  Rows j + 1, j + 2 of lanes 30 / 31 belong to the next quarter's warp: every warp publishes its first
+                    // rows of S1 (row 0) and S2 (rows 0, 1) in shared memory, one half of the exchange area per 32-column chunk (so one
+                    // barrier per chunk orders writes against the previous reads of the same half).
+                    const uint32_t col_s0 = p.flip ? 128u : 0u, col_s2 = p.flip ? 0u : 128u;
+#pragma unroll 1
+                    for (int cc = 0; cc < 2; ++cc) {
+                        float* xch = xch_s + (grp * 2 + cc) * (4 * 3 * 32);              // [quarter][3 rows][32 columns]
+                        float f[32];
+                        tmem_ld32_nowait(t_base + col_s0 + (uint32_t)(cc * 32), va);
+                        tmem_ld32_nowait(t_base + 64u + (uint32_t)(cc * 32), vb);
+                        tmem_ld_wait(va);
+                        tmem_ld_wait(vb);
+                        if (lane == 0) {
+#pragma unroll
+                            for (int k = 0; k < 32; k += 4)
+                                *reinterpret_cast<uint4*>(xch + (quarter * 3 + 0) * 32 + k) = make_uint4(vb[k], vb[k + 1], vb[k + 2], vb[k + 3]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const float nx = __shfl_down_sync(0xffffffffu, __uint_as_float(vb[k]), 1);
+                            f[k] = __uint_as_float(va[k]) + (lane < 31 ? nx : 0.f);
+                        }
+                        tmem_ld32_nowait(t_base + col_s2 + (uint32_t)(cc * 32), va);
+                        tmem_ld_wait(va);
+                        if (lane < 2) {
+#pragma unroll
+                            for (int k = 0; k < 32; k += 4)
+                                *reinterpret_cast<uint4*>(xch + (quarter * 3 + 1 + lane) * 32 + k) = make_uint4(va[k], va[k + 1], va[k + 2], va[k + 3]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const float nx = __shfl_down_sync(0xffffffffu, __uint_as_float(va[k]), 2);
+                            f[k] += (lane < 30 ? nx : 0.f);
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");
+                        if (lane >= 30 && quarter < 3) {
+                            // lane 31: S1 row 0 + S2 row 1 of the next warp; lane 30: S2 row 0
+                            const float* nx = xch + (quarter + 1) * 3 * 32;
+                            const float* a = nx + (lane == 31 ? 0 : 32);
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                float add = a[k];
+                                if (lane == 31) add += nx[64 + k];
+                                f[k] += add;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) va[k] = __float_as_uint(f[k]);
+                        emit(va, cc);
+                    }
+                    c = chunks;
+                }
+#ifdef SR_WITH_PROBES
+                if (p.dbg & 2) c = chunks;
+#endif
                 if (c < chunks) tmem_ld32_nowait(t_base + (uint32_t)(c * 32), va);
                 while (c < chunks) {
                     tmem_ld_wait(va);
@@ -284,6 +389,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + buf);
+                if (quarter == 0 && lane == 0) HL_TRACE(80 + grp * 16 + it * 2 + 1);
             }
         }
         // buffer bookkeeping of BOTH issuers (identical in every epilogue warp)
@@ -295,12 +401,12 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
 
 // POOL: the instantiation whose epilogue also emits the CLAM pooling partials (RAB conv2 launches only) — a separate
 // kernel so that its extra register pressure (spills) never touches the other convolutions
-template <typename OutT, bool POOL>
+template <typename OutT, bool POOL, bool STACK>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = p.block_n * 128;
+    const int b_bytes = (p.stack ? 192 : p.block_n) * 128;
     const int k_blocks = 9 * p.c_blocks;
     // [resident weights: k_blocks x B] [A ring(s)] [B ring] [barriers] [bias]
     uint8_t* a_base = smem + (p.resident ? (size_t)k_blocks * b_bytes : 0);
@@ -315,16 +421,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* r_full = acc_empty + 4;             // [HL_MAX_RES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + HL_MAX_RES);
     float* bias_s = reinterpret_cast<float*>(bars) + 256;                 // 1024 B after the barrier block
+    float* xch_s = bias_s + HL_BIAS_MAX;                                  // stack mode only: [2 groups][2 chunks][4 quarters][3 rows][32] floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int issuers = p.dual ? 2 : 1;
-    const int ring_a = p.num_a_stages / issuers;  // each issuer owns a private ring of activation stages
+    const int issuers = p.dual ? 2 : 1;           // tile slots of an item (stack mode: both served by the ONE issuer warp)
+    const int ring_a = p.num_a_stages / issuers;  // each slot owns a private ring of activation stages
+    const int b_taps = p.stack ? 3 : 9;           // weight stages per channel block (stack: one per filter row)
+    if (threadIdx.x == 0) {
+        HL_TRACE(0);
+#ifdef SR_WITH_PROBES
+        if (p.trace) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.trace[(long long)blockIdx.x * HL_TRACE_SLOTS + 3] = gt; }
+#endif
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < p.num_a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < p.num_b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, issuers); }
+        for (int s = 0; s < p.num_b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, p.stack ? 1 : issuers); }
         for (int a = 0; a < 4; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, p.dual ? 4 : HL_EPI_WARPS); }
         if (p.resident) for (int kb = 0; kb < k_blocks; ++kb) mbar_init(r_full + kb, 1);
         fence_barrier_init();
@@ -343,6 +457,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) HL_TRACE(1);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -362,11 +477,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         mbar_wait(a_empty + st, pa[w] ^ 1);
                         mbar_expect_tx(a_full + st, (uint32_t)p.a_box_bytes);
                         tma_load_4d(a_base + (size_t)st * p.a_stage_bytes, &map_a, a_full + st, cb * 64, x0 - 1, y0 - 1, n);
+                        if (cb == 0) HL_TRACE(8 + it * 2 + w);
                         if (++sa[w] == ring_a) { sa[w] = 0; pa[w] ^= 1; }
                     }
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < b_taps; ++tap) {
                         const int kb = cb * 9 + tap;
-                        if (p.resident) {
+                        if (p.stack) {
+                            mbar_wait(b_empty + sb, pb ^ 1);
+                            mbar_expect_tx(b_full + sb, (uint32_t)b_bytes);
+                            tma_load_2d(b_base + (size_t)sb * b_bytes, &map_b, b_full + sb, cb * 64, tap * 192);
+                            if (++sb == p.num_b_stages) { sb = 0; pb ^= 1; }
+                        } else if (p.resident) {
                             if (it == 0) {
                                 mbar_expect_tx(r_full + kb, (uint32_t)b_bytes);
                                 tma_load_2d(smem + (size_t)kb * b_bytes, &map_b, r_full + kb, cb * 64, tap * p.Cout + nb * p.block_n);
@@ -386,7 +507,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // sustains ~100 clk per instruction; two issuers on independent accumulators reach the 64 clk floor of an
         // M=128 x N=128 instruction (profiles/r01_umma_issue_rate.txt).  The warp walks the schedule converged. =====
         const int w = warp - 1;
-        if (w < issuers) {
+        if (STACK) {
+            // ===== stack mode: ONE issuer, both tiles of an item per weight stage, N = 192 =====
+            if (w == 0) {
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(192 >> 3) << 17) | ((128u >> 4) << 24);
+                int sa[2] = {0, 0}; uint32_t pa[2] = {0, 0};
+                int sb = 0; uint32_t pb = 0;
+                uint32_t acc_phase[2] = {0, 0};
+                int t0, t1, nb;
+                for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
+                    const bool has[2] = {t0 >= 0, t1 >= 0};
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (has[g]) mbar_wait(acc_empty + g * 2, acc_phase[g] ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) HL_TRACE(32 + it * 3);
+                    for (int cb = 0; cb < p.c_blocks; ++cb) {
+                        uint64_t adesc[2] = {0, 0};
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+                            if (has[g]) {
+                                const int st = g * ring_a + sa[g];
+                                mbar_wait(a_full + st, pa[g]);
+                                adesc[g] = make_kmajor_sw128_desc(smem_u32(a_base + (size_t)st * p.a_stage_bytes));
+                            }
+                        if (lane == 0 && cb == 0) HL_TRACE(32 + it * 3 + 1);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            mbar_wait(b_full + sb, pb);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)sb * b_bytes));
+                                const uint32_t row_off = (uint32_t)((p.flip ? 2 - ky : ky) * p.TWp) * 8u;
+                                const uint32_t accum = (cb | ky) ? 1u : 0u;
+                                if (has[0]) umma_f16_x4(tmem_base, adesc[0] + row_off, bdesc, idesc, accum);
+                                if (has[1]) umma_f16_x4(tmem_base + 192u, adesc[1] + row_off, bdesc, idesc, accum);
+                                umma_commit(b_empty + sb);
+                            }
+                            __syncwarp();
+                            if (++sb == p.num_b_stages) { sb = 0; pb ^= 1; }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+                            if (has[g]) {
+                                if (lane == 0) umma_commit(a_empty + g * ring_a + sa[g]);
+                                if (++sa[g] == ring_a) { sa[g] = 0; pa[g] ^= 1; }
+                            }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (has[g]) {
+                            if (lane == 0) umma_commit(acc_full + g * 2);
+                            acc_phase[g] ^= 1;
+                        }
+                    if (lane == 0) HL_TRACE(32 + it * 3 + 2);
+                    __syncwarp();
+                }
+            }
+        } else if (w < issuers) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((128u >> 4) << 24);
             uint32_t tap_off[9];      // descriptor start-address offsets (16-byte units) of the nine tap views
 #pragma unroll
@@ -411,6 +590,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     mbar_wait(acc_empty + w * 2 + acc, acc_phase ^ 1);
                     tc_fence_after();
                     d_tmem = tmem_base + (uint32_t)((w * 2 + acc) * acc_stride);
+                    if (lane == 0) HL_TRACE(32 + w * 24 + it * 3);
                 }
                 for (int cb = 0; cb < p.c_blocks; ++cb) {
                     uint64_t adesc0 = 0;
@@ -418,6 +598,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const bool mine = split ? ((cb & 1) == w) : has;       // this issuer multiplies channel block cb
                     if (mine) {
                         mbar_wait(a_full + st, pa);
+                        if (lane == 0 && cb == 0) HL_TRACE(32 + w * 24 + it * 3 + 1);
                         adesc0 = make_kmajor_sw128_desc(smem_u32(a_base + (size_t)st * p.a_stage_bytes));
                     }
                     if (p.resident) {
@@ -466,7 +647,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
                 if (has) {
                     if (p.resident) res_ready = true;
-                    if (lane == 0) umma_commit(acc_full + w * 2 + acc);
+                    if (lane == 0) { umma_commit(acc_full + w * 2 + acc); HL_TRACE(32 + w * 24 + it * 3 + 2); }
                     __syncwarp();
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
@@ -476,15 +657,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int e = warp - 3;                    // 0..7
         const int quarter = warp & 3, grp = e >> 2;
         switch (p.act) {
-            case SR_ACT_LRELU: hl_epilogue<OutT, SR_ACT_LRELU, POOL>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
-            case SR_ACT_RELU: hl_epilogue<OutT, SR_ACT_RELU, POOL>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
-            case SR_ACT_SIGMOID: hl_epilogue<OutT, SR_ACT_SIGMOID, false>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
-            default: hl_epilogue<OutT, SR_ACT_NONE, POOL>(p, tmem_base, acc_full, acc_empty, bias_s, quarter, grp, lane); break;
+            case SR_ACT_LRELU: hl_epilogue<OutT, SR_ACT_LRELU, POOL, STACK>(p, tmem_base, acc_full, acc_empty, bias_s, xch_s, quarter, grp, lane); break;
+            case SR_ACT_RELU: hl_epilogue<OutT, SR_ACT_RELU, POOL, STACK>(p, tmem_base, acc_full, acc_empty, bias_s, xch_s, quarter, grp, lane); break;
+            case SR_ACT_SIGMOID: hl_epilogue<OutT, SR_ACT_SIGMOID, false, false>(p, tmem_base, acc_full, acc_empty, bias_s, xch_s, quarter, grp, lane); break;
+            default: hl_epilogue<OutT, SR_ACT_NONE, POOL, STACK>(p, tmem_base, acc_full, acc_empty, bias_s, xch_s, quarter, grp, lane); break;
         }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (threadIdx.x == 0) {
+        HL_TRACE(2);
+#ifdef SR_WITH_PROBES
+        if (p.trace) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.trace[(long long)blockIdx.x * HL_TRACE_SLOTS + 4] = gt; }
+#endif
+    }
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -548,6 +735,9 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.shuffle_r = dgrad ? 0 : d->shuffle_r;
     p.bias = bias; p.residual = residual; p.out = dst;
     p.mask = mask; p.mask_slope = mask_slope;
+#ifdef SR_WITH_PROBES
+    p.trace = g_hl_trace; p.dbg = g_hl_dbg;
+#endif
     if (!dgrad && d->pool_sum && d->pool_key) {
         const int rows = conv_halo_pool_rows(d);
         if (!rows || residual || mask) { set_error("conv_halo: pooling partials need a plain bf16 forward convolution with 64 output channels"); return SR_ERR_UNSUPPORTED; }
@@ -569,14 +759,16 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     // the end) — junk accumulator columns that are simply never stored.
     p.narrow = Cd <= 4 ? 1 : 0;
     if (p.narrow && (residual || mask || p.shuffle_r > 1)) { set_error("conv_halo: thin outputs support bias / activation only"); return SR_ERR_UNSUPPORTED; }
+    // stack mode (64 output channels fed by >= 128 input channels: RAB conv2 and the input gradient of conv1)
+    const bool stack = Cd == 64 && Cs >= 128 && d->out_dtype == SR_BF16 && p.shuffle_r <= 1 && p.TR * p.TWp <= 128 && option("SR_HALO_STACK", 1);
     int bn;
     if (p.narrow) bn = 64; else if (Cd % 128 == 0) bn = 128; else if (Cd % 192 == 0) bn = 192; else bn = 64;
     long long res_bytes = (long long)k_blocks * bn * 128;
-    bool resident = k_blocks <= HL_MAX_RES && bn <= 128 && res_bytes + 2 * p.a_stage_bytes <= HL_TILE_BUDGET;
+    bool resident = !stack && k_blocks <= HL_MAX_RES && bn <= 128 && res_bytes + 2 * p.a_stage_bytes <= HL_TILE_BUDGET;
     if (!resident && Cd % 256 == 0) bn = 256;
     p.block_n = bn;
     p.n_blocks = p.narrow ? 1 : Cd / bn;
-    const int b_bytes = bn * 128;
+    const int b_bytes = (stack ? 192 : bn) * 128;
     res_bytes = (long long)k_blocks * b_bytes;
     int grid = g_hl_sms;
     if (resident) {
@@ -584,6 +776,7 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
         if (p.p_tiles * p.n_blocks <= grid) resident = false;       // every CTA would run a single tile: nothing to keep
     }
     p.resident = resident ? 1 : 0;
+    p.stack = stack ? 1 : 0;
     p.dual = (bn <= 128 && (resident || p.n_blocks == 1)) ? 1 : 0;
     // experiment option: resident-weights layers on ONE issuer with a two-deep activation ring
     if (option("SR_HALO_NODUAL_RES", 0) && resident) p.dual = 0;
@@ -598,13 +791,23 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
         p.n_pair_items = 0;
         p.n_items = resident ? p.p_tiles : p.p_tiles * p.n_blocks;
     }
-    p.split_ok = (option("SR_HALO_SPLITK", 1) && p.dual && !resident && p.c_blocks >= 2) ? 1 : 0;
+    p.split_ok = (option("SR_HALO_SPLITK", 1) && p.dual && !resident && !stack && p.c_blocks >= 2) ? 1 : 0;
     const int total_items = resident ? p.n_items * p.n_blocks : p.n_items;
     if (total_items < grid) { grid = total_items; if (resident) grid -= grid % p.n_blocks; }
     if (grid < 1) grid = p.n_blocks;
 
     size_t tile_bytes;
-    if (resident) {
+    const int xch_bytes = stack ? 2 * 2 * 4 * 3 * 32 * 4 : 0;      // [group][chunk][quarter][3 rows][32] floats
+    if (stack) {
+        // the junk rows' views may read past the rows a stage loads (into the next stage / the weight ring): tight stages
+        p.a_stage_bytes = (int)cdiv(rows_loaded * 128, 1024) * 1024;
+        const int na = 4;
+        int nbs = (HL_TILE_BUDGET - xch_bytes - na * p.a_stage_bytes) / b_bytes;
+        if (nbs > HL_MAX_B) nbs = HL_MAX_B;
+        if (nbs < 2) { set_error("conv_halo: tile does not fit shared memory (stack mode, TWp=%d TR=%d)", p.TWp, p.TR); return SR_ERR_UNSUPPORTED; }
+        p.num_a_stages = na; p.num_b_stages = nbs;
+        tile_bytes = (size_t)na * p.a_stage_bytes + (size_t)nbs * b_bytes;
+    } else if (resident) {
         int na = (int)((HL_TILE_BUDGET - res_bytes) / p.a_stage_bytes);
         if (na > HL_MAX_A) na = HL_MAX_A;
         if (p.dual) na -= na % 2;
@@ -622,21 +825,23 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     alignas(64) CUtensorMap map_a, map_b;
     rc = make_tiled4d_map(&map_a, src, d->N, d->H, d->W, Cs, p.TWp, p.TR + 2);
     if (rc != SR_OK) return rc;
-    rc = make_tiled2d_map(&map_b, w, (uint64_t)9 * Cd, (uint64_t)Cs, (uint32_t)bn);
+    rc = make_tiled2d_map(&map_b, w, (uint64_t)9 * Cd, (uint64_t)Cs, (uint32_t)(stack ? 192 : bn));
     if (rc != SR_OK) return rc;
-    const size_t smem = 1024 + tile_bytes + 1024 + HL_BIAS_MAX * 4;
+    const size_t smem = 1024 + tile_bytes + 1024 + HL_BIAS_MAX * 4 + xch_bytes;
     const bool out_bf16 = d->out_dtype == SR_BF16;
-    static bool attr_set[3] = {false, false, false};
-    if (p.pool_sum) {
-        if (!attr_set[2]) { cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[2] = true; }
-        conv_halo_kernel<__nv_bfloat16, true><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
-    } else if (out_bf16) {
-        if (!attr_set[0]) { cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[0] = true; }
-        conv_halo_kernel<__nv_bfloat16, false><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
-    } else {
-        if (!attr_set[1]) { cudaFuncSetAttribute(conv_halo_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[1] = true; }
-        conv_halo_kernel<float, false><<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);
-    }
+    static bool attr_set[5] = {false, false, false, false, false};
+#define HL_LAUNCH(slot, ...)                                                                                              \
+    do {                                                                                                                  \
+        if (!attr_set[slot]) { cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[slot] = true; } \
+        __VA_ARGS__<<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);                                                     \
+    } while (0)
+    if (stack && !out_bf16) { set_error("conv_halo: internal: stack mode needs a bf16 output"); return SR_ERR_UNSUPPORTED; }
+    if (p.pool_sum && stack) HL_LAUNCH(4, conv_halo_kernel<__nv_bfloat16, true, true>);
+    else if (p.pool_sum) HL_LAUNCH(2, conv_halo_kernel<__nv_bfloat16, true, false>);
+    else if (stack) HL_LAUNCH(3, conv_halo_kernel<__nv_bfloat16, false, true>);
+    else if (out_bf16) HL_LAUNCH(0, conv_halo_kernel<__nv_bfloat16, false, false>);
+    else HL_LAUNCH(1, conv_halo_kernel<float, false, false>);
+#undef HL_LAUNCH
     count_launch();
     return check_launch("conv_halo_kernel");
 }

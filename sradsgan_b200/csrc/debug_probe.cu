@@ -138,4 +138,47 @@ int debug_umma_rate(int n, int num_acc, int iters, int k_steps, int grid, long l
     return check_launch("umma_rate_probe_kernel");
 }
 
+// Store-pattern probe: the epilogue of a convolution writes [rows][row_bytes] bf16 outputs of which one warp owns a 32-row x
+// 64-byte chunk at a time.  pattern 0: lane = row, four 16-byte stores (32 lines per instruction); 1: lane quads share a row
+// (64 contiguous bytes per row, 8 rows per instruction); 2: lane octets write 128 bytes of a row (4 rows per instruction, chunk =
+// 128 bytes); 3: the whole warp writes 512 contiguous bytes (1 row per instruction, chunk = 512 bytes).  Every pattern writes the
+// same `rows * row_bytes` bytes once; the time per launch tells which of L2 write bandwidth / LSU line rate bounds the epilogue.
+__global__ void __launch_bounds__(256, 1)
+store_pattern_probe_kernel(uint4* out, int rows, int row_bytes, int pattern) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31, warps = gridDim.x * 8;
+    const int units_per_row = row_bytes / 16;                      // 16-byte units
+    const uint4 v = make_uint4(warp, lane, 0x3f803f80u, 0x3f803f80u);
+    if (pattern == 0 || pattern == 1) {
+        const int chunks_per_row = row_bytes / 64;
+        const int tiles = (rows / 32) * chunks_per_row;
+        for (int t = warp; t < tiles; t += warps) {
+            const int rb = (t / chunks_per_row) * 32, cu = (t % chunks_per_row) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = pattern == 0 ? rb + lane : rb + (lane & ~3) + i;
+                const int unit = pattern == 0 ? cu + i : cu + (lane & 3);
+                out[(size_t)row * units_per_row + unit] = v;
+            }
+        }
+    } else if (pattern == 2) {
+        const int chunks_per_row = row_bytes / 128;
+        const int tiles = (rows / 32) * chunks_per_row;
+        for (int t = warp; t < tiles; t += warps) {
+            const int rb = (t / chunks_per_row) * 32, cu = (t % chunks_per_row) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[(size_t)(rb + i * 4 + (lane >> 3)) * units_per_row + cu + (lane & 7)] = v;
+        }
+    } else {
+        const size_t total = (size_t)rows * units_per_row;
+        for (size_t u = (size_t)warp * 32 + lane; u < total; u += (size_t)warps * 32) out[u] = v;
+    }
+}
+
+int debug_store_pattern(void* out, int rows, int row_bytes, int pattern, int grid, cudaStream_t st) {
+    SR_REQUIRE(out && rows % 32 == 0 && row_bytes % 512 == 0 && pattern >= 0 && pattern <= 3 && grid > 0, "store_pattern probe: bad arguments");
+    store_pattern_probe_kernel<<<grid, 256, 0, st>>>((uint4*)out, rows, row_bytes, pattern);
+    count_launch();
+    return check_launch("store_pattern_probe_kernel");
+}
+
 }  // namespace sr

@@ -80,7 +80,7 @@ la_fwd_band_kernel(const LaBandFwd p) {
     const long long pix0 = (long long)n * P + (long long)y0 * W;
 
     // ---- operands that do not depend on the data ----
-    for (int i = t; i < LA_C * LA_C; i += 256) st_split1(Ws + (i >> 6) * LA_LD + (i & 63), Wl + (i >> 6) * LA_LD + (i & 63), p.Wm[i]);
+    la_stage_w_split(Ws, Wl, p.Wm, t);
     if (t < LA_C) bias_s[t] = p.bias[t];
     if (t < 98) w7s[t] = p.w7[t];
 

@@ -385,7 +385,7 @@ la_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
     __shared__ __align__(16) __nv_bfloat16 Vs[LA_C * LA_LD], Vl[LA_C * LA_LD];     // [pixel][ci] = m*s*x, hi / lo
     __shared__ float bias_s[LA_C], w7s[98];
     const int t = threadIdx.x;
-    for (int i = t; i < LA_C * LA_C; i += 256) st_split1(Ws + (i >> 6) * LA_LD + (i & 63), Wl + (i >> 6) * LA_LD + (i & 63), Wm[i]);
+    la_stage_w_split(Ws, Wl, Wm, t);
     if (t < LA_C) bias_s[t] = bias[t];
     if (t < 98) w7s[t] = w7[t];
     const int warp = t >> 5, lane = t & 31, mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
@@ -475,7 +475,7 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
     __nv_bfloat16* Ul = Us + LA_C * LA_LD;                                   //                   lo
     __shared__ float ms[LA_C], dm_part[2][LA_C], bsum[LA_C];
     const int t = threadIdx.x;
-    for (int i = t; i < LA_C * LA_C; i += 256) st_split1(Ws + (i >> 6) * LA_LD + (i & 63), Wl + (i >> 6) * LA_LD + (i & 63), Wm[i]);
+    la_stage_w_split(Ws, Wl, Wm, t);
     if (t < LA_C) bsum[t] = 0.f;
     const int warp = t >> 5, lane = t & 31, mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
     const int r8a = (lane & 7) + ((lane >> 3) & 1) * 8, c8a = ((lane >> 4) & 1) * 8;     // matrices 1/2 = rows+8 / cols+8

@@ -78,6 +78,19 @@ __device__ __forceinline__ void la_gate_bwd_body(int n, const float* __restrict_
 }
 
 
+// W [co][ci] (fp32, 16-byte aligned) -> hi / lo bf16 rows of pitch LA_LD in shared memory: four independent 16-byte loads per
+// thread issued together (a scalar loop here costs 16 dependent L2 round trips at the start of every block)
+__device__ __forceinline__ void la_stage_w_split(__nv_bfloat16* Ws, __nv_bfloat16* Wl, const float* __restrict__ Wm, int t) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(Wm + (t + k * 256) * 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = (t + k * 256) * 4, row = e >> 6, col = e & 63;
+        st_split4(Ws + row * LA_LD + col, Wl + row * LA_LD + col, v[k].x, v[k].y, v[k].z, v[k].w);
+    }
+}
+
 // parameter blocks of the band kernels (la_band.cu), filled by la_chain.cu
 struct LaBandFwd {
     const __nv_bfloat16* x; const float* t; const float* acc_in;

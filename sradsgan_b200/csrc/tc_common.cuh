@@ -349,6 +349,89 @@ __device__ __forceinline__ void tc_store_chunk(const uint32_t (&v)[32], const fl
     }
 }
 
+// Row-coalesced variant of tc_store_chunk for bf16 outputs.  With lane = accumulator row, a 16-byte store instruction of the
+// plain variant touches 32 different 128-byte lines (one per row); the L1/LSU path handles one line per cycle and shares its
+// data path with the tensor core's shared-memory operand fetch, so those stores both dominated the epilogue and halved the
+// MMA rate next to it (profiles/r02_halo_trace.txt).  Here the four 16-byte units of a lane's row chunk are transposed inside
+// each lane quad (two butterfly steps, 16 shuffles), after which store instruction i writes, for every quad, the 64
+// contiguous bytes of row 4k+i from its four lanes: 8 lines per instruction instead of 32.
+//   q_ptr[i]  : address of this chunk's first column in row (lane & ~3) + i, already offset by (lane & 3) * 8 elements
+//   q_ok      : bit i = that row is stored
+//   res / mask: as in tc_store_chunk, for the lane's OWN row (nullptr when the row is not stored)
+// Every lane of the warp must call (shuffles).
+template <int ACT>
+__device__ __forceinline__ void tc_store_chunk_quads(const uint32_t (&v)[32], const float* bias_s, float slope, const __nv_bfloat16* res,
+                                                     const __nv_bfloat16* mask, float mask_slope, __nv_bfloat16* const (&q_ptr)[4],
+                                                     unsigned q_ok, int lane) {
+    float f[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float4 b = lds128(bias_s + g * 4);
+        f[g * 4 + 0] = tc_act<ACT>(__uint_as_float(v[g * 4 + 0]) + b.x, slope);
+        f[g * 4 + 1] = tc_act<ACT>(__uint_as_float(v[g * 4 + 1]) + b.y, slope);
+        f[g * 4 + 2] = tc_act<ACT>(__uint_as_float(v[g * 4 + 2]) + b.z, slope);
+        f[g * 4 + 3] = tc_act<ACT>(__uint_as_float(v[g * 4 + 3]) + b.w, slope);
+    }
+    if (mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(mask);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 mv = mp[g];
+            const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (!(__low2float(m2[h]) > 0.f)) f[g * 8 + h * 2] *= mask_slope;
+                if (!(__high2float(m2[h]) > 0.f)) f[g * 8 + h * 2 + 1] *= mask_slope;
+            }
+        }
+    }
+    if (res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(res);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 rv = rp[g];
+            const __nv_bfloat162* r2p = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                f[g * 8 + h * 2] += __low2float(r2p[h]);
+                f[g * 8 + h * 2 + 1] += __high2float(r2p[h]);
+            }
+        }
+    }
+    uint32_t w[16];                                   // unit u (16 bytes = columns 8u .. 8u+7) = w[4u .. 4u+3]
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    // step 1 (partner = lane ^ 2): afterwards R[b][e] = unit 2*((lane >> 1) & 1) + e of the quad row whose bit 1 is b
+    const bool hi = (lane & 2) != 0, odd = (lane & 1) != 0;
+    uint32_t R[2][2][4];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo_u = w[e * 4 + k], hi_u = w[(2 + e) * 4 + k];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, hi ? lo_u : hi_u, 2);
+            R[0][e][k] = hi ? recv : lo_u;
+            R[1][e][k] = hi ? hi_u : recv;
+        }
+    // step 2 (partner = lane ^ 1): T[2b + c] = unit (lane & 3) of quad row 2b + c
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        uint32_t t0[4], t1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? R[b][0][k] : R[b][1][k], 1);
+            const uint32_t keep = odd ? R[b][1][k] : R[b][0][k];
+            t0[k] = odd ? recv : keep;
+            t1[k] = odd ? keep : recv;
+        }
+        if ((q_ok >> (2 * b)) & 1) *reinterpret_cast<uint4*>(q_ptr[2 * b]) = make_uint4(t0[0], t0[1], t0[2], t0[3]);
+        if ((q_ok >> (2 * b + 1)) & 1) *reinterpret_cast<uint4*>(q_ptr[2 * b + 1]) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+    }
+}
+
 // MN-major, 128B-swizzled operand tile ([k rows][64 bf16 of M/N], 8-row groups 1024 B apart, further
 // 64-wide M/N panels `lbo_bytes` apart): UMMA smem descriptor (cute::UMMA canonical MN-major SW128 layout)
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {

@@ -243,6 +243,13 @@ HALO_CASES = [
     (1, 64, 5, 7, 64),         # fewer rows than TR
     (2, 64, 130, 33, 128),     # W + 2 <= 129 with 3 rows per tile, ragged height
     (1, 64, 40, 300, 64),      # three column strips
+    # 64 output channels from >= 128 input channels (and the input gradients of the mirrored shapes): the three kx taps of a filter
+    # row stacked along N, column shift in the epilogue (conv_halo.cu `stack` mode)
+    (1, 128, 40, 300, 64),     # three column strips, two channel blocks
+    (2, 256, 130, 33, 64),     # three rows per tile, ragged height
+    (1, 128, 9, 62, 64),       # TR * TWp = 128: the last output row of a tile reads accumulator rows 126 / 127
+    (1, 192, 5, 7, 64),        # fewer rows than TR, three channel blocks
+    (3, 64, 27, 27, 128),      # dgrad: 128 -> 64 stacked, odd number of tiles (single-tile items)
 ]
 
 
@@ -271,6 +278,30 @@ def test_halo_fwd_dgrad_match_cpu_and_im2col_kernel(be, case):
     dx = be.conv_dgrad(gyc, be.pack_weights(wt.cuda(), 1, torch.bfloat16), g, impl=IMPL_HALO)
     dx_ref = torch.nn.grad.conv2d_input(x.shape, wt.bfloat16().float(), gy.float(), stride=1, padding=1)
     assert rel(dx, dx_ref) < 4e-3
+
+
+@pytest.mark.parametrize("case", [(2, 256, 54, 54, 64), (1, 128, 31, 45, 64)])
+def test_halo_stack_mode_residual_and_plain_mode_agree(be, case):
+    """stack mode (N = 192 instructions + epilogue column shift) against the nine-tap mode of the same kernel (SR_HALO_STACK 0)
+    and torch CPU, with a bf16 residual in the epilogue."""
+    from sradsgan_b200 import _lib
+    n, cin, h, w, cout = case
+    x, wt, b = _mk(n, cin, h, w, cout, 3, torch.bfloat16, seed=7)
+    g = conv_geom(x.shape, wt.shape, 1, 1)
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
+    res = torch.randn(n, cout, h, w, generator=torch.Generator().manual_seed(3)).bfloat16()
+    wp = be.pack_weights(wt.cuda(), 0, torch.bfloat16)
+    lib = _lib.load()
+    try:
+        lib.sr_set_option(b"SR_HALO_STACK", 0)
+        y_plain = be.conv_fwd(cl(x), wp, b.cuda(), cl(res), g, ACT_NONE, 0.0, impl=IMPL_HALO)
+        torch.cuda.synchronize()
+    finally:
+        lib.sr_set_option(b"SR_HALO_STACK", 1)
+    y = be.conv_fwd(cl(x), wp, b.cuda(), cl(res), g, ACT_NONE, 0.0, impl=IMPL_HALO)
+    y_ref = F.conv2d(x.float(), wt.bfloat16().float(), b, padding=1) + res.float()
+    assert rel(y, y_ref) < 4e-3 and rel(y_plain, y_ref) < 4e-3
+    assert rel(y, y_plain) < 3e-3       # same products, different fp32 summation order, one bf16 rounding each
 
 
 @pytest.mark.parametrize("r,cout", [(2, 256), (3, 576)])
