@@ -251,6 +251,37 @@ int sr_cgam_fwd(const float* x, const float* gamma, int N, int P, float* y32, vo
 int sr_cgam_bwd(const float* dy, const float* x, const float* A, const float* gamma, int N, int P, float* dx, float* dgamma,
                 int accumulate, void* workspace, void* stream);
 
+/* ---- Discriminator attention (CBAM after block 6: model/base_networks.py:366-457, model/sradsgan.py:476-499), csrc/cbam.cu ----
+ * A closed family of memory-bound primitives: the derivative of each is again a member, so the host wires them as autograd
+ * nodes that are differentiable to any order (the critic is differentiated twice by WGAN-GP, model/sradsgan.py:611-639).
+ * full = [N][P][C] NHWC activations in `dtype` (C a multiple of 64, 16-byte aligned); chan = [N][C] fp32; pix = [N][P] fp32;
+ * every optional operand may be NULL.  Deterministic (fixed summation order), nothing synchronises.
+ *
+ * sr_cbam_ew:  y = x*s*m + s2*(g0/C + g1*[c == cidx_p]) + (a + b*[p == idx_c]) + acc
+ *     x full, s chan (NULL = 1), m pix (NULL = 1): the gate application m * (s * x) (ChannelAttention :380-383, SpatialAttention :455-457)
+ *     s2 chan, g0 / g1 pix, cidx pix (int32): adjoint of the channel pooling torch.mean / torch.max(dim=1) (:447-450)
+ *     a / b chan, idx chan (int32): adjoint of AdaptiveAvgPool2d / AdaptiveMaxPool2d (:371-372); acc full (acc_dtype): added
+ * sr_cbam_red_c:  out_c = scale * sum_p a*b*m + sum_p a*g1*[c == cidx_p]      (a full, b full | NULL, m pix | NULL)
+ * sr_cbam_pool_hw: avg_c = mean_p x, mx_c = max_p x, idx_c = its first pixel
+ * sr_cbam_red_p:  out_p = scale * sum_c a*b*s                                  (a full, b full | NULL, s chan | NULL)
+ * sr_cbam_cpool:  q [N][2][P]: plane 0 = mean_c s_c*x_pc, plane 1 = max_c s_c*x_pc; cidx_p = its first channel
+ * sr_cbam_gather_hw: out_c = x[idx_c][c];   sr_cbam_gather_c: out_p = x[p][cidx_p] * s[cidx_p] (s NULL = 1)
+ * sr_small_gemm_nt: C[M][N] = sum_k A[m*lda_m + k*lda_k] * B[n*ldb_n + k*ldb_k] (fp32; the 256 <-> 16 shared MLP :374-378 and
+ *     its gradients as strided views; replaces cuBLAS gemv/gemm launches on [16][256] operands). */
+int sr_cbam_ew(const void* x, const float* s, const float* m, const float* s2, const float* g0, const float* g1, const int32_t* cidx,
+               const float* a, const float* b, const int32_t* idx, const void* acc, int acc_dtype, void* y, int dtype, int N, int P, int C,
+               void* stream);
+int sr_cbam_red_c(const void* a, int a_dtype, const void* b, int b_dtype, const float* m, const float* g1, const int32_t* cidx, float scale,
+                  int N, int P, int C, float* out, void* stream);
+int sr_cbam_pool_hw(const void* x, int dtype, int N, int P, int C, float* avg, float* mx, int32_t* idx, void* stream);
+int sr_cbam_red_p(const void* a, int a_dtype, const void* b, int b_dtype, const float* s, float scale, int N, int P, int C, float* out,
+                  void* stream);
+int sr_cbam_cpool(const void* x, int dtype, const float* s, int N, int P, int C, float* q, int32_t* cidx, void* stream);
+int sr_cbam_gather_hw(const void* x, int dtype, const int32_t* idx, int N, int P, int C, float* out, void* stream);
+int sr_cbam_gather_c(const void* x, int dtype, const float* s, const int32_t* cidx, int N, int P, int C, float* out, void* stream);
+int sr_small_gemm_nt(const float* A, int64_t lda_m, int64_t lda_k, const float* B, int64_t ldb_n, int64_t ldb_k, int M, int N, int K, float* C,
+                     void* stream);
+
 /* ---- loss reductions and elementwise glue of one iteration (csrc/losses.cu) --------------------------------------------
  * Reductions are deterministic (per-block partials, the last block adds them in a fixed order) and need a caller-owned
  * workspace of sr_reduce_workspace_bytes() bytes that was ZERO when first used (every launch re-arms it) and is used by one

@@ -307,6 +307,95 @@ class EmuBackend:
             return dx, None
         return dx, dg.reshape(1)
 
+    # -- discriminator attention primitives (csrc/cbam.cu) ------------------------------------------------
+    @staticmethod
+    def _pc(t):
+        """(N, C, H, W) -> [N, P, C] fp32"""
+        n, c, h, w = t.shape
+        return t.detach().float().permute(0, 2, 3, 1).reshape(n, h * w, c)
+
+    def cbam_ew(self, like, x=None, s=None, m=None, s2=None, g0=None, g1=None, cidx=None, a=None, b=None, idx=None, acc=None):
+        self.launches += 1
+        n, c, h, w = like.shape
+        P = h * w
+        y = torch.zeros(n, P, c)
+        f = lambda t, shape: None if t is None else t.detach().float().reshape(shape)
+        s, s2, a, b = (f(t, (n, 1, c)) for t in (s, s2, a, b))
+        m, g0, g1 = (f(t, (n, P, 1)) for t in (m, g0, g1))
+        if x is not None:
+            y = y + self._pc(x) * (s if s is not None else 1.0) * (m if m is not None else 1.0)
+        if s2 is not None:
+            wgt = torch.zeros(n, P, c)
+            if g0 is not None:
+                wgt = wgt + g0 / c
+            if g1 is not None:
+                wgt = wgt + g1 * torch.nn.functional.one_hot(cidx.long().reshape(n, P), c).float()
+            y = y + s2 * wgt
+        if a is not None:
+            y = y + a
+        if b is not None:
+            y = y + b * torch.nn.functional.one_hot(idx.long().reshape(n, c), P).float().permute(0, 2, 1)
+        if acc is not None:
+            y = y + self._pc(acc)
+        return y.reshape(n, h, w, c).permute(0, 3, 1, 2).to(like.dtype).contiguous(memory_format=torch.channels_last)
+
+    def cbam_red_c(self, a, b=None, m=None, scale=1.0, g1=None, cidx=None):
+        self.launches += 1
+        n, c, h, w = a.shape
+        P = h * w
+        v = self._pc(a)
+        if b is not None:
+            v = v * self._pc(b)
+        wgt = torch.full((n, P, 1), float(scale))
+        if m is not None:
+            wgt = wgt * m.detach().float().reshape(n, P, 1)
+        out = (v * wgt).sum(1)
+        if g1 is not None:
+            out = out + (v * g1.detach().float().reshape(n, P, 1) * torch.nn.functional.one_hot(cidx.long().reshape(n, P), c).float()).sum(1)
+        return out
+
+    def cbam_pool_hw(self, x):
+        self.launches += 1
+        v = self._pc(x)
+        mx, idx = v.max(dim=1)
+        # first maximum (torch.max over a dim does not promise it)
+        first = (v == mx.unsqueeze(1)).float().argmax(dim=1)
+        return torch.stack([v.mean(1), mx]), first.to(torch.int32)
+
+    def cbam_red_p(self, a, b=None, s=None, scale=1.0):
+        self.launches += 1
+        n, c, h, w = a.shape
+        v = self._pc(a)
+        if b is not None:
+            v = v * self._pc(b)
+        if s is not None:
+            v = v * s.detach().float().reshape(n, 1, c)
+        return v.sum(2) * scale
+
+    def cbam_cpool(self, x, s):
+        self.launches += 1
+        n, c, h, w = x.shape
+        v = self._pc(x) * s.detach().float().reshape(n, 1, c)
+        mx = v.max(dim=2)[0]
+        first = (v == mx.unsqueeze(2)).float().argmax(dim=2)
+        return torch.stack([v.mean(2), mx], dim=1).reshape(n, 2, h, w), first.to(torch.int32)
+
+    def cbam_gather_hw(self, x, idx):
+        self.launches += 1
+        return torch.gather(self._pc(x), 1, idx.long().unsqueeze(1)).squeeze(1)
+
+    def cbam_gather_c(self, x, s, cidx):
+        self.launches += 1
+        n, c, h, w = x.shape
+        v = self._pc(x)
+        if s is not None:
+            v = v * s.detach().float().reshape(n, 1, c)
+        return torch.gather(v, 2, cidx.long().reshape(n, -1, 1)).squeeze(2)
+
+    def small_gemm_nt(self, a, b):
+        self.launches += 1
+        return a.detach().float() @ b.detach().float().t()
+
     def colsum(self, x2d, want_sq=False):
         self.launches += 1
         f = x2d.float()

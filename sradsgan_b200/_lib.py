@@ -26,6 +26,7 @@ EXPORTS = [
     "sr_reduce_workspace_bytes", "sr_diff_mean_fwd", "sr_diff_mean_bwd", "sr_mean_fwd", "sr_mean_bwd", "sr_gp_penalty_fwd", "sr_gp_penalty_bwd",
     "sr_lerp_nhwc", "sr_nchw_to_nhwc", "sr_add_cast", "sr_cgam_workspace_bytes", "sr_cgam_fwd", "sr_cgam_bwd",
     "sr_la_chain_band_path", "sr_la_chain_pool_rows", "sr_la_chain_forward", "sr_la_chain_backward", "sr_conv_pool_rows",
+    "sr_cbam_ew", "sr_cbam_red_c", "sr_cbam_pool_hw", "sr_cbam_red_p", "sr_cbam_cpool", "sr_cbam_gather_hw", "sr_cbam_gather_c", "sr_small_gemm_nt",
 ]
 
 
@@ -118,6 +119,17 @@ def load():
     lib.sr_bn_act_bwd.argtypes = [vp, vp, i32, i64, i32, vp, f32, vp, vp, vp, vp]
     lib.sr_bn_act_bwd_bwd.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
     lib.sr_bn_act_bwd_bwd.restype = i32
+    lib.sr_cbam_ew.argtypes = [vp] * 11 + [i32, vp, i32, i32, i32, i32, vp]
+    lib.sr_cbam_red_c.argtypes = [vp, i32, vp, i32, vp, vp, vp, f32, i32, i32, i32, vp, vp]
+    lib.sr_cbam_pool_hw.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.sr_cbam_red_p.argtypes = [vp, i32, vp, i32, vp, f32, i32, i32, i32, vp, vp]
+    lib.sr_cbam_cpool.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp]
+    lib.sr_cbam_gather_hw.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
+    lib.sr_cbam_gather_c.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp]
+    lib.sr_small_gemm_nt.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp, vp]
+    for f in (lib.sr_cbam_ew, lib.sr_cbam_red_c, lib.sr_cbam_pool_hw, lib.sr_cbam_red_p, lib.sr_cbam_cpool, lib.sr_cbam_gather_hw,
+              lib.sr_cbam_gather_c, lib.sr_small_gemm_nt):
+        f.restype = i32
     if hasattr(lib, "sr_debug_umma_shift"):             # diagnostics build only (-DSR_WITH_PROBES)
         lib.sr_debug_umma_shift.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
         lib.sr_debug_umma_shift.restype = i32
@@ -761,6 +773,98 @@ class CudaBackend:
         return dx, (None if dgamma_into is not None else dg)
 
     # -- reductions / optimiser ----------------------------------------------------------------
+    # -- discriminator attention primitives (csrc/cbam.cu) ------------------------------------------------
+    # full: (N, C, H, W) NHWC in the compute dtype; chan: [N, C] fp32; pix: [N, H*W] fp32 (any shape with N*H*W elements)
+    @staticmethod
+    def _f32c(t):
+        return None if t is None else t.detach().float().contiguous()
+
+    def cbam_ew(self, like, x=None, s=None, m=None, s2=None, g0=None, g1=None, cidx=None, a=None, b=None, idx=None, acc=None):
+        n, c, h, w = like.shape
+        x = _nhwc(x.detach()) if x is not None else None
+        acc = _nhwc(acc.detach()) if acc is not None else None
+        s, m, s2, g0, g1, a, b = (self._f32c(t) for t in (s, m, s2, g0, g1, a, b))
+        y = torch.empty((n, c, h, w), dtype=like.dtype, device=like.device, memory_format=torch.channels_last)
+        if x is not None and x.dtype != y.dtype:
+            x = x.to(y.dtype)
+        nbytes = float(y.numel() * y.element_size()) * (1 + (x is not None) + (acc is not None))
+        self._timed_rec("d_attention", 0.0, nbytes, lambda: _check(self.lib.sr_cbam_ew(
+            _ptr(x), _ptr(s), _ptr(m), _ptr(s2), _ptr(g0), _ptr(g1), _ptr(cidx), _ptr(a), _ptr(b), _ptr(idx), _ptr(acc),
+            _dt(acc) if acc is not None else _dt(y), _ptr(y), _dt(y), n, h * w, c, _stream()), "cbam_ew"))
+        return y
+
+    def cbam_red_c(self, a, b=None, m=None, scale=1.0, g1=None, cidx=None):
+        a = _nhwc(a.detach())
+        b = _nhwc(b.detach()) if b is not None else None
+        n, c, h, w = a.shape
+        m, g1 = self._f32c(m), self._f32c(g1)
+        out = torch.empty((n, c), dtype=torch.float32, device=a.device)
+        self._timed_rec("d_attention", 0.0, float(a.numel() * a.element_size()) * (1 + (b is not None)), lambda: _check(self.lib.sr_cbam_red_c(
+            _ptr(a), _dt(a), _ptr(b), _dt(b) if b is not None else _dt(a), _ptr(m), _ptr(g1), _ptr(cidx), float(scale), n, h * w, c, _ptr(out),
+            _stream()), "cbam_red_c"))
+        return out
+
+    def cbam_pool_hw(self, x):
+        """-> (pooled [2, N, C] fp32: avg then max, idx [N, C] int32: first pixel of the maximum)"""
+        x = _nhwc(x.detach())
+        n, c, h, w = x.shape
+        pooled = torch.empty((2, n, c), dtype=torch.float32, device=x.device)
+        idx = torch.empty((n, c), dtype=torch.int32, device=x.device)
+        self._timed_rec("d_attention", 0.0, float(x.numel() * x.element_size()), lambda: _check(self.lib.sr_cbam_pool_hw(
+            _ptr(x), _dt(x), n, h * w, c, _ptr(pooled[0]), _ptr(pooled[1]), _ptr(idx), _stream()), "cbam_pool_hw"))
+        return pooled, idx
+
+    def cbam_red_p(self, a, b=None, s=None, scale=1.0):
+        a = _nhwc(a.detach())
+        b = _nhwc(b.detach()) if b is not None else None
+        n, c, h, w = a.shape
+        s = self._f32c(s)
+        out = torch.empty((n, h * w), dtype=torch.float32, device=a.device)
+        self._timed_rec("d_attention", 0.0, float(a.numel() * a.element_size()) * (1 + (b is not None)), lambda: _check(self.lib.sr_cbam_red_p(
+            _ptr(a), _dt(a), _ptr(b), _dt(b) if b is not None else _dt(a), _ptr(s), float(scale), n, h * w, c, _ptr(out), _stream()), "cbam_red_p"))
+        return out
+
+    def cbam_cpool(self, x, s):
+        """-> (q (N, 2, H, W) fp32 NCHW: mean / max over the channels of s*x, cidx [N, H*W] int32)"""
+        x = _nhwc(x.detach())
+        n, c, h, w = x.shape
+        s = self._f32c(s)
+        q = torch.empty((n, 2, h, w), dtype=torch.float32, device=x.device)
+        cidx = torch.empty((n, h * w), dtype=torch.int32, device=x.device)
+        self._timed_rec("d_attention", 0.0, float(x.numel() * x.element_size()), lambda: _check(self.lib.sr_cbam_cpool(
+            _ptr(x), _dt(x), _ptr(s), n, h * w, c, _ptr(q), _ptr(cidx), _stream()), "cbam_cpool"))
+        return q, cidx
+
+    def cbam_gather_hw(self, x, idx):
+        x = _nhwc(x.detach())
+        n, c, h, w = x.shape
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        _check(self.lib.sr_cbam_gather_hw(_ptr(x), _dt(x), _ptr(idx), n, h * w, c, _ptr(out), _stream()), "cbam_gather_hw")
+        return out
+
+    def cbam_gather_c(self, x, s, cidx):
+        x = _nhwc(x.detach())
+        n, c, h, w = x.shape
+        s = self._f32c(s)
+        out = torch.empty((n, h * w), dtype=torch.float32, device=x.device)
+        _check(self.lib.sr_cbam_gather_c(_ptr(x), _dt(x), _ptr(s), _ptr(cidx), n, h * w, c, _ptr(out), _stream()), "cbam_gather_c")
+        return out
+
+    def small_gemm_nt(self, a, b):
+        """a [M, K] @ b [N, K]^T -> [M, N] fp32; a, b: fp32 2-d tensors with ANY strides (views are not copied)"""
+        a, b = a.detach(), b.detach()
+        if a.dtype != torch.float32:
+            a = a.float()
+        if b.dtype != torch.float32:
+            b = b.float()
+        (m, k), (n, k2) = a.shape, b.shape
+        if k != k2:
+            raise ValueError("small_gemm_nt: inner dimensions differ")
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+        _check(self.lib.sr_small_gemm_nt(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), m, n, k, _ptr(out), _stream()),
+               "small_gemm_nt")
+        return out
+
     def colsum(self, x2d, want_sq=False):
         _require_cuda(x2d)
         x2d = x2d.contiguous()

@@ -102,6 +102,35 @@ int lerp_nhwc(const void*, int, int, const void*, int, const float*, long long, 
 int nchw_to_nhwc(const float*, long long, int, long long, void*, int, cudaStream_t);
 int add_cast(const void*, int, const void*, int, long long, void*, int, cudaStream_t);
 
+// cbam.cu
+struct CbamEw {
+    const void* x; const float* s; const float* m;
+    const float* s2; const float* g0; const float* g1; const int* cidx;
+    const float* a; const float* b; const int* idx;
+    const void* acc;
+    void* y;
+    int N, P, C;
+    float inv_c;
+};
+struct CbamRedC {
+    const void* a; const void* b; const float* m; const float* g1; const int* cidx;
+    float* out; float* out_max; int* out_idx;
+    int N, P, C;
+    float scale;
+};
+struct CbamRedP {
+    const void* a; const void* b; const float* s;
+    float* out; int* cidx;
+    long long NP; int P, C;
+    float scale;
+};
+int cbam_ew(const CbamEw&, int, int, cudaStream_t);
+int cbam_red_c(const CbamRedC&, int, int, bool, cudaStream_t);
+int cbam_red_p(const CbamRedP&, int, int, bool, cudaStream_t);
+int cbam_gather_hw(const void*, int, const int*, int, int, int, float*, cudaStream_t);
+int cbam_gather_c(const void*, int, const float*, const int*, int, int, int, float*, cudaStream_t);
+int small_gemm_nt(const float*, long long, long long, const float*, long long, long long, int, int, int, float*, cudaStream_t);
+
 // sgam.cu
 struct SgCommon {
     const void* a; const void* b; int ab_f32;
@@ -567,6 +596,80 @@ int sr_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, int64_t 
     SR_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0),
                "add_cast: 16-byte aligned buffers required");
     return add_cast(a, a_dtype, b, b ? b_dtype : a_dtype, n, out, out_dtype, (cudaStream_t)stream);
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+#define CBAM_DIMS_OK(N, P, C) ((N) > 0 && (P) > 0 && (C) >= 64 && (C) % 64 == 0 && (long long)(N) * (P) < (1ll << 31))
+
+int sr_cbam_ew(const void* x, const float* s, const float* m, const float* s2, const float* g0, const float* g1, const int32_t* cidx,
+               const float* a, const float* b, const int32_t* idx, const void* acc, int acc_dtype, void* y, int dtype, int N, int P, int C,
+               void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(y && dt_ok(dtype) && CBAM_DIMS_OK(N, P, C), "cbam_ew: bad arguments (C must be a multiple of 64)");
+    SR_REQUIRE(x || s2 || a || b || acc, "cbam_ew: no term given");
+    SR_REQUIRE((!g1 || cidx) && (!b || idx) && (!acc || dt_ok(acc_dtype)) && ((!g0 && !g1) || s2), "cbam_ew: inconsistent optional operands");
+    SR_REQUIRE(al16(x) && al16(s) && al16(s2) && al16(a) && al16(b) && al16(idx) && al16(acc) && al16(y), "cbam_ew: 16-byte aligned buffers required");
+    CbamEw q{x, s, m, s2, g0, g1, cidx, a, b, idx, acc, y, N, P, C, 1.f / (float)C};
+    return cbam_ew(q, dtype, acc ? acc_dtype : dtype, (cudaStream_t)stream);
+}
+
+int sr_cbam_red_c(const void* a, int a_dtype, const void* b, int b_dtype, const float* m, const float* g1, const int32_t* cidx, float scale,
+                  int N, int P, int C, float* out, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && out && dt_ok(a_dtype) && (!b || dt_ok(b_dtype)) && (!g1 || cidx) && CBAM_DIMS_OK(N, P, C), "cbam_red_c: bad arguments");
+    SR_REQUIRE(al16(a) && al16(b), "cbam_red_c: 16-byte aligned buffers required");
+    CbamRedC q{a, b, m, g1, cidx, out, nullptr, nullptr, N, P, C, scale};
+    return cbam_red_c(q, a_dtype, b ? b_dtype : a_dtype, false, (cudaStream_t)stream);
+}
+
+int sr_cbam_pool_hw(const void* x, int dtype, int N, int P, int C, float* avg, float* mx, int32_t* idx, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && avg && mx && idx && dt_ok(dtype) && CBAM_DIMS_OK(N, P, C) && al16(x), "cbam_pool_hw: bad arguments");
+    CbamRedC q{x, nullptr, nullptr, nullptr, nullptr, avg, mx, idx, N, P, C, 1.f / (float)P};
+    return cbam_red_c(q, dtype, dtype, true, (cudaStream_t)stream);
+}
+
+int sr_cbam_red_p(const void* a, int a_dtype, const void* b, int b_dtype, const float* s, float scale, int N, int P, int C, float* out,
+                  void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(a && out && dt_ok(a_dtype) && (!b || dt_ok(b_dtype)) && CBAM_DIMS_OK(N, P, C), "cbam_red_p: bad arguments");
+    SR_REQUIRE(al16(a) && al16(b) && al16(s), "cbam_red_p: 16-byte aligned buffers required");
+    CbamRedP q{a, b, s, out, nullptr, (long long)N * P, P, C, scale};
+    return cbam_red_p(q, a_dtype, b ? b_dtype : a_dtype, false, (cudaStream_t)stream);
+}
+
+int sr_cbam_cpool(const void* x, int dtype, const float* s, int N, int P, int C, float* q2, int32_t* cidx, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && q2 && cidx && dt_ok(dtype) && CBAM_DIMS_OK(N, P, C) && al16(x) && al16(s), "cbam_cpool: bad arguments");
+    CbamRedP q{x, nullptr, s, q2, cidx, (long long)N * P, P, C, 1.f / (float)C};
+    return cbam_red_p(q, dtype, dtype, true, (cudaStream_t)stream);
+}
+
+int sr_cbam_gather_hw(const void* x, int dtype, const int32_t* idx, int N, int P, int C, float* out, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && idx && out && dt_ok(dtype) && CBAM_DIMS_OK(N, P, C), "cbam_gather_hw: bad arguments");
+    return cbam_gather_hw(x, dtype, idx, N, P, C, out, (cudaStream_t)stream);
+}
+
+int sr_cbam_gather_c(const void* x, int dtype, const float* s, const int32_t* cidx, int N, int P, int C, float* out, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(x && cidx && out && dt_ok(dtype) && CBAM_DIMS_OK(N, P, C), "cbam_gather_c: bad arguments");
+    return cbam_gather_c(x, dtype, s, cidx, N, P, C, out, (cudaStream_t)stream);
+}
+
+int sr_small_gemm_nt(const float* A, int64_t lda_m, int64_t lda_k, const float* B, int64_t ldb_n, int64_t ldb_k, int M, int N, int K, float* C,
+                     void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && (long long)M * N <= (1 << 22), "small_gemm_nt: bad arguments");
+    return small_gemm_nt(A, lda_m, lda_k, B, ldb_n, ldb_k, M, N, K, C, (cudaStream_t)stream);
 }
 
 #ifdef SR_WITH_PROBES

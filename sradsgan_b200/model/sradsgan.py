@@ -468,6 +468,9 @@ class Discriminator(nn.Module):
             return ops.bn_leaky_relu(m(x), nxt, nxt2.negative_slope), i + 3             # conv -> fused BN+LReLU
         if isinstance(m, Conv2d) and isinstance(nxt, LeakyReLU):
             return ops.conv2d_act(x, m.weight, m.bias, m.stride, m.padding, ACT_LRELU, nxt.negative_slope), i + 2   # conv + LReLU epilogue
+        if (isinstance(m, ChannelAttention) and isinstance(nxt, SpatialAttention) and m.pool_mode == 'Avg|Max' and nxt.pool_mode == 'Avg|Max'
+                and x.shape[1] % 64 == 0 and ops.config.fused_d_attention):
+            return ops.cbam_attention(x, m.fc1.weight, m.fc2.weight, nxt.conv1), i + 2                              # csrc/cbam.cu primitives
         return m(x), i + 1
 
 

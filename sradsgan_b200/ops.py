@@ -21,6 +21,7 @@ class Config:
     double_backward = False            # force the any-order differentiable (unfused) discriminator path
     input_grad_only = False            # backward passes skip parameter gradients (see input_grad_only())
     direct_grad = True                 # first-order backward adds weight gradients straight into FlatAdam's flat buffer
+    fused_d_attention = True           # discriminator CBAM through the csrc/cbam.cu primitives (False: module-by-module ATen path)
 
 
 config = Config()
@@ -782,3 +783,213 @@ def cgam_attention(x, gamma):
         y32._sr_lowp = y16
         return y32
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Discriminator attention (CBAM after block 6; csrc/cbam.cu): a closed family of primitives whose backward passes are
+# each other, so the critic stays differentiable to any order (WGAN-GP differentiates it twice) while every pass over
+# the [N, C, H, W] activation is one custom kernel.   full = (N, C, H, W) NHWC; chan = [N, C] fp32; pix = [N, H*W] fp32
+# ----------------------------------------------------------------------------------------------
+def _need(ctx, i):
+    return ctx.needs_input_grad[i]
+
+
+class Gate3(Function):
+    """y = m_p * s_c * x_pc  (x full, s chan, m pix)"""
+
+    @staticmethod
+    def forward(ctx, x, s, m):
+        ctx.save_for_backward(x, s, m)
+        return _lib.backend().cbam_ew(x, x=x, s=s, m=m)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s, m = ctx.saved_tensors
+        return (Gate3.apply(g, s, m) if _need(ctx, 0) else None,
+                RedC.apply(g, x, m) if _need(ctx, 1) else None,
+                RedP.apply(g, x, s) if _need(ctx, 2) else None)
+
+
+class RedC(Function):
+    """out_c = sum_p a_pc * b_pc * m_p  (a, b full, m pix) -> chan"""
+
+    @staticmethod
+    def forward(ctx, a, b, m):
+        ctx.save_for_backward(a, b, m)
+        return _lib.backend().cbam_red_c(a, b, m)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, m = ctx.saved_tensors
+        return (Gate3.apply(b, g, m) if _need(ctx, 0) else None,
+                Gate3.apply(a, g, m) if _need(ctx, 1) else None,
+                RedP.apply(a, b, g) if _need(ctx, 2) else None)
+
+
+class RedP(Function):
+    """out_p = sum_c a_pc * b_pc * s_c  (a, b full, s chan) -> pix"""
+
+    @staticmethod
+    def forward(ctx, a, b, s):
+        ctx.save_for_backward(a, b, s)
+        return _lib.backend().cbam_red_p(a, b, s)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, s = ctx.saved_tensors
+        g = g.reshape(g.shape[0], -1)
+        return (Gate3.apply(b, s, g) if _need(ctx, 0) else None,
+                Gate3.apply(a, s, g) if _need(ctx, 1) else None,
+                RedC.apply(a, b, g) if _need(ctx, 2) else None)
+
+
+class PoolHW(Function):
+    """AdaptiveAvgPool2d(1) and AdaptiveMaxPool2d(1) of x in one pass -> [2, N, C] fp32 (avg, max); the arg-max pixels are saved
+    (reference model/base_networks.py:371-372)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        pooled, idx = _lib.backend().cbam_pool_hw(x)
+        ctx.idx = idx
+        ctx.like = x
+        ctx.hw = x.shape[2] * x.shape[3]
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        return BcastScatterHW.apply(g[0] / ctx.hw, g[1], ctx.idx, ctx.like)
+
+
+class PoolLinHW(Function):
+    """[sum_p x_pc, x[idx_c][c]] -> [2, N, C]: PoolHW with the arg-max pixels given (linear in x)"""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        be = _lib.backend()
+        ctx.idx = idx
+        ctx.like = x
+        return torch.stack([be.cbam_red_c(x), be.cbam_gather_hw(x, idx)])
+
+    @staticmethod
+    def backward(ctx, g):
+        return BcastScatterHW.apply(g[0], g[1], ctx.idx, ctx.like), None
+
+
+class BcastScatterHW(Function):
+    """y_pc = a_c + b_c * [p == idx_c] -> full (the adjoint of PoolLinHW)"""
+
+    @staticmethod
+    def forward(ctx, a, b, idx, like):
+        ctx.idx = idx
+        return _lib.backend().cbam_ew(like, a=a, b=b, idx=idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        r = PoolLinHW.apply(g, ctx.idx)
+        return r[0], r[1], None, None
+
+
+class CPool(Function):
+    """q = [mean_c s_c x_pc, max_c s_c x_pc] -> (N, 2, H, W) fp32 NCHW, the input of SpatialAttention's 7x7 convolution
+    (reference model/base_networks.py:447-450 applied to ChannelAttention's output s*x without materialising it)"""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        q, cidx = _lib.backend().cbam_cpool(x, s)
+        ctx.cidx = cidx
+        ctx.save_for_backward(x, s)
+        return q
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        n = g.shape[0]
+        g0, g1 = g[:, 0].reshape(n, -1), g[:, 1].reshape(n, -1)
+        return (CPoolBx.apply(g0, g1, s, ctx.cidx, x) if _need(ctx, 0) else None,
+                CPoolBs.apply(g0, g1, x, ctx.cidx) if _need(ctx, 1) else None)
+
+
+class CPoolLin(Function):
+    """CPool with the arg-max channels given (bilinear in x and s)"""
+
+    @staticmethod
+    def forward(ctx, x, s, cidx):
+        be = _lib.backend()
+        ctx.cidx = cidx
+        ctx.save_for_backward(x, s)
+        n, c, h, w = x.shape
+        return torch.stack([be.cbam_red_p(x, None, s, 1.0 / c), be.cbam_gather_c(x, s, cidx)], dim=1).view(n, 2, h, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        n = g.shape[0]
+        g0, g1 = g[:, 0].reshape(n, -1), g[:, 1].reshape(n, -1)
+        return (CPoolBx.apply(g0, g1, s, ctx.cidx, x) if _need(ctx, 0) else None,
+                CPoolBs.apply(g0, g1, x, ctx.cidx) if _need(ctx, 1) else None, None)
+
+
+class CPoolBx(Function):
+    """y_pc = s_c * (g0_p / C + g1_p * [c == cidx_p]) -> full (the x-adjoint of CPoolLin)"""
+
+    @staticmethod
+    def forward(ctx, g0, g1, s, cidx, like):
+        ctx.cidx = cidx
+        ctx.save_for_backward(g0, g1, s)
+        return _lib.backend().cbam_ew(like, s2=s, g0=g0, g1=g1, cidx=cidx)
+
+    @staticmethod
+    def backward(ctx, G):
+        g0, g1, s = ctx.saved_tensors
+        n = G.shape[0]
+        gg = CPoolLin.apply(G, s, ctx.cidx) if (_need(ctx, 0) or _need(ctx, 1)) else None
+        return (gg[:, 0].reshape(n, -1) if gg is not None else None, gg[:, 1].reshape(n, -1) if gg is not None else None,
+                CPoolBs.apply(g0, g1, G, ctx.cidx) if _need(ctx, 2) else None, None, None)
+
+
+class CPoolBs(Function):
+    """out_c = sum_p x_pc * (g0_p / C + g1_p * [c == cidx_p]) -> chan (the s-adjoint of CPoolLin)"""
+
+    @staticmethod
+    def forward(ctx, g0, g1, x, cidx):
+        ctx.cidx = cidx
+        ctx.save_for_backward(g0, g1, x)
+        return _lib.backend().cbam_red_c(x, None, g0, 1.0 / x.shape[1], g1, cidx)
+
+    @staticmethod
+    def backward(ctx, G):
+        g0, g1, x = ctx.saved_tensors
+        n = G.shape[0]
+        gg = CPoolLin.apply(x, G, ctx.cidx) if (_need(ctx, 0) or _need(ctx, 1)) else None
+        return (gg[:, 0].reshape(n, -1) if gg is not None else None, gg[:, 1].reshape(n, -1) if gg is not None else None,
+                CPoolBx.apply(g0, g1, G, ctx.cidx, x) if _need(ctx, 2) else None, None)
+
+
+class SmallMatmulNT(Function):
+    """a [M, K] @ b [N, K]^T in fp32 (the 256 <-> 16 shared MLP of ChannelAttention; strided views, no cuBLAS launch)"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return _lib.backend().small_gemm_nt(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return (SmallMatmulNT.apply(g, b.t()) if _need(ctx, 0) else None,
+                SmallMatmulNT.apply(g.t(), a.t()) if _need(ctx, 1) else None)
+
+
+def cbam_attention(x, fc1_w, fc2_w, conv7):
+    """ChannelAttention(C) followed by SpatialAttention (reference model/base_networks.py:366-383, :441-457) on the compute-dtype
+    activation x (N, C, H, W): three passes over x (pooling, channel pooling of s*x, gate application), everything else on
+    [N, C] / [N, 2, H, W] tensors."""
+    n, c, h, w = x.shape
+    cr = fc1_w.shape[0]
+    pooled = PoolHW.apply(x)                                                   # [2, N, C]: avg, max
+    hid = torch.relu(SmallMatmulNT.apply(pooled.view(2 * n, c), fc1_w.view(cr, c)))
+    o = SmallMatmulNT.apply(hid, fc2_w.view(c, cr)).view(2, n, c)
+    s = torch.sigmoid(o[0] + o[1])                                             # [N, C]
+    q = CPool.apply(x, s)                                                      # (N, 2, H, W) fp32
+    m = torch.sigmoid(conv7(q).float()).view(n, h * w)
+    return Gate3.apply(x, s, m)
