@@ -23,9 +23,9 @@ def world_size():
 
 
 def all_reduce_flat(buf, group=None):
+    """sum all-reduce of a flat gradient buffer on the current stream (no-op for one process)"""
     from . import ops
     ops.wgrad_join()
-    """sum all-reduce of a flat gradient buffer on the current stream (no-op for one process)"""
     if is_dist():
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
 

@@ -231,9 +231,10 @@ class SRADSGAN(object):
     def graphed_step(self, imgs_lr, imgs_hr):
         """train_step captured ONCE into CUDA graphs (~6k kernel launches -> a few cudaGraphLaunch) and replayed;
         inputs / the GP interpolation factors are staged into static device buffers, the Adam step counters live
-        on the device.  One process: a single graph.  Data parallel: three graph segments (G phase | Adam_G + D
-        phase | Adam_D) with the two NCCL gradient all-reduces issued BETWEEN the replays — collectives are never
-        captured.  Re-capture happens when the input shape or a learning rate changes."""
+        on the device.  One process: a single graph.  Data parallel: four graph segments (G phase | Adam_G | D phase |
+        Adam_D) with the two NCCL gradient all-reduces issued BETWEEN the replays (collectives are never captured) and the
+        generator's all-reduce + Adam running next to the D phase (_replay_dp).  Re-capture happens when the input shape or
+        a learning rate changes."""
         key = (tuple(imgs_lr.shape), tuple(imgs_hr.shape), self.optimizer_G.param_groups[0]["lr"], self.optimizer_D.param_groups[0]["lr"])
         if self._graph is None or self._graph["key"] != key:
             self._capture(imgs_lr, imgs_hr, key)
@@ -261,12 +262,27 @@ class SRADSGAN(object):
         return g["out"]
 
     def _replay_dp(self, g):
-        """data parallel: G phase | all-reduce(G) | Adam_G + D phase | all-reduce(D) | Adam_D — collectives are never captured"""
-        g["graphs"][0].replay()
-        dp.all_reduce_flat(self.optimizer_G.flat_grad)
-        g["graphs"][1].replay()
+        """data parallel: G phase | all-reduce(G) + Adam_G on the communication stream NEXT TO the D phase (which reads neither
+        the generator's gradients nor its updated weights: gen_hr is detached, reference :857-861) | all-reduce(D) | Adam_D.
+        Collectives are never captured; the main stream joins the communication stream before the next G phase.
+        SR_DP_OVERLAP=0 restores the serial order (G phase | all-reduce | Adam_G + D phase | all-reduce | Adam_D)."""
+        g_phase, adam_g, d_phase, adam_d = g["graphs"]
+        main = torch.cuda.current_stream()
+        comm = g.get("comm_stream")
+        g_phase.replay()
+        if comm is not None:
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                dp.all_reduce_flat(self.optimizer_G.flat_grad)
+                adam_g.replay()
+        else:
+            dp.all_reduce_flat(self.optimizer_G.flat_grad)
+            adam_g.replay()
+        d_phase.replay()
         dp.all_reduce_flat(self.optimizer_D.flat_grad)
-        g["graphs"][2].replay()
+        adam_d.replay()
+        if comm is not None:
+            main.wait_stream(comm)
 
     def _capture(self, imgs_lr, imgs_hr, key):
         dev = self.device                 # the batch may still be in (pinned) host memory: the static inputs live on the device
@@ -293,22 +309,24 @@ class SRADSGAN(object):
             if os.environ.get("SR_PACK_PLAN", "1") == "1":
                 self._pack_plans = [ops.PackPlan(self.optimizer_G.params), ops.PackPlan(self.optimizer_D.params)]
             n0 = _lib.backend().launch_count()
-            if world == 1:
+            if world == 1 and os.environ.get("SR_DP_FORCE_SEGMENTS", "0") != "1":      # (the knob: scripts/dp_overlap_check.py on one GPU)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     st["out"] = self.train_step(st["lr"], st["hr"])
                 graphs = [graph]
             else:
-                g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                g1, ga, g2, g3 = (torch.cuda.CUDAGraph() for _ in range(4))
                 with torch.cuda.graph(g1, capture_error_mode="thread_local"):
                     out = self._g_phase(st["lr"], st["hr"])
-                with torch.cuda.graph(g2, pool=g1.pool(), capture_error_mode="thread_local"):
+                with torch.cuda.graph(ga, pool=g1.pool(), capture_error_mode="thread_local"):
                     self.optimizer_G.step(grad_scale=1.0 / world)
+                with torch.cuda.graph(g2, pool=g1.pool(), capture_error_mode="thread_local"):
                     out.update(self._d_phase(out["_hr_nhwc"], out["gen_hr"]))
                 with torch.cuda.graph(g3, pool=g1.pool(), capture_error_mode="thread_local"):
                     self.optimizer_D.step(grad_scale=1.0 / world)
                 st["out"] = out
-                graphs = [g1, g2, g3]
+                graphs = [g1, ga, g2, g3]
+                st["comm_stream"] = torch.cuda.Stream() if os.environ.get("SR_DP_OVERLAP", "1") == "1" else None
             st["launches"] = _lib.backend().launch_count() - n0     # library kernels per replay
             torch.cuda.synchronize()
         finally:
