@@ -251,6 +251,14 @@ int sr_cgam_fwd(const float* x, const float* gamma, int N, int P, float* y32, vo
 int sr_cgam_bwd(const float* dy, const float* x, const float* A, const float* gamma, int N, int P, float* dx, float* dgamma,
                 int accumulate, void* workspace, void* stream);
 
+/* One separable pass of PIL's 8-bit resampling (`Image.resize(size, Image.BICUBIC)` in the reference's datasets,
+ * data/dataset.py:403-438; Pillow libImaging/Resample.c): out = clip8((2^21 + sum_k in[lo_o + k] * coeffs[o][k]) >> 22), int32,
+ * bit-exact.  in [planes][H][W] uint8; axis 0: along W -> out [planes][H][out_size]; axis 1: along H -> out [planes][out_size][W];
+ * bounds [out_size][2] = (first input index, tap count <= ksize), coeffs [out_size][ksize] with 22 fractional bits — both built by
+ * the caller exactly like precompute_coeffs / normalize_coeffs_8bpc (sradsgan_b200/data.py: pil_coeffs). */
+int sr_resample_u8(const uint8_t* in, int planes, int H, int W, uint8_t* out, int out_size, int axis, const int32_t* bounds,
+                   const int32_t* coeffs, int ksize, void* stream);
+
 /* ---- Discriminator attention (CBAM after block 6: model/base_networks.py:366-457, model/sradsgan.py:476-499), csrc/cbam.cu ----
  * A closed family of memory-bound primitives: the derivative of each is again a member, so the host wires them as autograd
  * nodes that are differentiable to any order (the critic is differentiated twice by WGAN-GP, model/sradsgan.py:611-639).

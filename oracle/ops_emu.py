@@ -396,6 +396,18 @@ class EmuBackend:
         self.launches += 1
         return a.detach().float() @ b.detach().float().t()
 
+    def resample_u8(self, img, out_size, axis, bounds, coeffs):
+        """integer restatement of Pillow's ImagingResampleHorizontal_8bpc / Vertical_8bpc (libImaging/Resample.c)"""
+        self.launches += 1
+        x = img.to(torch.int32)
+        if axis:
+            x = x.transpose(-1, -2)
+        ks = coeffs.shape[1]
+        idx = (bounds[:, :1].long() + torch.arange(ks)[None]).clamp_(max=x.shape[-1] - 1)          # taps past the count have coefficient 0
+        acc = (x[..., idx] * coeffs.to(torch.int32)).sum(-1, dtype=torch.int32) + (1 << 21)
+        out = (acc >> 22).clamp_(0, 255).to(torch.uint8)
+        return (out.transpose(-1, -2) if axis else out).contiguous()
+
     def colsum(self, x2d, want_sq=False):
         self.launches += 1
         f = x2d.float()

@@ -27,6 +27,7 @@ EXPORTS = [
     "sr_lerp_nhwc", "sr_nchw_to_nhwc", "sr_add_cast", "sr_cgam_workspace_bytes", "sr_cgam_fwd", "sr_cgam_bwd",
     "sr_la_chain_band_path", "sr_la_chain_pool_rows", "sr_la_chain_forward", "sr_la_chain_backward", "sr_conv_pool_rows",
     "sr_cbam_ew", "sr_cbam_red_c", "sr_cbam_pool_hw", "sr_cbam_red_p", "sr_cbam_cpool", "sr_cbam_gather_hw", "sr_cbam_gather_c", "sr_small_gemm_nt",
+    "sr_resample_u8",
 ]
 
 
@@ -119,6 +120,8 @@ def load():
     lib.sr_bn_act_bwd.argtypes = [vp, vp, i32, i64, i32, vp, f32, vp, vp, vp, vp]
     lib.sr_bn_act_bwd_bwd.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
     lib.sr_bn_act_bwd_bwd.restype = i32
+    lib.sr_resample_u8.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp]
+    lib.sr_resample_u8.restype = i32
     lib.sr_cbam_ew.argtypes = [vp] * 11 + [i32, vp, i32, i32, i32, i32, vp]
     lib.sr_cbam_red_c.argtypes = [vp, i32, vp, i32, vp, vp, vp, f32, i32, i32, i32, vp, vp]
     lib.sr_cbam_pool_hw.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
@@ -863,6 +866,19 @@ class CudaBackend:
         out = torch.empty((m, n), dtype=torch.float32, device=a.device)
         _check(self.lib.sr_small_gemm_nt(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), m, n, k, _ptr(out), _stream()),
                "small_gemm_nt")
+        return out
+
+    def resample_u8(self, img, out_size, axis, bounds, coeffs):
+        """one pass of PIL's 8-bit resampling: img (..., H, W) uint8 contiguous -> resampled along W (axis 0) or H (axis 1);
+        bounds [out, 2] / coeffs [out, ksize] int32 on the device (data.pil_coeffs)"""
+        _require_cuda(img, bounds, coeffs)
+        img = img.contiguous()
+        h, w = img.shape[-2:]
+        planes = img.numel() // (h * w)
+        shape = tuple(img.shape[:-2]) + ((out_size, w) if axis else (h, out_size))
+        out = torch.empty(shape, dtype=torch.uint8, device=img.device)
+        _check(self.lib.sr_resample_u8(_ptr(img), planes, h, w, _ptr(out), int(out_size), int(axis), _ptr(bounds), _ptr(coeffs),
+                                       int(coeffs.shape[1]), _stream()), "resample_u8")
         return out
 
     def colsum(self, x2d, want_sq=False):

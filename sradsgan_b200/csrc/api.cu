@@ -102,6 +102,8 @@ int lerp_nhwc(const void*, int, int, const void*, int, const float*, long long, 
 int nchw_to_nhwc(const float*, long long, int, long long, void*, int, cudaStream_t);
 int add_cast(const void*, int, const void*, int, long long, void*, int, cudaStream_t);
 
+int resample_u8(const unsigned char*, int, int, int, unsigned char*, int, int, const int*, const int*, int, cudaStream_t);
+
 // cbam.cu
 struct CbamEw {
     const void* x; const float* s; const float* m;
@@ -596,6 +598,15 @@ int sr_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, int64_t 
     SR_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0),
                "add_cast: 16-byte aligned buffers required");
     return add_cast(a, a_dtype, b, b ? b_dtype : a_dtype, n, out, out_dtype, (cudaStream_t)stream);
+}
+
+int sr_resample_u8(const uint8_t* in, int planes, int H, int W, uint8_t* out, int out_size, int axis, const int32_t* bounds,
+                   const int32_t* coeffs, int ksize, void* stream) {
+    int rc = arch_check();
+    if (rc) return rc;
+    SR_REQUIRE(in && out && bounds && coeffs && planes > 0 && H > 0 && W > 0 && out_size > 0 && ksize > 0 && (axis == 0 || axis == 1),
+               "resample_u8: bad arguments");
+    return resample_u8(in, planes, H, W, out, out_size, axis, bounds, coeffs, ksize, (cudaStream_t)stream);
 }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -374,4 +374,42 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
     return check_launch("adam_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// One separable pass of PIL's 8-bit resampling (Pillow src/libImaging/Resample.c, ImagingResampleHorizontal_8bpc /
+// ImagingResampleVertical_8bpc — what `Image.resize(..., Image.BICUBIC)` of the reference's datasets runs,
+// data/dataset.py:403-438): out = clip8((2^21 + sum_k in[lo + k] * coeff[k]) >> 22) with the caller's fixed-point coefficient
+// table (22 fractional bits, built on the host exactly like precompute_coeffs / normalize_coeffs_8bpc).  int32 arithmetic,
+// arithmetic shift: bit-exact.  in: [planes][H][W] uint8; axis 0 resamples along W (out [planes][H][out_size]), axis 1 along H.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resample_u8_kernel(const unsigned char* __restrict__ in, int planes, int H, int W, unsigned char* __restrict__ out, int out_size, int axis,
+                   const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+    const int oh = axis ? out_size : H, ow = axis ? W : out_size;
+    const long long total = (long long)planes * oh * ow;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % ow);
+        const long long r = i / ow;
+        const int y = (int)(r % oh), pl = (int)(r / oh);
+        const int o = axis ? y : x;
+        const int lo = bounds[2 * o], n = bounds[2 * o + 1];
+        const int* k = kk + (long long)o * ksize;
+        const unsigned char* src = in + (long long)pl * H * W + (axis ? (long long)lo * W + x : (long long)y * W + lo);
+        const int stride = axis ? W : 1;
+        int ss = 1 << 21;
+        for (int t = 0; t < n; ++t) ss += (int)src[(long long)t * stride] * k[t];
+        ss >>= 22;
+        out[i] = (unsigned char)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+    }
+}
+
+int resample_u8(const unsigned char* in, int planes, int H, int W, unsigned char* out, int out_size, int axis, const int* bounds,
+                const int* kk, int ksize, cudaStream_t st) {
+    const long long total = (long long)planes * (axis ? out_size : H) * (axis ? W : out_size);
+    long long grid = cdiv(total, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    resample_u8_kernel<<<(int)grid, 256, 0, st>>>(in, planes, H, W, out, out_size, axis, bounds, kk, ksize);
+    count_launch();
+    return check_launch("resample_u8_kernel");
+}
+
 }  // namespace sr

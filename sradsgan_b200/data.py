@@ -58,33 +58,100 @@ class FolderSRDataset(Dataset):
 # ----------------------------------------------------------------------------------------------
 # device-side input pipeline
 # ----------------------------------------------------------------------------------------------
+_PIL_PRECISION_BITS = 32 - 8 - 2
+_coeff_cache = {}
+
+
+def pil_coeffs(in_size, out_size):
+    """Fixed-point BICUBIC coefficient table of one resampling pass, built like Pillow's precompute_coeffs +
+    normalize_coeffs_8bpc (src/libImaging/Resample.c; Keys cubic a = -0.5, support 2 scaled by the shrink factor; IEEE double
+    arithmetic in the same operation order, truncating casts) -> (bounds int32 [out, 2] = (first tap, tap count),
+    coeffs int32 [out, ksize] with 22 fractional bits)."""
+    key = (in_size, out_size)
+    if key in _coeff_cache:
+        return _coeff_cache[key]
+    import math
+    import numpy as np
+    a = -0.5
+
+    def cubic(x):
+        x = abs(x)
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [cubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x in range(xmax):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(-0.5 + v * (1 << _PIL_PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PIL_PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    out = (torch.from_numpy(bounds), torch.from_numpy(kk))
+    _coeff_cache[key] = out
+    return out
+
+
+_dev_coeffs = {}
+
+
+def _resample_pass(img, out_size, axis):
+    """one pass of PIL's 8-bit resampling along W (axis 0) or H (axis 1) of a (..., H, W) uint8 tensor — on a CUDA tensor the
+    library kernel (sr_resample_u8), on a host tensor the same integer arithmetic in torch (the reference resamples on the host too)"""
+    in_size = img.shape[-2] if axis else img.shape[-1]
+    bounds, kk = pil_coeffs(in_size, out_size)
+    if img.is_cuda:
+        from . import _lib
+        key = (in_size, out_size, img.device)
+        if key not in _dev_coeffs:
+            _dev_coeffs[key] = (bounds.to(img.device), kk.to(img.device))
+        return _lib.backend().resample_u8(img, out_size, axis, *_dev_coeffs[key])
+    x = img.to(torch.int32)
+    if axis:
+        x = x.transpose(-1, -2)
+    idx = (bounds[:, :1].long() + torch.arange(kk.shape[1])[None]).clamp_(max=x.shape[-1] - 1)
+    acc = (x[..., idx] * kk).sum(-1, dtype=torch.int32) + (1 << (_PIL_PRECISION_BITS - 1))
+    out = (acc >> _PIL_PRECISION_BITS).clamp_(0, 255).to(torch.uint8)
+    return (out.transpose(-1, -2) if axis else out).contiguous()
+
+
 def pil_bicubic(img_u8, out_h, out_w):
-    """`PIL.Image.resize((out_w, out_h), Image.BICUBIC)` of uint8-valued images, on the tensor's device.
-    img_u8: (N, C, H, W) float tensor holding integer values 0..255.  PIL resamples 8-bit images in two separable
-    antialiased passes (horizontal, then vertical; Keys cubic a = -0.5 with its support scaled by the shrink factor) and
-    rounds + clips to uint8 after EACH pass — reproduced here with two 1-D `interpolate(..., antialias=True)` calls.
-    Parity (tests/test_input_pipeline_cpu.py): identical on >99.8 % of the pixels (bit-exact on most images); the rest differ
-    by 1 grey level (2 after a down + up round trip) — PIL evaluates the filter with fixed-point coefficients."""
+    """`PIL.Image.resize((out_w, out_h), Image.BICUBIC)` of 8-bit images, BIT-EXACT, on the tensor's device.
+    img_u8: (N, C, H, W) uint8 tensor, or a float tensor holding the integer values 0..255 (the result has the input's dtype).
+    PIL resamples 8-bit images in two separable passes (horizontal, then vertical) with fixed-point coefficients (22 fractional
+    bits), rounding and clipping to uint8 after EACH pass (libImaging/Resample.c) — reproduced with the same integer arithmetic
+    (`pil_coeffs`, `sr_resample_u8`).  Parity: tests/test_input_pipeline_cpu.py (every pixel equal to PIL's)."""
     h, w = img_u8.shape[-2:]
-    y = img_u8.float()
+    y = img_u8 if img_u8.dtype == torch.uint8 else img_u8.to(torch.uint8)
     if w != out_w:
-        y = F.interpolate(y, size=(h, out_w), mode="bicubic", antialias=True, align_corners=False)
-        y = torch.floor(y + 0.5).clamp_(0, 255)
+        y = _resample_pass(y, out_w, 0)
     if h != out_h:
-        y = F.interpolate(y, size=(out_h, out_w), mode="bicubic", antialias=True, align_corners=False)
-        y = torch.floor(y + 0.5).clamp_(0, 255)
-    return y
+        y = _resample_pass(y, out_h, 1)
+    return y if img_u8.dtype == torch.uint8 else y.to(img_u8.dtype)
 
 
 def synthesize_lr_bc(hr_u8, scale):
     """(lr, hr, bc) in [0, 1] float, exactly what the reference's dataset returns per image (data/dataset.py:403-438):
     LR = PIL-bicubic(HR), BC = PIL-bicubic(LR back to the HR size), all `to_tensor`-scaled (/255).  hr_u8: (N, 3, H, W) uint8."""
-    hr = hr_u8.float()
-    h, w = hr.shape[-2:]
-    lr = pil_bicubic(hr, h // scale, w // scale)
+    h, w = hr_u8.shape[-2:]
+    lr = pil_bicubic(hr_u8, h // scale, w // scale)
     bc = pil_bicubic(lr, h, w)
-    d = hr.new_full((1,), 255.0)      # tensor / tensor: IEEE division like `to_tensor` on the host (a Python-scalar divisor is turned
-    return lr / d, hr / d, bc / d      # into a multiplication by the reciprocal on CUDA: 1 ulp off)
+    d = torch.full((1,), 255.0, device=hr_u8.device)      # tensor / tensor: IEEE division like `to_tensor` on the host (a Python-scalar
+    return lr.float() / d, hr_u8.float() / d, bc.float() / d   # divisor is turned into a multiplication by the reciprocal on CUDA: 1 ulp off)
 
 
 class FolderHRDataset(FolderSRDataset):
