@@ -444,6 +444,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    pdl_trigger();                 // the next kernel of the stream may be scheduled as this grid's blocks exit
+    pdl_wait();                    // everything above overlapped the predecessor's tail; global memory is read from here on
     {
         const int r2 = p.shuffle_r > 1 ? p.shuffle_r * p.shuffle_r : 1;
         const int cq = p.Cout / r2;
@@ -833,9 +835,10 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
 #define HL_LAUNCH(slot, ...)                                                                                              \
     do {                                                                                                                  \
         if (!attr_set[slot]) { cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[slot] = true; } \
-        __VA_ARGS__<<<grid, HL_THREADS, smem, st>>>(map_a, map_b, p);                                                     \
+        launch_pdl(__VA_ARGS__, dim3(grid), dim3(HL_THREADS), smem, st, pdl, map_a, map_b, p);                            \
     } while (0)
     if (stack && !out_bf16) { set_error("conv_halo: internal: stack mode needs a bf16 output"); return SR_ERR_UNSUPPORTED; }
+    const bool pdl = option("SR_PDL", 0) != 0;
     if (p.pool_sum && stack) HL_LAUNCH(4, conv_halo_kernel<__nv_bfloat16, true, true>);
     else if (p.pool_sum) HL_LAUNCH(2, conv_halo_kernel<__nv_bfloat16, true, false>);
     else if (stack) HL_LAUNCH(3, conv_halo_kernel<__nv_bfloat16, false, true>);

@@ -157,6 +157,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    pdl_trigger();
+    pdl_wait();                    // (common.cuh) global memory is read from here on
     {   // bias in packed-column order (subpixel-major when the epilogue does the PixelShuffle)
         const int r2 = p.shuffle_r > 1 ? p.shuffle_r * p.shuffle_r : 1;
         const int cq = p.Cout / r2;
@@ -295,10 +297,10 @@ static int launch_tc(TcParams p, const CUtensorMap& map_a, const CUtensorMap& ma
     static bool attr_set[2] = {false, false};
     if (out_bf16) {
         if (!attr_set[0]) { cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[0] = true; }
-        conv_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+        launch_pdl(conv_tc_kernel<__nv_bfloat16>, dim3(grid), dim3(TC_THREADS), smem, st, option("SR_PDL", 0) != 0, map_a, map_b, p);
     } else {
         if (!attr_set[1]) { cudaFuncSetAttribute(conv_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[1] = true; }
-        conv_tc_kernel<float><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+        launch_pdl(conv_tc_kernel<float>, dim3(grid), dim3(TC_THREADS), smem, st, option("SR_PDL", 0) != 0, map_a, map_b, p);
     }
     count_launch();
     return check_launch("conv_tc_kernel");

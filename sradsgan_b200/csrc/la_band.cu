@@ -56,6 +56,8 @@ la_pool_pack_kernel(const __nv_bfloat16* __restrict__ x, int P, int S, float* __
 
 __global__ void __launch_bounds__(256, 3)
 la_fwd_band_kernel(const LaBandFwd p) {
+    pdl_trigger();
+    pdl_wait();                    // (common.cuh) launched with the programmatic-serialization attribute
     extern __shared__ __align__(16) unsigned char lb_smem[];
     __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(lb_smem);            // [co][ci] hi
     __nv_bfloat16* Wl = Ws + LA_C * LA_LD;                                    //          lo
@@ -327,6 +329,8 @@ la_fwd_band_kernel(const LaBandFwd p) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 la_bwd_band_kernel(const LaBandBwd p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float lbb_smem[];
     float* qs = lbb_smem;                                       // [(R+6)][W][2]
     float* des = qs + (size_t)(p.R + 6) * p.W * 2;              // [(R+6)][W]: de = dm * m * (1 - m), zero outside the image
@@ -530,7 +534,7 @@ int la_band_fwd(LaBandFwd p, cudaStream_t st) {
     const size_t smem = la_band_fwd_smem(p.R, p.W);
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(la_fwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 96 * 1024)); attr = std::max<size_t>(smem, 96 * 1024); }
-    la_fwd_band_kernel<<<p.N * p.bands, 256, smem, st>>>(p);
+    launch_pdl(la_fwd_band_kernel, dim3(p.N * p.bands), dim3(256), smem, st, option("SR_PDL", 0) != 0, p);
     count_launch();
     return check_launch("la_fwd_band_kernel");
 }
@@ -542,7 +546,7 @@ int la_band_bwd(LaBandBwd p, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)(p.R + 6) * p.W * 3 + (size_t)p.R * p.W * 2 + 100 + 8 * LA_C);
     static size_t attr = 0;
     if (smem > attr) { cudaFuncSetAttribute(la_bwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 96 * 1024)); attr = std::max<size_t>(smem, 96 * 1024); }
-    la_bwd_band_kernel<<<p.N * p.bands, 256, smem, st>>>(p);
+    launch_pdl(la_bwd_band_kernel, dim3(p.N * p.bands), dim3(256), smem, st, option("SR_PDL", 0) != 0, p);
     count_launch();
     return check_launch("la_bwd_band_kernel");
 }

@@ -466,6 +466,8 @@ la_bwd_apply_mma_kernel(const float* __restrict__ gz32, const __nv_bfloat16* __r
                         const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ Wm, int P, long long NP,
                         int tiles, float* __restrict__ g_out, float* __restrict__ dm, float* __restrict__ dW, float* __restrict__ db,
                         float* __restrict__ dz_out, float* __restrict__ wpart) {
+    pdl_trigger();
+    pdl_wait();                    // (common.cuh) the band path launches this kernel with the programmatic-serialization attribute
     extern __shared__ __align__(16) unsigned char la_mma_smem[];
     __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(la_mma_smem);      // [co][ci] hi
     __nv_bfloat16* Wl = Ws + LA_C * LA_LD;                                   //          lo
@@ -756,6 +758,8 @@ la_bwd_stats_kernel(const float* __restrict__ g, const float* __restrict__ dq, c
 template <typename T>
 __global__ void __launch_bounds__(256)
 la_fix_kernel(T* __restrict__ dx, const float* __restrict__ da, const float* __restrict__ dmx, const int* __restrict__ pstar, int P, long long total) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= total) return;
     const int c = (int)(i % LA_C);
@@ -958,8 +962,9 @@ int la_chain_backward(const sr_la_chain_grad_args* a, cudaStream_t st) {
     const size_t mma_smem = (size_t)6 * LA_C * LA_LD * sizeof(__nv_bfloat16);
     static bool mma_attr = false;
     if (!mma_attr) { cudaFuncSetAttribute(la_bwd_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma_smem); mma_attr = true; }
-    la_bwd_apply_mma_kernel<<<grid, 256, mma_smem, st>>>(a->gz32, (const __nv_bfloat16*)a->gz16, a->gacc, (const __nv_bfloat16*)a->x, a->s, a->m, a->Wm,
-                                                         P, NP, tiles, g, dm, a->dW, a->db, a->dz_out, wpart);
+    const bool pdl = option("SR_PDL", 0) != 0;
+    launch_pdl(la_bwd_apply_mma_kernel, dim3(grid), dim3(256), mma_smem, st, pdl, a->gz32, (const __nv_bfloat16*)a->gz16, a->gacc,
+               (const __nv_bfloat16*)a->x, a->s, a->m, a->Wm, P, NP, tiles, g, dm, a->dW, a->db, a->dz_out, wpart);
     count_launch();
     LaBandBwd p;
     memset(&p, 0, sizeof(p));
@@ -970,7 +975,8 @@ int la_chain_backward(const sr_la_chain_grad_args* a, cudaStream_t st) {
     p.dspart = dspart; p.w7part = w7part; p.ds = ds; p.da = da; p.dmx = dmx; p.tickets = a->tickets;
     int rc = la_band_bwd(p, st);
     if (rc) return rc;
-    la_fix_kernel<__nv_bfloat16><<<(unsigned)cdiv(NP * LA_C / 4, 256), 256, 0, st>>>((__nv_bfloat16*)a->dx, da, dmx, a->pstar, P, NP * LA_C);
+    launch_pdl(la_fix_kernel<__nv_bfloat16>, dim3((unsigned)cdiv(NP * LA_C / 4, 256)), dim3(256), 0, st, pdl, (__nv_bfloat16*)a->dx, (const float*)da,
+               (const float*)dmx, (const int*)a->pstar, P, NP * LA_C);
     count_launch();
     return check_launch("la_chain_backward");
 }
