@@ -45,6 +45,9 @@ struct HaloParams {
     int stack;                       // Cout = 64: the three kx taps of a filter row stacked along N (one N = 192 instruction instead of three N = 64
                                      // ones, which are issue-bound); accumulator = [R_kx0 | R_kx1 | R_kx2], out[j] = sum_kx R_kx[j + shift(kx)] in the
                                      // epilogue.  Tile pairs (dual = 1) on ONE issuer, single-buffered accumulators (2 x 192 TMEM columns)
+    int mcast;                       // stack mode on single tiles: clusters of TWO CTAs share every streamed weight stage (each loads half of
+                                     // it and multicasts it into both; the two weight rings advance in lockstep, the CTA with fewer
+                                     // tiles running "ghost" items that only load and release weights)
     const float* bias;
     const void* residual;
     const void* mask;                // nullable bf16 tensor shaped like the output: out *= act'(mask)
@@ -189,7 +192,8 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
     const OutT* res = reinterpret_cast<const OutT*>(p.residual);
     const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(p.mask);
     int accs[2] = {0, 0}; uint32_t phs[2] = {0, 0};
-    const int nbuf = p.stack ? 1 : 2;            // accumulator buffers per issuer / tile slot
+    const int nbuf = (p.stack && p.dual) ? 1 : 2;   // accumulator buffers per issuer / tile slot (stack mode on tile PAIRS: one each)
+    int xq = 0;                                     // stack mode: which half of this group's exchange area the next chunk uses
     auto advance = [&](int w) { if (++accs[w] == nbuf) { accs[w] = 0; phs[w] ^= 1; } };
     int t0, t1, nb;
     for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
@@ -314,7 +318,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                 mbar_wait(acc_full + buf, phs[own]);
                 tc_fence_after();
                 if (quarter == 0 && lane == 0) HL_TRACE(80 + grp * 16 + it * 2);
-                const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(STACK ? own * 192 : buf * acc_stride);
+                const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(STACK ? (p.dual ? own : buf) * 192 : buf * acc_stride);
                 int c = c_first;
                 if (STACK) {
                     // out[j] = S0[j] + S1[j + 1] + S2[j + 2], S_s = the 64-column block whose taps sit s pixels to the right (flip mirrors
@@ -322,9 +326,11 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                     // rows of S1 (row 0) and S2 (rows 0, 1) in shared memory, one half of the exchange area per 32-column chunk (so one
                     // barrier per chunk orders writes against the previous reads of the same half).
                     const uint32_t col_s0 = p.flip ? 128u : 0u, col_s2 = p.flip ? 0u : 128u;
+                    // tile pairs: group = tile, both chunks; single tiles: both groups on the one tile, chunk = group
 #pragma unroll 1
-                    for (int cc = 0; cc < 2; ++cc) {
-                        float* xch = xch_s + (grp * 2 + cc) * (4 * 3 * 32);              // [quarter][3 rows][32 columns]
+                    for (int cc = p.dual ? 0 : grp; cc < (p.dual ? 2 : grp + 1); ++cc) {
+                        float* xch = xch_s + (grp * 2 + xq) * (4 * 3 * 32);              // [quarter][3 rows][32 columns]
+                        xq ^= 1;
                         float f[32];
                         tmem_ld32_nowait(t_base + col_s0 + (uint32_t)(cc * 32), va);
                         tmem_ld32_nowait(t_base + 64u + (uint32_t)(cc * 32), vb);
@@ -385,7 +391,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                     emit(vb, c);
                     c += c_step;
                 }
-                if (POOL) pool_flush(3);
+                if (POOL) pool_flush((STACK && !p.dual) ? (1 << grp) : 3);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + buf);
@@ -438,7 +444,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < p.num_a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < p.num_b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, p.stack ? 1 : issuers); }
+        for (int s = 0; s < p.num_b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, p.mcast ? 2 : (p.stack ? 1 : issuers)); }
         for (int a = 0; a < 4; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, p.dual ? 4 : HL_EPI_WARPS); }
         if (p.resident) for (int kb = 0; kb < k_blocks; ++kb) mbar_init(r_full + kb, 1);
         fence_barrier_init();
@@ -460,8 +466,46 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) HL_TRACE(1);
+    // multicast mode: items of the cluster's longer lane (its even CTA); the barriers of BOTH CTAs are initialised before any
+    // remote arrival / multicast box can land
+    int mc_rounds = 0;
+    uint32_t cta_rank = 0;
+    if (STACK && p.mcast) {
+        cta_rank = cluster_ctarank();
+        const int first = (int)(blockIdx.x & ~1u);
+        mc_rounds = first < p.n_items ? (p.n_items - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        cluster_sync_all();
+    }
 
-    if (warp == 0) {
+    if (warp == 0 && STACK && p.mcast) {
+        // ===== TMA producer, multicast mode: own activation tiles; HALF of every weight stage, multicast into both CTAs =====
+        if (lane == 0) {
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            for (int it = 0; it < mc_rounds; ++it) {
+                int t0, t1, nb;
+                const bool real = hl_item_at(p, it, t0, t1, nb);
+                int n = 0, y0 = 0, x0 = 0;
+                if (real) hl_tile_origin(p, t0, n, y0, x0);
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    if (real) {
+                        mbar_wait(a_empty + sa, pa ^ 1);
+                        mbar_expect_tx(a_full + sa, (uint32_t)p.a_box_bytes);
+                        tma_load_4d(a_base + (size_t)sa * p.a_stage_bytes, &map_a, a_full + sa, cb * 64, x0 - 1, y0 - 1, n);
+                        if (cb == 0) HL_TRACE(8 + it * 2);
+                        if (++sa == ring_a) { sa = 0; pa ^= 1; }
+                    }
+                    for (int ky = 0; ky < 3; ++ky) {
+                        mbar_wait(b_empty + sb, pb ^ 1);                       // released by BOTH CTAs' issuers
+                        mbar_expect_tx(b_full + sb, (uint32_t)b_bytes);        // both halves land here (the peer's may arrive first)
+                        tma_load_2d_mcast(b_base + (size_t)sb * b_bytes + (size_t)cta_rank * (96 * 128), &map_b, b_full + sb, cb * 64,
+                                          ky * 192 + (int)cta_rank * 96, (uint16_t)3);
+                        if (++sb == p.num_b_stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int sa[2] = {0, 0}; uint32_t pa[2] = {0, 0};
@@ -510,18 +554,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // M=128 x N=128 instruction (profiles/r01_umma_issue_rate.txt).  The warp walks the schedule converged. =====
         const int w = warp - 1;
         if (STACK) {
-            // ===== stack mode: ONE issuer, both tiles of an item per weight stage, N = 192 =====
+            // ===== stack mode: ONE issuer, N = 192.  Tile PAIRS (p.dual): both tiles of an item per weight stage, one accumulator
+            // each (2 x 192 columns) — half the weight traffic, but the epilogue cannot overlap the next item.  SINGLE tiles: the
+            // accumulator is double buffered (2 x 192), the epilogue of tile i runs under the MMAs of tile i + 1. =====
             if (w == 0) {
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(192 >> 3) << 17) | ((128u >> 4) << 24);
                 int sa[2] = {0, 0}; uint32_t pa[2] = {0, 0};
                 int sb = 0; uint32_t pb = 0;
                 uint32_t acc_phase[2] = {0, 0};
+                int acc = 0;                     // single tiles: accumulator buffer of the next item
                 int t0, t1, nb;
-                for (int it = 0; hl_item_at(p, it, t0, t1, nb); ++it) {
-                    const bool has[2] = {t0 >= 0, t1 >= 0};
+                for (int it = 0;; ++it) {
+                    // multicast mode: `mc_rounds` items in both CTAs of the cluster; a CTA without a tile in a round still waits for and
+                    // releases every weight stage
+                    const bool real = hl_item_at(p, it, t0, t1, nb);
+                    if (p.mcast ? it >= mc_rounds : !real) break;
+                    const bool has[2] = {real && t0 >= 0, real && p.dual && t1 >= 0};
+                    // barrier index / TMEM column of slot g: pairs -> (g * 2, g * 192); single tiles -> (acc, acc * 192)
+                    const int bar_of[2] = {p.dual ? 0 : acc, 2};
+                    const uint32_t col_of[2] = {p.dual ? 0u : (uint32_t)acc * 192u, 192u};
 #pragma unroll
                     for (int g = 0; g < 2; ++g)
-                        if (has[g]) mbar_wait(acc_empty + g * 2, acc_phase[g] ^ 1);
+                        if (has[g]) mbar_wait(acc_empty + bar_of[g], acc_phase[p.dual ? g : acc] ^ 1);
                     tc_fence_after();
                     if (lane == 0) HL_TRACE(32 + it * 3);
                     for (int cb = 0; cb < p.c_blocks; ++cb) {
@@ -542,9 +596,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)sb * b_bytes));
                                 const uint32_t row_off = (uint32_t)((p.flip ? 2 - ky : ky) * p.TWp) * 8u;
                                 const uint32_t accum = (cb | ky) ? 1u : 0u;
-                                if (has[0]) umma_f16_x4(tmem_base, adesc[0] + row_off, bdesc, idesc, accum);
-                                if (has[1]) umma_f16_x4(tmem_base + 192u, adesc[1] + row_off, bdesc, idesc, accum);
-                                umma_commit(b_empty + sb);
+                                if (has[0]) umma_f16_x4(tmem_base + col_of[0], adesc[0] + row_off, bdesc, idesc, accum);
+                                if (has[1]) umma_f16_x4(tmem_base + col_of[1], adesc[1] + row_off, bdesc, idesc, accum);
+                                if (p.mcast) umma_commit_mcast(b_empty + sb, (uint16_t)3); else umma_commit(b_empty + sb);
                             }
                             __syncwarp();
                             if (++sb == p.num_b_stages) { sb = 0; pb ^= 1; }
@@ -560,9 +614,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                     for (int g = 0; g < 2; ++g)
                         if (has[g]) {
-                            if (lane == 0) umma_commit(acc_full + g * 2);
-                            acc_phase[g] ^= 1;
+                            if (lane == 0) umma_commit(acc_full + bar_of[g]);
+                            acc_phase[p.dual ? g : acc] ^= 1;
                         }
+                    if (!p.dual && has[0]) acc ^= 1;
                     if (lane == 0) HL_TRACE(32 + it * 3 + 2);
                     __syncwarp();
                 }
@@ -668,6 +723,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (STACK && p.mcast) cluster_sync_all();      // the peer may still signal this CTA's barriers / this CTA the peer's
     if (threadIdx.x == 0) {
         HL_TRACE(2);
 #ifdef SR_WITH_PROBES
@@ -780,6 +836,10 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.resident = resident ? 1 : 0;
     p.stack = stack ? 1 : 0;
     p.dual = (bn <= 128 && (resident || p.n_blocks == 1)) ? 1 : 0;
+    // stack mode on single tiles (double-buffered accumulator) instead of tile pairs: measured SLOWER (K2 forward 37.5k vs 35.9k
+    // cycles per CTA, profiles/r02_halo_stack_variants.txt) — every SM has to take in the whole 295 KB weight stream per tile,
+    // and that intake (~48 B/clk per SM), not the L2, is the limit, so sharing the stream between two tiles of the same CTA wins
+    if (stack && !option("SR_HALO_STACK_PAIRS", 1)) p.dual = 0;
     // experiment option: resident-weights layers on ONE issuer with a two-deep activation ring
     if (option("SR_HALO_NODUAL_RES", 0) && resident) p.dual = 0;
     const int lane_ctas = resident ? grid / p.n_blocks : grid;
@@ -824,27 +884,46 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
         p.num_a_stages = na; p.num_b_stages = nbs;
         tile_bytes = (size_t)na * p.a_stage_bytes + (size_t)nbs * b_bytes;
     }
+    const size_t smem = 1024 + tile_bytes + 1024 + HL_BIAS_MAX * 4 + xch_bytes;
+    const bool out_bf16 = d->out_dtype == SR_BF16;
+    if (stack && !out_bf16) { set_error("conv_halo: internal: stack mode needs a bf16 output"); return SR_ERR_UNSUPPORTED; }
+    const bool pdl = option("SR_PDL", 0) != 0;
+    static bool attr_set[5] = {false, false, false, false, false};
+#define HL_ATTR(slot, ...)                                                                                                \
+    do {                                                                                                                  \
+        if (!attr_set[slot]) { cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[slot] = true; } \
+    } while (0)
+    // multicast mode (stack mode on single tiles): clusters of two CTAs, as many as can be resident at once
+    int cluster = 1;
+    // (measured: no gain — 42.5k cycles; the multicast halves the L2 reads but not what each SM must take in; kept as an option)
+    if (stack && !p.dual && option("SR_HALO_MCAST", 0) && p.n_items >= 2 * 2) {
+        static int max_clusters[2] = {-1, -1};
+        const int which = p.pool_sum ? 1 : 0;
+        if (max_clusters[which] < 0) {
+            if (which) { HL_ATTR(4, conv_halo_kernel<__nv_bfloat16, true, true>); max_clusters[1] = max_active_clusters(conv_halo_kernel<__nv_bfloat16, true, true>, HL_THREADS, smem, 2, g_hl_sms); }
+            else { HL_ATTR(3, conv_halo_kernel<__nv_bfloat16, false, true>); max_clusters[0] = max_active_clusters(conv_halo_kernel<__nv_bfloat16, false, true>, HL_THREADS, smem, 2, g_hl_sms); }
+        }
+        int g2 = 2 * max_clusters[which];
+        if (g2 > p.n_items) g2 = p.n_items & ~1;
+        if (g2 >= 2) { cluster = 2; grid = g2; p.mcast = 1; }
+    }
     alignas(64) CUtensorMap map_a, map_b;
     rc = make_tiled4d_map(&map_a, src, d->N, d->H, d->W, Cs, p.TWp, p.TR + 2);
     if (rc != SR_OK) return rc;
-    rc = make_tiled2d_map(&map_b, w, (uint64_t)9 * Cd, (uint64_t)Cs, (uint32_t)(stack ? 192 : bn));
+    rc = make_tiled2d_map(&map_b, w, (uint64_t)9 * Cd, (uint64_t)Cs, (uint32_t)(stack ? (p.mcast ? 96 : 192) : bn));
     if (rc != SR_OK) return rc;
-    const size_t smem = 1024 + tile_bytes + 1024 + HL_BIAS_MAX * 4 + xch_bytes;
-    const bool out_bf16 = d->out_dtype == SR_BF16;
-    static bool attr_set[5] = {false, false, false, false, false};
 #define HL_LAUNCH(slot, ...)                                                                                              \
     do {                                                                                                                  \
-        if (!attr_set[slot]) { cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); attr_set[slot] = true; } \
-        launch_pdl(__VA_ARGS__, dim3(grid), dim3(HL_THREADS), smem, st, pdl, map_a, map_b, p);                            \
+        HL_ATTR(slot, __VA_ARGS__);                                                                                       \
+        launch_ex(__VA_ARGS__, dim3(grid), dim3(HL_THREADS), smem, st, pdl, cluster, map_a, map_b, p);                    \
     } while (0)
-    if (stack && !out_bf16) { set_error("conv_halo: internal: stack mode needs a bf16 output"); return SR_ERR_UNSUPPORTED; }
-    const bool pdl = option("SR_PDL", 0) != 0;
     if (p.pool_sum && stack) HL_LAUNCH(4, conv_halo_kernel<__nv_bfloat16, true, true>);
     else if (p.pool_sum) HL_LAUNCH(2, conv_halo_kernel<__nv_bfloat16, true, false>);
     else if (stack) HL_LAUNCH(3, conv_halo_kernel<__nv_bfloat16, false, true>);
     else if (out_bf16) HL_LAUNCH(0, conv_halo_kernel<__nv_bfloat16, false, false>);
     else HL_LAUNCH(1, conv_halo_kernel<float, false, false>);
 #undef HL_LAUNCH
+#undef HL_ATTR
     count_launch();
     return check_launch("conv_halo_kernel");
 }
