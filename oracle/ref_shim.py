@@ -24,6 +24,9 @@ _STUBS = [
 ]
 
 
+_MISSING = {"model.srgan": {"data.data": ["get_training_datasets", "get_test_datasets", "get_RGB_trainDataset", "get_RGB_testDataset"]}}
+
+
 class _Anything(types.ModuleType):
     """Module whose every attribute is a callable returning None (never reached by the hot path)."""
 
@@ -71,6 +74,13 @@ def load_reference(module="model.sradsgan"):
             del sys.modules[k]
     sys.path.insert(0, REF_ROOT)
     try:
+        # model/srgan.py:34 imports names its own data/data.py does not define (the sibling cannot be imported in the reference tree
+        # as shipped); they are dataset factories, never reached by the arithmetic: inert stand-ins on the reference's module
+        for host, names in _MISSING.get(module, {}).items():
+            hm = importlib.import_module(host)
+            for n in names:
+                if not hasattr(hm, n):
+                    setattr(hm, n, lambda *a, **k: None)
         mod = importlib.import_module(module)
         mod.srutils_mod = importlib.import_module("utils.utils")
     finally:
