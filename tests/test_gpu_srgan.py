@@ -64,7 +64,9 @@ def test_generator_per_block_parity(precision, scale):
     tol = TOL[precision]
     worst = max((rel(v, taps[k]), k) for k, v in got.items())
     assert worst[0] < tol, "per-block error %g at %s" % worst
-    assert rel(y, y_ref) < tol
+    # end to end (trunk + conv2 / BatchNorm + one or two conv / BatchNorm / shuffle stages + the 9x9 output conv + tanh): the roundings of
+    # the bf16 stages behind the last tap add up — bounded by twice the per-layer tolerance, like the full-depth EDSR test
+    assert rel(y, y_ref) < 2 * tol
     gsd = net.state_dict()
     for k in sd:                                   # BatchNorm running statistics, incl. the shared up-sampling BatchNorm
         if "running" in k:
