@@ -37,6 +37,7 @@ struct HaloParams {
     int tiles_x, tiles_y, p_tiles;   // pixel tiles = N * tiles_y * tiles_x
     int block_n, n_blocks, c_blocks;
     int flip;                        // dgrad: filter taps mirrored
+    int quads;                       // bf16 outputs: row-coalesced (quad-transposed) stores
     int act; float slope; int shuffle_r;
     int a_stage_bytes, a_box_bytes, num_a_stages, num_b_stages, resident;
     int dual;                        // 1: two MMA-issuer warps work on two pixel tiles at once (shared weights)
@@ -239,7 +240,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
             };
             // bf16 outputs: row-coalesced stores (tc_store_chunk_quads) — the row bases of the lane's quad, fetched once per tile
-            const bool quads = sizeof(OutT) == 2 && !POOL && !p.narrow;
+            const bool quads = sizeof(OutT) == 2 && !POOL && !p.narrow && p.quads;
             const long long row_base = r > 1 ? ((((long long)n * p.H * r + (long long)oy * r) * ((long long)p.W * r)) + (long long)ox * r) * cq : row_idx;
             long long q_base[4] = {0, 0, 0, 0};
             unsigned q_ok = 0;
@@ -279,7 +280,7 @@ __device__ __forceinline__ void hl_epilogue(const HaloParams& p, uint32_t tmem_b
                     const int si = sub / r, sj = sub - si * r;
                     chunk_off = (si * p.W * r + sj) * cq + ch0;
                 }
-                if (sizeof(OutT) == 2) {
+                if (sizeof(OutT) == 2 && quads) {
                     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
                     __nv_bfloat16* const qp[4] = {ob + q_base[0] + chunk_off, ob + q_base[1] + chunk_off, ob + q_base[2] + chunk_off, ob + q_base[3] + chunk_off};
                     const long long idx = row_base + chunk_off;
@@ -789,6 +790,7 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.p_tiles = d->N * p.tiles_y * p.tiles_x;
     p.c_blocks = Cs / 64;
     p.flip = dgrad ? 1 : 0;
+    p.quads = option("SR_HALO_QUADS", 1) ? 1 : 0;
     p.act = dgrad ? SR_ACT_NONE : d->act; p.slope = d->slope;
     p.shuffle_r = dgrad ? 0 : d->shuffle_r;
     p.bias = bias; p.residual = residual; p.out = dst;
@@ -818,7 +820,11 @@ int conv_halo_run(const sr_conv_desc* d, bool dgrad, const void* src, const void
     p.narrow = Cd <= 4 ? 1 : 0;
     if (p.narrow && (residual || mask || p.shuffle_r > 1)) { set_error("conv_halo: thin outputs support bias / activation only"); return SR_ERR_UNSUPPORTED; }
     // stack mode (64 output channels fed by >= 128 input channels: RAB conv2 and the input gradient of conv1)
-    const bool stack = Cd == 64 && Cs >= 128 && d->out_dtype == SR_BF16 && p.shuffle_r <= 1 && p.TR * p.TWp <= 128 && option("SR_HALO_STACK", 1);
+    // ... and only when the nine-tap mode could NOT keep the [9*Cin] x 64 weight slab resident (Cin = 128: 147 KB fits, and loading the
+    // weights once beats streaming them per tile pair — 128->64 @108^2 input gradient: 41.7 us resident vs 49.8 us stacked)
+    const bool slab_fits = (long long)k_blocks * 64 * 128 + 2 * p.a_stage_bytes <= HL_TILE_BUDGET && k_blocks <= HL_MAX_RES;
+    const bool stack = Cd == 64 && Cs >= 128 && !slab_fits && d->out_dtype == SR_BF16 && p.shuffle_r <= 1 && p.TR * p.TWp <= 128 &&
+                       option("SR_HALO_STACK", 1);
     int bn;
     if (p.narrow) bn = 64; else if (Cd % 128 == 0) bn = 128; else if (Cd % 192 == 0) bn = 192; else bn = 64;
     long long res_bytes = (long long)k_blocks * bn * 128;
