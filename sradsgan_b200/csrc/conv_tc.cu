@@ -90,20 +90,36 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         long long row_idx;     // element index of column 0 of this row (plain / strided-scatter modes)
         if (p.os > 1) row_idx = (((long long)n * p.Hfull + (oy * p.os + p.py)) * p.Wfull + (ox * p.os + p.px)) * p.Cout;
         else row_idx = m * p.Cout;
+        // bf16 outputs: row-coalesced stores (tc_store_chunk_quads, tc_common.cuh) — the row bases of the lane's quad, once per tile
+        const long long row_base = r > 1 ? ((((long long)n * p.Ho * r + (long long)oy * r) * ((long long)p.Wo * r)) + (long long)ox * r) * cq : row_idx;
+        long long q_base[4] = {0, 0, 0, 0};
+        unsigned q_ok = 0;
+        if (sizeof(OutT) == 2) {
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            q_ok = (vm >> (lane & ~3)) & 0xFu;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q_base[i] = __shfl_sync(0xffffffffu, row_base, (lane & ~3) + i) + (lane & 3) * 8;
+        }
         mbar_wait(acc_full + acc, acc_phase);
         tc_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_ACC_STRIDE);
         auto emit = [&](const uint32_t (&v)[32], int c) {
-            if (!valid) return;
             const int col = nb * p.block_n + c * 32;     // packed (GEMM) output column of v[0]
-            long long idx;
+            int chunk_off = col;                         // offset of this chunk's first column from the row base (the same for every row)
             if (r > 1) {
                 const int sub = col / cq, ch0 = col - sub * cq;
                 const int si = sub / r, sj = sub - si * r;
-                idx = ((((long long)n * p.Ho * r + (oy * r + si)) * ((long long)p.Wo * r)) + (ox * r + sj)) * cq + ch0;
-            } else {
-                idx = row_idx + col;
+                chunk_off = (si * p.Wo * r + sj) * cq + ch0;
             }
+            const long long idx = row_base + chunk_off;
+            if (sizeof(OutT) == 2) {                     // every lane takes part (shuffles); invalid rows store nothing
+                __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
+                __nv_bfloat16* const qp[4] = {ob + q_base[0] + chunk_off, ob + q_base[1] + chunk_off, ob + q_base[2] + chunk_off, ob + q_base[3] + chunk_off};
+                tc_store_chunk_quads<ACT>(v, bias_s + col, p.slope, (res && valid) ? reinterpret_cast<const __nv_bfloat16*>(res) + idx : nullptr,
+                                          nullptr, 0.f, qp, q_ok, lane);
+                return;
+            }
+            if (!valid) return;
             tc_store_chunk<OutT, ACT>(v, bias_s + col, p.slope, res ? res + idx : nullptr, out + idx);
         };
         uint32_t va[32], vb[32];
