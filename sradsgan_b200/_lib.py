@@ -178,7 +178,7 @@ def load():
     lib.sr_la_chain_backward.restype = i32
     # experiment knobs: the library never reads the environment; SR_* variables of THIS process are forwarded explicitly
     for k, v in os.environ.items():
-        if k.startswith(("SR_LA_", "SR_HALO_", "SR_WG_", "SR_S2_")):
+        if k.startswith(("SR_LA_", "SR_HALO_", "SR_WG_", "SR_S2_", "SR_PDL")):
             try:
                 lib.sr_set_option(k.encode(), int(v))
             except ValueError:

@@ -77,8 +77,10 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 // completed and flushed).  A predecessor that calls pdl_trigger() lets the dependent's blocks take over its SMs as its own
 // blocks exit — launch latency and the dependent's prologue (barrier init, TMEM allocation, descriptor prefetch) then overlap
 // the predecessor's tail.  Both are no-ops for launches without the attribute.  Captured by CUDA graphs as programmatic edges.
-// Option "SR_PDL" (default 0): measured on the B200 training step under graph replay, 22.94 ms with vs 22.96 ms without
-// (gpurun r2c15; all GPU tests pass either way) — the step is not launch-latency bound, so the attribute stays off.
+// Option "SR_PDL" (default 0): a captured chain of 24 dependent RAB convolutions replays at 22.75 us per launch without and
+// 22.83 us with the attribute (scripts/graph_gap_probe.py, profiles/r02_graph_gap_probe.txt) — graph replay already hides the
+// launch latency, and a dependent's blocks cannot become resident before the predecessor's blocks (227 KB of shared memory
+// each) have left, so the attribute stays off; it is exercised by that probe only, not by the test suite.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
