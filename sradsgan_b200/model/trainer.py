@@ -309,9 +309,12 @@ class SRADSGAN(object):
             if os.environ.get("SR_PACK_PLAN", "1") == "1":
                 self._pack_plans = [ops.PackPlan(self.optimizer_G.params), ops.PackPlan(self.optimizer_D.params)]
             n0 = _lib.backend().launch_count()
+            # SR_GRAPH_PRIORITY=1: capture the main chain on a HIGH-priority stream, so that its kernel nodes win the block scheduler
+            # against the weight-gradient branches forked onto the (default-priority) side streams
+            cap = {"stream": torch.cuda.Stream(priority=-1)} if os.environ.get("SR_GRAPH_PRIORITY", "0") == "1" else {}
             if world == 1 and os.environ.get("SR_DP_FORCE_SEGMENTS", "0") != "1":      # (the knob: scripts/dp_overlap_check.py on one GPU)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local", **cap):
                     st["out"] = self.train_step(st["lr"], st["hr"])
                 graphs = [graph]
             else:
