@@ -67,7 +67,7 @@ def noise_grad_keys(spec):
     turns the rounding noise of any implementation into +-lr steps — such entries cannot be compared between implementations"""
     out = set()
     for k in spec:
-        if k.endswith(".bias") and not (k[:-5] + ".running_mean") in spec:
+        if k.endswith(".bias") and "." in k[:-5] and not (k[:-5] + ".running_mean") in spec:
             head, idx = k[:-5].rsplit(".", 1)
             if idx.isdigit() and ("%s.%d.running_mean" % (head, int(idx) + 1)) in spec:
                 out.add(k)
