@@ -24,7 +24,8 @@ _STUBS = [
 ]
 
 
-_MISSING = {"model.srgan": {"data.data": ["get_training_datasets", "get_test_datasets", "get_RGB_trainDataset", "get_RGB_testDataset"]}}
+_DATA_FACTORIES = {"data.data": ["get_training_datasets", "get_test_datasets", "get_RGB_trainDataset", "get_RGB_testDataset"]}
+_MISSING = {"model.srgan": _DATA_FACTORIES, "model.ndsrgan": _DATA_FACTORIES}
 
 
 class _Anything(types.ModuleType):

@@ -92,6 +92,9 @@ def main(argv=None):
     elif args.model_name == 'SRAGAN':
         from .model.sragan import SRAGAN        # reference main_sragan.py: SRADSGAN's predecessor
         net = SRAGAN(args)
+    elif args.model_name == 'NDSRGAN':
+        from .model.ndsrgan import NDSRGAN      # reference main_ndsrgan.py
+        net = NDSRGAN(args)
     elif args.model_name == 'SRGAN':
         from .model.srgan import SRGAN          # reference main_srgan.py: the first of the sibling GANs
         net = SRGAN(args)
