@@ -171,3 +171,24 @@ def test_trainer_steps_match_reference_golden(emu, agolden):
         for k, w in want["G_state"].items():
             if k not in noise and "num_batches" not in k:
                 assert abs(summarize(gsd[k].float(), 8)["norm"] - w["norm"]) <= 5e-4 * max(1e-9, w["norm"]), (it, k)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_eval_mode_forward_matches_reference_module(emu):
+    """validate() / inference run the generator in eval mode: BatchNorm with its running statistics == the reference module"""
+    ref = ref_shim.load_reference("model.sragan")
+    sd = A.make_state(A.generator_spec(4, 2, 2), seed=5, init="fan")
+    g = torch.Generator().manual_seed(2)
+    for k in sd:
+        if "running_mean" in k:
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        if "running_var" in k:
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    A.tie_upsampling(sd)
+    want = ref.GeneratorResNet(ref.ResidualBlock_Block_WithAttention, n_residual_blocks=2, n_basic_blocks=2, upscale_factor=4)
+    want.load_state_dict(sd, strict=True)
+    mine = _gen(4, 2, 2)
+    mine.load_state_dict(sd, strict=True)
+    x = torch.rand(2, 3, 10, 10, generator=g)
+    with torch.no_grad():
+        assert rel(mine.eval()(x), want.eval()(x)) < 1e-5

@@ -180,3 +180,24 @@ def test_trainer_steps_match_reference_golden(emu, sgolden):
                 if k in noise:
                     continue
                 assert abs(summarize(msd[k].float(), 8)["norm"] - w["norm"]) <= 5e-4 * max(1e-9, w["norm"]), (it, name, k)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_eval_mode_forward_matches_reference_module(emu):
+    """validate() / inference run the generator in eval mode: BatchNorm with its running statistics == the reference module"""
+    ref = ref_shim.load_reference("model.srgan")
+    sd = S.make_state(S.generator_spec(4, 2), seed=5, init="fan")
+    g = torch.Generator().manual_seed(2)
+    for k in sd:
+        if "running_mean" in k:
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        if "running_var" in k:
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    S.tie_upsampling(sd)
+    want = ref.GeneratorResNet(n_residual_blocks=2, upscale_factor=4)
+    want.load_state_dict(sd, strict=True)
+    mine = GeneratorResNet(n_residual_blocks=2, upscale_factor=4)
+    mine.load_state_dict(sd, strict=True)
+    x = torch.rand(2, 3, 10, 10, generator=g)
+    with torch.no_grad():
+        assert rel(mine.eval()(x), want.eval()(x)) < 1e-5
