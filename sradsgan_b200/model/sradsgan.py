@@ -451,21 +451,28 @@ class Discriminator(nn.Module):
             return self.model(x)
         taps = self.block_taps
         i, n = 0, len(self.model)
+        counters = []                 # num_batches_tracked of the BatchNorm layers of this pass: advanced together below
         while i < n:
-            x, i = self.run_block(i, x)
+            x, i = self.run_block(i, x, counters)
             if taps is not None:
                 taps[i - 1] = x.detach()
+        if counters:
+            with torch.no_grad():
+                torch._foreach_add_(counters, 1)
         return x
 
-    def run_block(self, i, x):
+    def run_block(self, i, x, counters=None):
         """one fused block of the training path starting at Sequential index i: conv -> BatchNorm(train) + LeakyReLU,
-        conv + LeakyReLU (epilogue), or a single module.  Returns (output, index of the next block)."""
+        conv + LeakyReLU (epilogue), or a single module.  Returns (output, index of the next block).  `counters`: list that
+        receives the BatchNorm layer's `num_batches_tracked` instead of it being advanced here."""
         mods = self.model
         m = mods[i]
         nxt = mods[i + 1] if i + 1 < len(mods) else None
         nxt2 = mods[i + 2] if i + 2 < len(mods) else None
         if isinstance(m, Conv2d) and isinstance(nxt, BatchNorm2d) and isinstance(nxt2, LeakyReLU):
-            return ops.bn_leaky_relu(m(x), nxt, nxt2.negative_slope), i + 3             # conv -> fused BN+LReLU
+            if counters is not None:
+                counters.append(nxt.num_batches_tracked)
+            return ops.bn_leaky_relu(m(x), nxt, nxt2.negative_slope, bump=counters is None), i + 3             # conv -> fused BN+LReLU
         if isinstance(m, Conv2d) and isinstance(nxt, LeakyReLU):
             return ops.conv2d_act(x, m.weight, m.bias, m.stride, m.padding, ACT_LRELU, nxt.negative_slope), i + 2   # conv + LReLU epilogue
         if (isinstance(m, ChannelAttention) and isinstance(nxt, SpatialAttention) and m.pool_mode == 'Avg|Max' and nxt.pool_mode == 'Avg|Max'

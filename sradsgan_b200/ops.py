@@ -659,11 +659,13 @@ class BatchNormLeakyReLU(Function):
         return dx, dgamma, dbeta, None, None, None, None, None
 
 
-def bn_leaky_relu(x, bn, slope):
-    """bn: sradsgan_b200.nn.BatchNorm2d in training mode"""
+def bn_leaky_relu(x, bn, slope, bump=True):
+    """bn: sradsgan_b200.nn.BatchNorm2d in training mode.  bump=False: the caller advances `num_batches_tracked` itself (the critic does it
+    for all its BatchNorm layers with ONE multi-tensor launch per pass instead of one tiny kernel per layer)"""
     y = BatchNormLeakyReLU.apply(to_compute(x), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, slope)
-    with torch.no_grad():
-        bn.num_batches_tracked += 1
+    if bump:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
     return y
 
 
